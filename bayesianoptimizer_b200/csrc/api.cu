@@ -1,0 +1,212 @@
+// C ABI (include/bo_b200.h) of the B200 GP surrogate + acquisition library.
+#include "gemm.cuh"
+#include <new>
+
+using namespace bo;
+
+namespace bo {
+int acq_grad_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
+                  const double* Xq_dev, int k, double* val_dev, double* grad_dev, cudaStream_t st);
+int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
+                const double* starts_dev, int k, int iters, double* x_dev, double* val_dev, cudaStream_t st);
+int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st);
+int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st);
+int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
+             const double* theta_host, int R, double* lml_host, double* grad_host, int* status_host,
+             cudaStream_t st);
+}
+
+extern "C" {
+
+int bo_abi_version(void) { return BO_ABI_VERSION; }
+
+int bo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bo_create(bo_handle** out, int device) {
+    if (!out) return BO_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return BO_E_CUDA; }
+    if (device < 0 || device >= ndev) return BO_E_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return BO_E_CUDA; }
+    if (prop.major != 10) return BO_E_CUDA;      // built for sm_100a only; no fallback
+    bo_handle* h = new (std::nothrow) bo_handle();
+    if (!h) return BO_E_NOMEM;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaMalloc(&h->info_dev, sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&h->info_host, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->out_stage_val, BO_MAX_TOPK * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->out_stage_idx, BO_MAX_TOPK * sizeof(int64_t)) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        gemm_init(h) != 0) {
+        cudaGetLastError();
+        bo_destroy(h);
+        return BO_E_CUDA;
+    }
+    *out = h;
+    return 0;
+}
+
+int bo_release_workspace(bo_handle* h) {
+    if (!h) return BO_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->panel) cudaFree(h->panel);
+    h->panel = nullptr; h->panel_bytes = 0;
+    if (h->cand_stage) cudaFree(h->cand_stage);
+    h->cand_stage = nullptr; h->cand_stage_bytes = 0;
+    return 0;
+}
+
+void bo_destroy(bo_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    bo_release_workspace(h);
+    void* ptrs[] = {h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2,
+                    h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
+                    h->out_stage_val, h->out_stage_idx};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->info_host) cudaFreeHost(h->info_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    cudaGetLastError();
+    delete h;
+}
+
+const char* bo_last_error(const bo_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int bo_num_obs(const bo_handle* h) { return (h && h->fitted) ? h->n : 0; }
+int64_t bo_launch_count(const bo_handle* h) { return h ? h->launches : 0; }
+
+int bo_fit(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d, int32_t kernel_kind,
+           const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
+           void* stream) {
+    if (!h) return BO_E_INVALID;
+    return fit_impl(h, X_dev, y_dev, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter,
+                    (cudaStream_t)stream);
+}
+
+int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_t n, int32_t d,
+                int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
+                double mean, double jitter, void* stream) {
+    if (!h) return BO_E_INVALID;
+    if (n < 1 || d < 1 || !X_host || !y_host) return fail(h, BO_E_INVALID, "bo_fit_host: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const size_t need = ((size_t)n * d + n) * sizeof(double);
+    if (need > h->cand_stage_bytes) {
+        if (h->cand_stage) cudaFree(h->cand_stage);
+        h->cand_stage = nullptr; h->cand_stage_bytes = 0;
+        BO_CUDA(h, cudaMalloc(&h->cand_stage, need));
+        h->cand_stage_bytes = need;
+    }
+    double* Xd = h->cand_stage; double* yd = Xd + (size_t)n * d;
+    BO_CUDA(h, cudaMemcpyAsync(Xd, X_host, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    BO_CUDA(h, cudaMemcpyAsync(yd, y_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    return fit_impl(h, Xd, yd, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, st);
+}
+
+int bo_get_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    if (!h->fitted) return fail(h, BO_E_NOTFIT, "bo_get_state before a successful bo_fit");
+    return export_state(h, alpha_dev, chol_dev, linv_dev, (cudaStream_t)stream);
+}
+
+int bo_posterior(bo_handle* h, const double* Xs_dev, int64_t N, double min_variance, double* mean_dev,
+                 double* var_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    if (!Xs_dev && N > 0) return fail(h, BO_E_INVALID, "bo_posterior: null candidates");
+    return sweep_impl(h, BO_ACQ_MEAN, 0.0, 0.0, min_variance, Xs_dev, nullptr, 0, N, 0, nullptr, nullptr,
+                      mean_dev, var_dev, nullptr, (cudaStream_t)stream);
+}
+
+int bo_sweep(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+             const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N, int32_t topk,
+             double* vals_dev, int64_t* idx_dev, double* mean_dev, double* var_dev, double* acq_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return sweep_impl(h, acq_kind, best_f, beta, min_variance, cand_dev, sobol_host, first_index, N, topk,
+                      vals_dev, idx_dev, mean_dev, var_dev, acq_dev, (cudaStream_t)stream);
+}
+
+int bo_sweep_host(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+                  const double* cand_host, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
+                  int32_t topk, double* vals_host, int64_t* idx_host, void* stream) {
+    if (!h) return BO_E_INVALID;
+    if (topk < 1 || topk > BO_MAX_TOPK || !vals_host || !idx_host) return fail(h, BO_E_INVALID, "bo_sweep_host: bad topk/outputs");
+    if (!h->fitted) return fail(h, BO_E_NOTFIT, "sweep before a successful bo_fit");
+    cudaStream_t st = (cudaStream_t)stream;
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const double* cand_dev = nullptr;
+    if (cand_host) {
+        const size_t need = (size_t)N * h->d * sizeof(double);
+        if (need > h->cand_stage_bytes) {
+            if (h->cand_stage) cudaFree(h->cand_stage);
+            h->cand_stage = nullptr; h->cand_stage_bytes = 0;
+            BO_CUDA(h, cudaMalloc(&h->cand_stage, need ? need : 8));
+            h->cand_stage_bytes = need ? need : 8;
+        }
+        if (need) BO_CUDA(h, cudaMemcpyAsync(h->cand_stage, cand_host, need, cudaMemcpyHostToDevice, st));
+        cand_dev = h->cand_stage;
+    }
+    int rc = sweep_impl(h, acq_kind, best_f, beta, min_variance, cand_dev, sobol_host, first_index, N, topk,
+                        h->out_stage_val, h->out_stage_idx, nullptr, nullptr, nullptr, st);
+    if (rc) return rc;
+    BO_CUDA(h, cudaMemcpyAsync(vals_host, h->out_stage_val, topk * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BO_CUDA(h, cudaMemcpyAsync(idx_host, h->out_stage_idx, topk * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int bo_sobol_points(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N, double* out_dev,
+                    void* stream) {
+    if (!h) return BO_E_INVALID;
+    return sobol_points_impl(h, sobol_host, idx_dev, N, out_dev, (cudaStream_t)stream);
+}
+
+int bo_refine(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+              const double* starts_dev, int32_t k, int32_t iters, double* x_dev, double* val_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return refine_impl(h, acq_kind, best_f, beta, min_variance, starts_dev, k, iters, x_dev, val_dev, (cudaStream_t)stream);
+}
+
+int bo_acq_grad(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+                const double* Xq_dev, int32_t k, double* val_dev, double* grad_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return acq_grad_impl(h, acq_kind, best_f, beta, min_variance, Xq_dev, k, val_dev, grad_dev, (cudaStream_t)stream);
+}
+
+int bo_append(bo_handle* h, const double* x_dev, double y, int32_t use_believer, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return append_impl(h, x_dev, y, use_believer, (cudaStream_t)stream);
+}
+
+int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d,
+                        int32_t kernel_kind, double mean, const double* theta_host, int32_t R, double* lml_host,
+                        double* grad_host, int32_t* status_host, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return lml_impl(h, X_dev, y_dev, n, d, kernel_kind, mean, theta_host, R, lml_host, grad_host, status_host,
+                    (cudaStream_t)stream);
+}
+
+int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_host) {
+    if (!h || !tflops_host) return BO_E_INVALID;
+    return fp64_peak_impl(h, use_dmma, seconds, tflops_host);
+}
+
+double bo_last_sweep_ms(bo_handle* h) {
+    if (!h || !h->sweep_timed) return -1.0;
+    cudaSetDevice(h->device);
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return (double)ms;
+}
+
+}  // extern "C"

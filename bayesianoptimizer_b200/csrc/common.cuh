@@ -1,0 +1,212 @@
+// Shared declarations for the B200 (sm_100a) GP surrogate + acquisition library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+
+#include "../../include/bo_b200.h"
+
+namespace bo {
+
+// ---- geometry of the packed operands (see DESIGN.md "Data layout in HBM") -----------------
+constexpr int NB        = 64;    // Cholesky / triangular-inverse leaf block size
+constexpr int PAD       = 128;   // n is padded to a multiple of PAD (identity on the padded diagonal)
+constexpr int SW_BM     = 128;   // sweep: rows of L^-1 per CTA tile
+constexpr int SW_BN     = 128;   // sweep: candidates per CTA tile
+constexpr int SW_BK     = 32;    // sweep: contraction (observation) chunk per pipeline stage
+constexpr int SW_TILE   = SW_BM * SW_BK;          // doubles per packed A (or B) stage tile = 4096 (32 KB)
+constexpr int SW_STAGES = 3;
+constexpr int SW_CONSUMER_WARPS = 8;
+constexpr int SW_THREADS = SW_CONSUMER_WARPS * 32;         // 2 warps per SM sub-partition: 255-register budget
+
+struct Hyper {
+    int    kind;
+    int    d;          // true input dimension
+    int    dp;         // padded dimension used by the templated kernels
+    double inv_ls[BO_MAX_DIM];
+    double outputscale;
+    double noise;
+    double mean;
+    double jitter;
+};
+
+// one problem of the grouped FP64 GEMM (gemm.cuh):  C = alpha * A * op(B) + beta * C, row-major
+struct GemmProblem {
+    const double* A; const double* B; double* C;
+    int M, N, K;
+    int lda, ldb, ldc;
+    double alpha, beta;
+    int transB;       // 0: B is [K][N] ; 1: B is [N][K]
+    int mode;         // GEMM_* structure flags
+    int tiles_n;      // N / BN
+    int tile_begin;   // first flattened tile of this problem
+    int tile_end;
+};
+struct GemmLaunch { int first, count, tiles, cfg; };   // cfg: 0 = 64x64 tiles, 1 = 128x128
+
+}  // namespace bo
+
+struct bo_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    // fitted state
+    bool fitted = false;
+    int n = 0, np = 0, d = 0, dp = 0;       // np = n padded to bo::PAD
+    int cap_np = 0, cap_d = 0;              // allocated capacity
+    bo::Hyper hyp{};
+    double* Xs = nullptr;        // [cap_np, BO_MAX_DIM] scaled inputs X / lengthscale (padded dims zero)
+    double* Xraw = nullptr;      // [cap_np, BO_MAX_DIM] unscaled copy (refit after append, lml)
+    double* yv = nullptr;        // [cap_np] targets
+    double* alpha = nullptr;     // [cap_np]
+    double* Lm = nullptr;        // [cap_np, cap_np] K then L (lower), row-major with ld = cap_np
+    double* Li = nullptr;        // [cap_np, cap_np] L^-1 (lower), row-major with ld = cap_np
+    double* Tw = nullptr;        // [cap_np * cap_np / 2] triangular-inverse workspace
+    double* Lp = nullptr;        // packed L^-1 tiles in DMMA fragment order (sweep A operand)
+    double* vec1 = nullptr;      // [cap_np] scratch vectors
+    double* vec2 = nullptr;
+    int*    info_dev = nullptr;  // pivot status
+    int*    info_host = nullptr; // pinned
+    // fit plan: every grouped-GEMM launch of the factorisation + inverse for the current np
+    std::vector<bo::GemmProblem> plan_probs;
+    std::vector<bo::GemmLaunch>  plan_launches;
+    bo::GemmProblem* plan_dev = nullptr;
+    size_t plan_dev_cap = 0;
+    int plan_np = -1;
+
+    // sweep workspaces
+    double* panel = nullptr;     // [grid, np/SW_BK, SW_TILE] K(X*,X) panels, one per resident CTA
+    size_t  panel_bytes = 0;
+    double* part_val = nullptr;  // [grid, BO_MAX_TOPK]
+    int64_t* part_idx = nullptr;
+    int     part_grid = 0;
+    bo_sobol* sobol_dev = nullptr;
+    double* cand_stage = nullptr; size_t cand_stage_bytes = 0;   // host-candidate staging
+    double* out_stage_val = nullptr; int64_t* out_stage_idx = nullptr;  // device top-k staging for *_host
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool sweep_timed = false;
+};
+
+namespace bo {
+
+#define BO_CUDA(h, call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            char buf__[512];                                                              \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,   \
+                     cudaGetErrorString(e__));                                            \
+            (h)->err = buf__;                                                             \
+            return (e__ == cudaErrorMemoryAllocation) ? BO_E_NOMEM : BO_E_CUDA;           \
+        }                                                                                 \
+    } while (0)
+
+#define BO_LAUNCH_CHECK(h)                                                                \
+    do {                                                                                  \
+        (h)->launches++;                                                                  \
+        BO_CUDA(h, cudaGetLastError());                                                   \
+    } while (0)
+
+inline int fail(bo_handle* h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// padded dimension served by the templated kernels
+inline int pad_dim(int d) {
+    if (d <= 2) return 2;
+    if (d <= 4) return 4;
+    if (d <= 6) return 6;
+    if (d <= 8) return 8;
+    if (d <= 12) return 12;
+    return 16;
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Matern-5/2 / RBF value from the scaled squared distance
+__device__ __forceinline__ double kernel_value(int kind, double sq, double outputscale) {
+    if (kind == BO_KERNEL_MATERN52) {
+        const double s5 = 2.23606797749978969640917366873128;
+        double r = sqrt(sq);
+        double p = fma(sq, 5.0 / 3.0, fma(s5, r, 1.0));
+        return outputscale * p * exp(-s5 * r);
+    }
+    return outputscale * exp(-0.5 * sq);
+}
+
+// better-than order of the top-k: value desc, index asc
+__device__ __forceinline__ bool tk_better(double va, long long ia, double vb, long long ib) {
+    return va > vb || (va == vb && ia < ib);
+}
+
+}  // namespace bo
+
+// internal cross-file API
+namespace bo {
+int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
+             const double* ls_host, double outputscale, double noise, double mean, double jitter,
+             cudaStream_t st);
+int ensure_capacity(bo_handle* h, int np, cudaStream_t st);
+int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
+               const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
+               int topk, double* vals_dev, int64_t* idx_dev, double* mean_dev, double* var_dev,
+               double* acq_dev, cudaStream_t st);
+int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,
+                      double* out_dev, cudaStream_t st);
+int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);
+int refit_factor(bo_handle* h, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv
+}  // namespace bo

@@ -1,0 +1,510 @@
+// GP fit on device: fused pairwise-distance + Matern-5/2/RBF Gram builder,
+// FP64 blocked right-looking Cholesky (DMMA SYRK/GEMM trailing updates), explicit L^-1 by
+// recursive block inversion, alpha with one step of iterative refinement, and the repack of
+// L^-1 into the sweep kernel's DMMA fragment order.
+// Replaces SingleTaskGP construction + prediction caches (optimization/Bayesian.py:89-94).
+#include "gemm.cuh"
+
+namespace bo {
+
+// ------------------------------------------------------------------------------------------
+// input staging: Xraw (unscaled, padded to BO_MAX_DIM columns), Xs = Xraw * inv_ls, y
+// ------------------------------------------------------------------------------------------
+__global__ void stage_inputs_kernel(const double* __restrict__ X, const double* __restrict__ y, int n, int d,
+                                    int np, Hyper hyp, double* __restrict__ Xraw, double* __restrict__ Xs,
+                                    double* __restrict__ yv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+#pragma unroll
+    for (int k = 0; k < BO_MAX_DIM; ++k) {
+        double v = (i < n && k < d) ? X[(size_t)i * d + k] : 0.0;
+        Xraw[(size_t)i * BO_MAX_DIM + k] = v;
+        Xs[(size_t)i * BO_MAX_DIM + k] = (k < d) ? v * hyp.inv_ls[k] : 0.0;
+    }
+    yv[i] = (i < n) ? y[i] : 0.0;
+}
+
+__global__ void rescale_inputs_kernel(int np, int d, Hyper hyp, const double* __restrict__ Xraw,
+                                      double* __restrict__ Xs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+#pragma unroll
+    for (int k = 0; k < BO_MAX_DIM; ++k)
+        Xs[(size_t)i * BO_MAX_DIM + k] = (k < d) ? Xraw[(size_t)i * BO_MAX_DIM + k] * hyp.inv_ls[k] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: Gram builder, lower triangle of K = k(X,X) + (noise + jitter) I, identity on the padding
+// ------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs, int n, int np, int ld,
+                                                   Hyper hyp, double* __restrict__ K) {
+    // block = 32 (cols) x 8 (rows) threads, tile 32 x 32
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int i0 = blockIdx.y * 32;
+    if (blockIdx.x > blockIdx.y) return;
+    double xj[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xj[k] = Xs[(size_t)j * BO_MAX_DIM + k];
+    const double diag = hyp.outputscale + hyp.noise + hyp.jitter;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + threadIdx.y + r * 8;
+        double v;
+        if (i >= n || j >= n) {
+            v = (i == j) ? 1.0 : 0.0;
+        } else if (i == j) {
+            v = diag;
+        } else {
+            double sq = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                double df = Xs[(size_t)i * BO_MAX_DIM + k] - xj[k];
+                sq = fma(df, df, sq);
+            }
+            v = kernel_value(hyp.kind, sq, hyp.outputscale);
+        }
+        if (j <= i) K[(size_t)i * ld + j] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 leaf: Cholesky of one NB x NB diagonal block in shared memory + its explicit inverse
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, int lda,
+                                                        double* __restrict__ Ainv, int ldi,
+                                                        int* __restrict__ info, int pivot_base) {
+    __shared__ double S[NB][NB + 1];
+    __shared__ double col[NB];
+    __shared__ double rdiag[NB];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 256) {
+        int i = e / NB, j = e % NB;
+        S[i][j] = (j <= i) ? A[(size_t)i * lda + j] : 0.0;
+    }
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int j = 0; j < NB; ++j) {
+        __syncthreads();
+        double dj = S[j][j];
+        if (!(dj > 0.0)) {                       // also catches NaN
+            if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+            dj = 1.0;
+        }
+        const double s = sqrt(dj);
+        const double inv = 1.0 / s;
+        if (tid < NB) {
+            const int i = tid;
+            double v = (i > j) ? S[i][j] * inv : (i == j ? s : 0.0);
+            col[i] = v;
+            if (i >= j) S[i][j] = v;
+        }
+        __syncthreads();
+        // rank-1 update of the trailing lower triangle
+        for (int i = j + 1 + ty; i < NB; i += 16) {
+            const double li = col[i];
+            for (int k = j + 1 + tx; k <= i; k += 16) S[i][k] = fma(-li, col[k], S[i][k]);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+        int i = e / NB, j = e % NB;
+        if (j <= i) A[(size_t)i * lda + j] = S[i][j];
+    }
+    if (tid < NB) rdiag[tid] = 1.0 / S[tid][tid];
+    __syncthreads();
+    // inverse by forward substitution: 4 threads per column c, thread q owns rows i with i % 4 == q
+    const int c = tid >> 2, q = tid & 3;
+    double x[NB / 4];
+#pragma unroll
+    for (int m = 0; m < NB / 4; ++m) x[m] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        double part = 0.0;
+#pragma unroll
+        for (int m = 0; m < NB / 4; ++m) {
+            if (4 * m + q < i) part = fma(S[i][4 * m + q], x[m], part);   // bound is warp-uniform up to q: static m
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        const double xi = ((i == c ? 1.0 : 0.0) - part) * rdiag[i];
+        if ((i & 3) == q) x[i >> 2] = xi;
+    }
+#pragma unroll
+    for (int m = 0; m < NB / 4; ++m) Ainv[(size_t)(4 * m + q) * ldi + c] = x[m];
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 vectors: triangular mat-vecs with the explicit inverse and the Gram mat-vec for refinement
+// ------------------------------------------------------------------------------------------
+__global__ void resid_init_kernel(const double* __restrict__ y, int n, int np, double mean, double* __restrict__ r) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) r[i] = (i < n) ? y[i] - mean : 0.0;
+}
+
+// z[i] = sum_{j<=i} Li[i][j] v[j]   (one warp per row)
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ Li, int ld, int np,
+                                                         const double* __restrict__ v, double* __restrict__ z) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= np) return;
+    const double* a = Li + (size_t)row * ld;
+    double s = 0.0;
+    for (int j = lane; j <= row; j += 32) s = fma(a[j], v[j], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) z[row] = s;
+}
+
+// out[j] (+)= sum_{i>=j} Li[i][j] z[i]   (block per 32 columns, 8 row lanes)
+__global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restrict__ Li, int ld, int np,
+                                                           const double* __restrict__ z, double* __restrict__ out,
+                                                           int accumulate) {
+    __shared__ double red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    for (int i = blockIdx.x * 32 + ty; i < np; i += 8)
+        if (i >= j) s = fma(Li[(size_t)i * ld + j], z[i], s);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][tx];
+        out[j] = accumulate ? out[j] + t : t;
+    }
+}
+
+// r2[i] = r[i] - sum_j Khat[i][j] a[j]   (one warp per row; K recomputed from the scaled inputs)
+template <int DP>
+__global__ void __launch_bounds__(256) gram_residual_kernel(const double* __restrict__ Xs, int n, int np, Hyper hyp,
+                                                            const double* __restrict__ a, const double* __restrict__ r,
+                                                            double* __restrict__ r2) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= np) return;
+    if (row >= n) { if (lane == 0) r2[row] = 0.0; return; }
+    double xi[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xi[k] = Xs[(size_t)row * BO_MAX_DIM + k];
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) {
+        double kv;
+        if (j == row) {
+            kv = hyp.outputscale + hyp.noise + hyp.jitter;
+        } else {
+            double sq = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                double df = xi[k] - Xs[(size_t)j * BO_MAX_DIM + k];
+                sq = fma(df, df, sq);
+            }
+            kv = kernel_value(hyp.kind, sq, hyp.outputscale);
+        }
+        s = fma(kv, a[j], s);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) r2[row] = r[row] - s;
+}
+
+// ------------------------------------------------------------------------------------------
+// repack L^-1 (row-major) into the sweep's A-operand stage tiles:
+//   tile (ib, kc), kc < (ib+1)*SW_BM/SW_BK, at index (ib*(ib+1)/2)*(SW_BM/SW_BK) + kc, SW_TILE doubles each;
+//   inside a tile the 8x8 sub-block (r8, k8) sits at (r8*(SW_BK/8) + k8)*64 and its element (r, k)
+//   at lane*2 + khalf with lane = (r%8)*4 + k%4, khalf = (k%8)/4  -> one LDS.128 per lane fetches the
+//   DMMA.8x8x4 A fragments of two consecutive k4 steps.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_linv_kernel(const double* __restrict__ Li, int ld, int np,
+                                                        double* __restrict__ Lp) {
+    constexpr int KCH = SW_BM / SW_BK;
+    const int ib = blockIdx.y;
+    const int kc = blockIdx.x;
+    if (kc >= (ib + 1) * KCH) return;
+    double* dst = Lp + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * SW_TILE;
+    const int row0 = ib * SW_BM, k0 = kc * SW_BK;
+    for (int e = threadIdx.x; e < SW_TILE; e += 256) {
+        const int r = e / SW_BK, k = e % SW_BK;          // coalesced 256 B reads along k
+        const double v = (k0 + k <= row0 + r) ? Li[(size_t)(row0 + r) * ld + k0 + k] : 0.0;
+        const int r8 = r >> 3, k8 = k >> 3;
+        const int lane = (r & 7) * 4 + (k & 3), khalf = (k & 7) >> 2;
+        dst[(r8 * (SW_BK / 8) + k8) * 64 + lane * 2 + khalf] = v;
+    }
+}
+
+// copy lower triangle (upper zero) of the leading n x n block to a dense n x n output
+__global__ void export_lower_kernel(const double* __restrict__ src, int ld, int n, double* __restrict__ dst) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    int i = (int)(e / n), j = (int)(e % n);
+    dst[e] = (j <= i) ? src[(size_t)i * ld + j] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// grouped GEMM launcher
+// ------------------------------------------------------------------------------------------
+int gemm_init(bo_handle* h) {
+    BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)GemmSmem<64, 64>::BYTES));
+    BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)GemmSmem<128, 128>::BYTES));
+    return 0;
+}
+
+int gemm_launch(bo_handle* h, const GemmLaunch& L, cudaStream_t st) {
+    if (L.tiles == 0) return 0;
+    if (L.cfg == 1)
+        dgemm_grouped_kernel<128, 128><<<L.tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(h->plan_dev + L.first, L.count);
+    else
+        dgemm_grouped_kernel<64, 64><<<L.tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(h->plan_dev + L.first, L.count);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+static void plan_push(bo_handle* h, const GemmBatch& b) {
+    GemmLaunch L{(int)h->plan_probs.size(), (int)b.probs.size(), b.tiles, b.bm == 128 ? 1 : 0};
+    h->plan_probs.insert(h->plan_probs.end(), b.probs.begin(), b.probs.end());
+    h->plan_launches.push_back(L);
+}
+
+// pick the tile: 128 when every dimension allows it and the launch still fills the GPU
+static int pick_tile(int sm, std::initializer_list<int> dims, long tiles128) {
+    for (int v : dims) if (v % 128) return 64;
+    return tiles128 >= sm ? 128 : 64;
+}
+
+// Build the launch plan of the factorisation (2 GEMM launches per block column) followed by the
+// recursive inverse (2 launches per level).  Layout of plan_launches:
+//   [2*kb]   TRSM of block column kb ; [2*kb+1] SYRK trailing update      (kb = 0 .. nb-2)
+//   then per inverse level (deepest first): T = C * Ainv ; Li[lower-left] = -Binv * T
+static int build_plan(bo_handle* h, cudaStream_t st) {
+    const int np = h->np, ld = h->cap_np, nb = np / NB;
+    h->plan_probs.clear();
+    h->plan_launches.clear();
+    for (int kb = 0; kb + 1 < nb; ++kb) {
+        const int r0 = (kb + 1) * NB, m = np - r0;
+        double* P = h->Lm + (size_t)r0 * ld + kb * NB;                 // panel below the diagonal block
+        const double* Dinv = h->Li + (size_t)kb * NB * ld + kb * NB;   // inverse of the diagonal block
+        GemmBatch trsm(64);     // in place: one CTA owns the full 64-wide row panel it overwrites
+        trsm.add(P, ld, Dinv, ld, P, ld, m, NB, NB, 1.0, 0.0, /*transB=*/1, GEMM_B_LOWER_NT);
+        plan_push(h, trsm);
+        double* C = h->Lm + (size_t)r0 * ld + r0;
+        long t128 = (long)(m / 128) * (m / 128 + 1) / 2;
+        GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
+        syrk.add(P, ld, P, ld, C, ld, m, m, NB, -1.0, 1.0, /*transB=*/1, GEMM_LOWER_C);
+        plan_push(h, syrk);
+    }
+    // recursive inverse: collect merge nodes by depth
+    struct Node { int lo, mid, hi, depth; };
+    std::vector<Node> nodes;
+    std::vector<Node> stack;
+    int maxdepth = 0;
+    if (nb > 1) stack.push_back({0, nb / 2, nb, 0});
+    while (!stack.empty()) {
+        Node nd = stack.back(); stack.pop_back();
+        nodes.push_back(nd);
+        if (nd.depth > maxdepth) maxdepth = nd.depth;
+        if (nd.mid - nd.lo > 1) stack.push_back({nd.lo, nd.lo + (nd.mid - nd.lo) / 2, nd.mid, nd.depth + 1});
+        if (nd.hi - nd.mid > 1) stack.push_back({nd.mid, nd.mid + (nd.hi - nd.mid) / 2, nd.hi, nd.depth + 1});
+    }
+    for (int depth = maxdepth; depth >= 0; --depth) {
+        bool all128 = true; long t128 = 0;
+        for (const Node& nd : nodes) if (nd.depth == depth) {
+            int p = (nd.mid - nd.lo) * NB, q = (nd.hi - nd.mid) * NB;
+            if (p % 128 || q % 128 || (nd.lo * NB) % 128) all128 = false;
+            t128 += (long)(p / 128) * (q / 128);
+        }
+        const int tile = (all128 && t128 >= h->sm_count) ? 128 : 64;
+        GemmBatch g1(tile), g2(tile);
+        size_t toff = 0;
+        for (const Node& nd : nodes) if (nd.depth == depth) {
+            const int lo = nd.lo * NB, mid = nd.mid * NB, p = (nd.mid - nd.lo) * NB, q = (nd.hi - nd.mid) * NB;
+            const double* Cblk = h->Lm + (size_t)mid * ld + lo;          // q x p
+            const double* Ainv = h->Li + (size_t)lo * ld + lo;           // p x p lower
+            const double* Binv = h->Li + (size_t)mid * ld + mid;         // q x q lower
+            double* T = h->Tw + toff;                                     // q x p, ld = p
+            double* Out = h->Li + (size_t)mid * ld + lo;
+            g1.add(Cblk, ld, Ainv, ld, T, p, q, p, p, 1.0, 0.0, 0, GEMM_B_LOWER_NN);
+            g2.add(Binv, ld, T, p, Out, ld, q, p, q, -1.0, 0.0, 0, GEMM_A_LOWER);
+            toff += (size_t)q * p;
+        }
+        plan_push(h, g1);
+        plan_push(h, g2);
+    }
+    const size_t bytes = h->plan_probs.size() * sizeof(GemmProblem);
+    if (bytes > h->plan_dev_cap) {
+        if (h->plan_dev) cudaFree(h->plan_dev);
+        h->plan_dev = nullptr; h->plan_dev_cap = 0;
+        BO_CUDA(h, cudaMalloc(&h->plan_dev, bytes + 4096));
+        h->plan_dev_cap = bytes + 4096;
+    }
+    if (bytes) BO_CUDA(h, cudaMemcpyAsync(h->plan_dev, h->plan_probs.data(), bytes, cudaMemcpyHostToDevice, st));
+    BO_CUDA(h, cudaStreamSynchronize(st));    // plan_probs is pageable host memory
+    h->plan_np = np;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// capacity management
+// ------------------------------------------------------------------------------------------
+static void free_fit(bo_handle* h) {
+    double** ptrs[] = {&h->Xs, &h->Xraw, &h->yv, &h->alpha, &h->Lm, &h->Li, &h->Tw, &h->Lp, &h->vec1, &h->vec2};
+    for (double** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    h->cap_np = 0;
+    h->plan_np = -1;
+}
+
+int ensure_capacity(bo_handle* h, int np, cudaStream_t st) {
+    if (np <= h->cap_np) return 0;
+    // grow geometrically past the first allocation so appends do not reallocate every time
+    int cap = h->cap_np ? round_up(np + np / 4, PAD) : np;
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    // keep the old state to preserve a fitted model across a growth (append path)
+    bo_handle old = *h;
+    h->Xs = h->Xraw = h->yv = h->alpha = h->Lm = h->Li = h->Tw = h->Lp = h->vec1 = h->vec2 = nullptr;
+    const size_t c = (size_t)cap;
+    const size_t packed = (c / SW_BM) * (c / SW_BM + 1) / 2 * (SW_BM / SW_BK) * SW_TILE;
+    struct { double** p; size_t elems; } reqs[] = {
+        {&h->Xs, c * BO_MAX_DIM}, {&h->Xraw, c * BO_MAX_DIM}, {&h->yv, c}, {&h->alpha, c},
+        {&h->Lm, c * c}, {&h->Li, c * c}, {&h->Tw, c * c / 4 + 64}, {&h->Lp, packed},
+        {&h->vec1, c}, {&h->vec2, c}};
+    for (auto& r : reqs) {
+        cudaError_t e = cudaMalloc(r.p, r.elems * sizeof(double));
+        if (e != cudaSuccess) {
+            for (auto& r2 : reqs) { if (*r2.p) cudaFree(*r2.p); *r2.p = nullptr; }
+            h->Xs = old.Xs; h->Xraw = old.Xraw; h->yv = old.yv; h->alpha = old.alpha; h->Lm = old.Lm;
+            h->Li = old.Li; h->Tw = old.Tw; h->Lp = old.Lp; h->vec1 = old.vec1; h->vec2 = old.vec2;
+            h->err = std::string("cudaMalloc failed growing capacity: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return BO_E_NOMEM;
+        }
+    }
+    h->cap_np = cap;
+    h->plan_np = -1;
+    if (old.cap_np > 0 && old.fitted) {
+        // carry the fitted state over (row pitch changes from old.cap_np to cap)
+        const size_t rows = old.np;
+        BO_CUDA(h, cudaMemcpyAsync(h->Xs, old.Xs, rows * BO_MAX_DIM * 8, cudaMemcpyDeviceToDevice, st));
+        BO_CUDA(h, cudaMemcpyAsync(h->Xraw, old.Xraw, rows * BO_MAX_DIM * 8, cudaMemcpyDeviceToDevice, st));
+        BO_CUDA(h, cudaMemcpyAsync(h->yv, old.yv, rows * 8, cudaMemcpyDeviceToDevice, st));
+        BO_CUDA(h, cudaMemcpyAsync(h->alpha, old.alpha, rows * 8, cudaMemcpyDeviceToDevice, st));
+        BO_CUDA(h, cudaMemcpy2DAsync(h->Lm, c * 8, old.Lm, (size_t)old.cap_np * 8, rows * 8, rows, cudaMemcpyDeviceToDevice, st));
+        BO_CUDA(h, cudaMemcpy2DAsync(h->Li, c * 8, old.Li, (size_t)old.cap_np * 8, rows * 8, rows, cudaMemcpyDeviceToDevice, st));
+        BO_CUDA(h, cudaStreamSynchronize(st));
+        // Lp (packed) does not depend on the pitch: tiles are indexed by (ib, kc) only
+        const size_t oldpacked = ((size_t)old.np / SW_BM) * (old.np / SW_BM + 1) / 2 * (SW_BM / SW_BK) * SW_TILE;
+        BO_CUDA(h, cudaMemcpy(h->Lp, old.Lp, oldpacked * 8, cudaMemcpyDeviceToDevice));
+    }
+    double* olds[] = {old.Xs, old.Xraw, old.yv, old.alpha, old.Lm, old.Li, old.Tw, old.Lp, old.vec1, old.vec2};
+    for (double* p : olds) if (p) cudaFree(p);
+    return 0;
+}
+
+template <int DP>
+static int launch_gram(bo_handle* h, cudaStream_t st) {
+    dim3 grid(h->np / 32, h->np / 32), block(32, 8);
+    gram_kernel<DP><<<grid, block, 0, st>>>(h->Xs, h->n, h->np, h->cap_np, h->hyp, h->Lm);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+template <int DP>
+static int launch_resid(bo_handle* h, const double* a, const double* r, double* r2, cudaStream_t st) {
+    gram_residual_kernel<DP><<<h->np / 8, 256, 0, st>>>(h->Xs, h->n, h->np, h->hyp, a, r, r2);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+#define BO_DISPATCH_DP(dp, fn, ...)                                   \
+    ((dp) == 2 ? fn<2>(__VA_ARGS__) : (dp) == 4 ? fn<4>(__VA_ARGS__) :  \
+     (dp) == 6 ? fn<6>(__VA_ARGS__) : (dp) == 8 ? fn<8>(__VA_ARGS__) :  \
+     (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
+
+// alpha = Khat^-1 r via the explicit inverse, plus one iterative-refinement step
+static int solve_alpha(bo_handle* h, cudaStream_t st) {
+    const int np = h->np, ld = h->cap_np;
+    resid_init_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->yv, h->n, np, h->hyp.mean, h->vec1);
+    BO_LAUNCH_CHECK(h);
+    trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->Li, ld, np, h->vec1, h->vec2);
+    BO_LAUNCH_CHECK(h);
+    trmv_lower_t_kernel<<<np / 32, 256, 0, st>>>(h->Li, ld, np, h->vec2, h->alpha, 0);
+    BO_LAUNCH_CHECK(h);
+    // refinement: r2 = r - Khat alpha ; alpha += Li^T (Li r2)
+    int rc = BO_DISPATCH_DP(h->dp, launch_resid, h, h->alpha, h->vec1, h->vec2, st);
+    if (rc) return rc;
+    trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->Li, ld, np, h->vec2, h->vec1);
+    BO_LAUNCH_CHECK(h);
+    trmv_lower_t_kernel<<<np / 32, 256, 0, st>>>(h->Li, ld, np, h->vec1, h->alpha, 1);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+int refit_factor(bo_handle* h, cudaStream_t st) {
+    const int np = h->np, ld = h->cap_np, nb = np / NB;
+    int rc;
+    if (h->plan_np != np && (rc = build_plan(h, st))) return rc;
+    BO_CUDA(h, cudaMemsetAsync(h->info_dev, 0, sizeof(int), st));
+    if ((rc = BO_DISPATCH_DP(h->dp, launch_gram, h, st))) return rc;
+    BO_CUDA(h, cudaMemset2DAsync(h->Li, (size_t)ld * 8, 0, (size_t)np * 8, np, st));
+    for (int kb = 0; kb < nb; ++kb) {
+        double* D = h->Lm + (size_t)kb * NB * ld + kb * NB;
+        double* Dinv = h->Li + (size_t)kb * NB * ld + kb * NB;
+        potf2_inv_kernel<<<1, 256, 0, st>>>(D, ld, Dinv, ld, h->info_dev, kb * NB);
+        BO_LAUNCH_CHECK(h);
+        if (kb + 1 < nb) {
+            if ((rc = gemm_launch(h, h->plan_launches[2 * kb], st))) return rc;
+            if ((rc = gemm_launch(h, h->plan_launches[2 * kb + 1], st))) return rc;
+        }
+    }
+    BO_CUDA(h, cudaMemcpyAsync(h->info_host, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    for (size_t li = 2 * (size_t)(nb - 1); li < h->plan_launches.size(); ++li)
+        if ((rc = gemm_launch(h, h->plan_launches[li], st))) return rc;
+    {
+        dim3 grid(np / SW_BK, np / SW_BM);
+        pack_linv_kernel<<<grid, 256, 0, st>>>(h->Li, ld, np, h->Lp);
+        BO_LAUNCH_CHECK(h);
+    }
+    if ((rc = solve_alpha(h, st))) return rc;
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    const int info = *h->info_host;
+    if (info != 0) {
+        h->fitted = false;
+        char buf[128];
+        snprintf(buf, sizeof buf, "matrix not positive definite at pivot %d", info);
+        h->err = buf;
+        return info > h->n ? h->n : info;
+    }
+    h->fitted = true;
+    return 0;
+}
+
+int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st) {
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const int n = h->n;
+    if (alpha_dev) BO_CUDA(h, cudaMemcpyAsync(alpha_dev, h->alpha, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    const unsigned blocks = (unsigned)(((size_t)n * n + 255) / 256);
+    if (chol_dev) { export_lower_kernel<<<blocks, 256, 0, st>>>(h->Lm, h->cap_np, n, chol_dev); BO_LAUNCH_CHECK(h); }
+    if (linv_dev) { export_lower_kernel<<<blocks, 256, 0, st>>>(h->Li, h->cap_np, n, linv_dev); BO_LAUNCH_CHECK(h); }
+    return 0;
+}
+
+int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
+             const double* ls_host, double outputscale, double noise, double mean, double jitter,
+             cudaStream_t st) {
+    if (n < 1 || d < 1 || !X_dev || !y_dev || !ls_host) return fail(h, BO_E_INVALID, "bo_fit: bad argument");
+    if (d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_fit: d exceeds BO_MAX_DIM");
+    if (kind != BO_KERNEL_MATERN52 && kind != BO_KERNEL_RBF) return fail(h, BO_E_INVALID, "bo_fit: unknown kernel kind");
+    if (!(outputscale > 0.0) || !(noise >= 0.0) || !(jitter >= 0.0)) return fail(h, BO_E_INVALID, "bo_fit: bad hyper-parameter");
+    for (int k = 0; k < d; ++k) if (!(ls_host[k] > 0.0)) return fail(h, BO_E_INVALID, "bo_fit: lengthscale must be positive");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    h->fitted = false;
+    const int np = round_up(n, PAD);
+    int rc = ensure_capacity(h, np, st);
+    if (rc) return rc;
+    h->n = n; h->np = np; h->d = d; h->dp = pad_dim(d);
+    Hyper& hy = h->hyp;
+    hy.kind = kind; hy.d = d; hy.dp = h->dp; hy.outputscale = outputscale; hy.noise = noise; hy.mean = mean; hy.jitter = jitter;
+    for (int k = 0; k < BO_MAX_DIM; ++k) hy.inv_ls[k] = k < d ? 1.0 / ls_host[k] : 0.0;
+    stage_inputs_kernel<<<(np + 127) / 128, 128, 0, st>>>(X_dev, y_dev, n, d, np, hy, h->Xraw, h->Xs, h->yv);
+    BO_LAUNCH_CHECK(h);
+    return refit_factor(h, st);
+}
+
+}  // namespace bo

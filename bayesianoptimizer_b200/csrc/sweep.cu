@@ -1,0 +1,590 @@
+// K4: fused acquisition sweep.
+//
+// One persistent CTA per SM.  Per block of SW_BN = 128 candidates a CTA
+//   phase A  generates the candidates (in-kernel scrambled Sobol or an explicit pool), builds the
+//            cross-covariance panel K(X, X*) in DMMA B-fragment order (its own L2/HBM-resident slot)
+//            and the posterior mean k*^T alpha on the way;
+//   phase B  contracts the packed lower-triangular L^-1 (A operand) with the panel on the FP64
+//            tensor path (DMMA.8x8x4), both operands streamed by TMA bulk copies (UBLKCP) into a
+//            3-stage shared-memory ring guarded by full/empty mbarriers (issued by one elected thread); each finished 128-row slab is squared and reduced per candidate in registers;
+//   epilogue var = max(s2 - ||L^-1 k*||^2, min_var), EI / LogEI / UCB with erfc/erfcx in registers,
+//            optional per-candidate outputs, CTA-local top-k by (value desc, index asc).
+// A single-block merge kernel reduces the per-CTA lists.  Replaces the chunked pool scan + CPU topk
+// of optimization/Bayesian7.py:664-682 and optimize_acqf's raw-sample scoring (Bayesian.py:105-112).
+#include "common.cuh"
+#include <cstdlib>
+
+namespace bo {
+
+constexpr long long IDX_EMPTY = 0x7fffffffffffffffLL;
+
+struct SweepArgs {
+    const double* Xs; const double* alpha; const double* Lp; double* panel;
+    const double* cand; const bo_sobol* sobol;
+    long long first_index, N, nblocks;
+    int n, np, d;
+    Hyper hyp;
+    int acq; double best_f, sqrt_beta, min_var;
+    int topk; double* part_val; long long* part_idx;
+    double* mean_out; double* var_out; double* acq_out;
+};
+
+// ---- analytic acquisition (botorch.acquisition.analytic semantics) ------
+__device__ __forceinline__ double log1mexp_d(double x) {
+    return (x > -0.69314718055994530942) ? log(-expm1(x)) : log1p(-exp(x));
+}
+
+__device__ double acq_value(int kind, double mu, double var, double best_f, double sqrt_beta) {
+    if (kind == BO_ACQ_VAR) return var;
+    if (kind == BO_ACQ_MEAN) return mu;
+    const double sigma = sqrt(var);
+    if (kind == BO_ACQ_UCB) return fma(sqrt_beta, sigma, mu);
+    const double u = (mu - best_f) / sigma;
+    const double inv_sqrt2 = 0.70710678118654752440, inv_sqrt_2pi = 0.39894228040143267794;
+    if (kind == BO_ACQ_EI) {
+        const double phi = inv_sqrt_2pi * exp(-0.5 * u * u);
+        const double Phi = 0.5 * erfc(-u * inv_sqrt2);
+        return sigma * fma(u, Phi, phi);
+    }
+    // LogEI
+    double lh;
+    if (u > -1.0) {
+        const double phi = inv_sqrt_2pi * exp(-0.5 * u * u);
+        const double Phi = 0.5 * erfc(-u * inv_sqrt2);
+        lh = log(fma(u, Phi, phi));
+    } else {
+        const double w = log(erfcx(-u * inv_sqrt2) * fabs(u)) + 0.22579135264472743236;   // + log(pi/2)/2
+        lh = -0.5 * u * u - 0.91893853320467274178 + log1mexp_d(w);                       // - log(2 pi)/2
+    }
+    return log(sigma) + lh;
+}
+
+// candidate coordinates (unscaled) of global index gi; point 0 reproduces torch's float32 first point
+template <int DP>
+__device__ __forceinline__ void sobol_point(const uint32_t* dirs /*[DP][30]*/, const uint32_t* shift, int d,
+                                            long long gi, double* x) {
+    const unsigned long long gray = (unsigned long long)gi ^ ((unsigned long long)gi >> 1);
+    uint32_t acc[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) acc[k] = shift[k];
+    for (int b = 0; b < BO_SOBOL_BITS; ++b) {
+        if ((gray >> b) & 1ULL) {
+#pragma unroll
+            for (int k = 0; k < DP; ++k) acc[k] ^= dirs[k * BO_SOBOL_BITS + b];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        double v = (gi == 0) ? (double)(float)acc[k] : (double)acc[k];
+        x[k] = (k < d) ? v * 9.31322574615478515625e-10 : 0.0;   // 2^-30
+    }
+}
+
+// ---- shared-memory carve-up ------------------------------------------------------------------
+struct SweepSmem {
+    static constexpr int STAGE_BYTES = 2 * SW_TILE * 8;                 // A tile + B tile
+    static constexpr int OFF_BAR   = SW_STAGES * STAGE_BYTES;           // full[S], empty[S]
+    static constexpr int OFF_COL   = OFF_BAR + 64;                      // colsum[2][SW_BN]
+    static constexpr int OFF_MU    = OFF_COL + 2 * SW_BN * 8;           // mu[SW_BN]
+    static constexpr int OFF_TKV   = OFF_MU + SW_BN * 8;                // tk_val[64]
+    static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;         // tk_idx[64]
+    static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;         // acq[SW_BN]
+    static constexpr int OFF_SOB   = OFF_ACQ + SW_BN * 8;               // dirs[16][30] + shift[16]
+    static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem + SweepSmem::OFF_BAR);
+    uint64_t* empty = full + SW_STAGES;
+    double* colsum  = reinterpret_cast<double*>(smem + SweepSmem::OFF_COL);
+    double* mu_s    = reinterpret_cast<double*>(smem + SweepSmem::OFF_MU);
+    double* tkv     = reinterpret_cast<double*>(smem + SweepSmem::OFF_TKV);
+    long long* tki  = reinterpret_cast<long long*>(smem + SweepSmem::OFF_TKI);
+    double* acq_s   = reinterpret_cast<double*>(smem + SweepSmem::OFF_ACQ);
+    uint32_t* dirs  = reinterpret_cast<uint32_t*>(smem + SweepSmem::OFF_SOB);
+    uint32_t* shift = dirs + BO_MAX_DIM * BO_SOBOL_BITS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int nbm = a.np / SW_BM;
+    constexpr int KCH = SW_BM / SW_BK;
+    double* panel = a.panel + (size_t)blockIdx.x * (a.np / SW_BK) * SW_TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < SW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SW_CONSUMER_WARPS); }
+        fence_mbar_init();
+    }
+    if (tid < BO_MAX_TOPK) { tkv[tid] = -INFINITY; tki[tid] = IDX_EMPTY; }
+    if (a.sobol) {
+        for (int e = tid; e < DP * BO_SOBOL_BITS; e += SW_THREADS)
+            dirs[e] = a.sobol->direction[e / BO_SOBOL_BITS][e % BO_SOBOL_BITS];
+        if (tid < DP) shift[tid] = a.sobol->shift[tid];
+    }
+    __syncthreads();
+
+    int stage = 0; uint32_t phase = 0;      // consumer ring position
+    int pstage = 0; uint32_t pphase = 0;    // producer ring position (thread 0 issues the TMA bulk copies)
+
+    for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+        // ================= phase A: candidates, K(X, X*) panel, posterior mean =================
+        {
+            double xc[2][DP];
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                long long li = blk * SW_BN + (warp + 8 * gi) * 8 + g;
+                if (li >= a.N) li = a.N - 1;
+                if (a.cand) {
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) xc[gi][k] = (k < a.d) ? a.cand[(size_t)li * a.d + k] : 0.0;
+                } else {
+                    sobol_point<DP>(dirs, shift, a.d, a.first_index + li, xc[gi]);
+                }
+#pragma unroll
+                for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
+            }
+            double mu0 = 0.0, mu1 = 0.0;
+            const int nj8 = a.np >> 3;
+#pragma unroll 2
+            for (int j8 = 0; j8 < nj8; ++j8) {
+                const int j0 = j8 * 8 + q, j1 = j0 + 4;
+                const double2* r0 = reinterpret_cast<const double2*>(a.Xs + (size_t)j0 * BO_MAX_DIM);
+                const double2* r1 = reinterpret_cast<const double2*>(a.Xs + (size_t)j1 * BO_MAX_DIM);
+                double x0[DP], x1[DP];
+#pragma unroll
+                for (int k = 0; k < DP / 2; ++k) {
+                    double2 t0 = __ldg(r0 + k), t1 = __ldg(r1 + k);
+                    x0[2 * k] = t0.x; x0[2 * k + 1] = t0.y; x1[2 * k] = t1.x; x1[2 * k + 1] = t1.y;
+                }
+                const double a0 = __ldg(a.alpha + j0), a1 = __ldg(a.alpha + j1);
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) {
+                        double d0 = xc[gi][k] - x0[k], d1 = xc[gi][k] - x1[k];
+                        s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
+                    }
+                    double2 kv;
+                    kv.x = (j0 < a.n) ? kernel_value(a.hyp.kind, s0, a.hyp.outputscale) : 0.0;
+                    kv.y = (j1 < a.n) ? kernel_value(a.hyp.kind, s1, a.hyp.outputscale) : 0.0;
+                    if (gi == 0) mu0 = fma(kv.x, a0, fma(kv.y, a1, mu0));
+                    else         mu1 = fma(kv.x, a0, fma(kv.y, a1, mu1));
+                    double* dst = panel + (size_t)(j8 >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (j8 & 3)) * 64 + lane * 2);
+                    *reinterpret_cast<double2*>(dst) = kv;
+                }
+            }
+            mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
+            mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
+            if (q == 0) { mu_s[warp * 8 + g] = mu0; mu_s[(warp + 8) * 8 + g] = mu1; }
+            __threadfence();
+            fence_proxy_async();      // generic-proxy panel writes -> visible to the async-proxy (TMA) reads
+        }
+        __syncthreads();
+
+        // ================= phase B: ||L^-1 k*||^2 on the DMMA path ============================
+        {
+            const long long T = (long long)nbm * (nbm + 1) / 2 * KCH;     // pipeline stages of this block
+            int pib = 0, pkc = 0;                                          // producer position (thread 0)
+            long long issued = 0;
+            auto issue = [&]() {
+                mbar_wait(&empty[pstage], pphase ^ 1);
+                unsigned char* sb = smem + pstage * SweepSmem::STAGE_BYTES;
+                const double* At = a.Lp + ((size_t)pib * (pib + 1) / 2 * KCH + pkc) * SW_TILE;
+                mbar_expect_tx(&full[pstage], SweepSmem::STAGE_BYTES);
+                bulk_g2s(sb, At, SW_TILE * 8, &full[pstage]);
+                bulk_g2s(sb + SW_TILE * 8, panel + (size_t)pkc * SW_TILE, SW_TILE * 8, &full[pstage]);
+                if (++pstage == SW_STAGES) { pstage = 0; pphase ^= 1; }
+                if (++pkc == (pib + 1) * KCH) { pkc = 0; ++pib; }
+                ++issued;
+            };
+            if (tid == 0)
+                while (issued < T && issued < SW_STAGES - 1) issue();
+
+            const int wm = warp >> 2, wn = warp & 3;
+            double colsq[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) colsq[e] = 0.0;
+            for (int ib = 0; ib < nbm; ++ib) {
+                double acc[8][4][2];
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                const int nkc = (ib + 1) * KCH;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    // refill the slot released one iteration ago (prefetch distance SW_STAGES - 1)
+                    if (tid == 0 && issued < T) issue();
+                    __syncwarp();
+                    mbar_wait(&full[stage], phase);
+                    const double* As = reinterpret_cast<const double*>(smem + stage * SweepSmem::STAGE_BYTES);
+                    const double* Bs = As + SW_TILE;
+#pragma unroll
+                    for (int k8 = 0; k8 < SW_BK / 8; ++k8) {
+                        double2 b[4];
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni)
+                            b[ni] = *reinterpret_cast<const double2*>(Bs + (((wn * 4 + ni) * (SW_BK / 8) + k8) * 64 + lane * 2));
+#pragma unroll
+                        for (int mi = 0; mi < 8; ++mi) {
+                            const double2 av = *reinterpret_cast<const double2*>(As + (((wm * 8 + mi) * (SW_BK / 8) + k8) * 64 + lane * 2));
+#pragma unroll
+                            for (int ni = 0; ni < 4; ++ni) {
+                                dmma884(acc[mi][ni][0], acc[mi][ni][1], av.x, b[ni].x);
+                                dmma884(acc[mi][ni][0], acc[mi][ni][1], av.y, b[ni].y);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+                }
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        colsq[ni * 2 + 0] = fma(acc[mi][ni][0], acc[mi][ni][0], colsq[ni * 2 + 0]);
+                        colsq[ni * 2 + 1] = fma(acc[mi][ni][1], acc[mi][ni][1], colsq[ni * 2 + 1]);
+                    }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                double v = colsq[e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (g == 0) colsum[wm * SW_BN + wn * 32 + (e >> 1) * 8 + 2 * q + (e & 1)] = v;
+            }
+        }
+        __syncthreads();
+
+        // ================= epilogue: variance, acquisition, CTA-local top-k =====================
+        if (tid < SW_BN) {
+            const long long li = blk * SW_BN + tid;
+            const double ss = colsum[tid] + colsum[SW_BN + tid];
+            const double var = fmax(a.hyp.outputscale - ss, a.min_var);
+            const double mean = a.hyp.mean + mu_s[tid];
+            double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
+            if (li < a.N) {
+                if (a.mean_out) a.mean_out[li] = mean;
+                if (a.var_out) a.var_out[li] = var;
+                if (a.acq_out) a.acq_out[li] = v;
+            }
+            if (!(v == v)) v = -INFINITY;                    // NaN ranks last
+            acq_s[tid] = (li < a.N) ? v : -INFINITY;
+        }
+        __syncthreads();
+        if (tid == 0 && a.topk > 0) {
+            const int K = a.topk;
+            for (int c = 0; c < SW_BN; ++c) {
+                const long long li = blk * SW_BN + c;
+                if (li >= a.N) break;
+                const double v = acq_s[c];
+                const long long gi = a.first_index + li;
+                if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
+                int p = K - 1;
+                while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
+                tkv[p] = v; tki[p] = gi;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < BO_MAX_TOPK && a.part_val) {
+        a.part_val[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tkv[tid];
+        a.part_idx[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tki[tid];
+    }
+}
+
+// ---- merge of the per-CTA top-k lists (k rounds of a block-wide arg-best) ------------------
+__global__ void __launch_bounds__(1024) topk_merge_kernel(double* __restrict__ pv, long long* __restrict__ pi,
+                                                          int total, int topk, double* __restrict__ vals,
+                                                          long long* __restrict__ idx) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    __shared__ int sp[32];
+    __shared__ int win;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int r = 0; r < topk; ++r) {
+        double bv = -INFINITY; long long bi = IDX_EMPTY; int bp = -1;
+        for (int e = tid; e < total; e += 1024) {
+            const long long ii = pi[e];
+            if (ii == IDX_EMPTY) continue;
+            const double v = pv[e];
+            if (bp < 0 || tk_better(v, ii, bv, bi)) { bv = v; bi = ii; bp = e; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (op >= 0 && (bp < 0 || tk_better(ov, oi, bv, bi))) { bv = ov; bi = oi; bp = op; }
+        }
+        if (lane == 0) { sv[warp] = bv; si[warp] = bi; sp[warp] = bp; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = sv[lane]; bi = si[lane]; bp = sp[lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                int op = __shfl_xor_sync(0xffffffffu, bp, o);
+                if (op >= 0 && (bp < 0 || tk_better(ov, oi, bv, bi))) { bv = ov; bi = oi; bp = op; }
+            }
+            if (lane == 0) {
+                vals[r] = (bp >= 0) ? bv : -INFINITY;
+                idx[r] = (bp >= 0) ? bi : -1;
+                win = bp;
+                if (bp >= 0) pi[bp] = IDX_EMPTY;
+            }
+        }
+        __syncthreads();
+        (void)win;
+    }
+}
+
+// ---- independent slow path (triage / tests): plain loads, row-major L^-1, no TMA, no DMMA ----
+template <int DP>
+__global__ void __launch_bounds__(256) sweep_reference_kernel(const SweepArgs a, const double* __restrict__ Li, int ld) {
+    extern __shared__ double ks[];           // k*[np]
+    __shared__ double red[8];
+    __shared__ double xs_c[DP];
+    const long long li = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        double x[DP];
+        if (a.cand) { for (int k = 0; k < DP; ++k) x[k] = (k < a.d) ? a.cand[(size_t)li * a.d + k] : 0.0; }
+        else {
+            const uint32_t* dirs = &a.sobol->direction[0][0];      // straight from global memory
+            const unsigned long long gi = (unsigned long long)(a.first_index + li);
+            const unsigned long long gray = gi ^ (gi >> 1);
+            for (int k = 0; k < DP; ++k) {
+                uint32_t acc = a.sobol->shift[k];
+                for (int b = 0; b < BO_SOBOL_BITS; ++b) if ((gray >> b) & 1ULL) acc ^= dirs[k * BO_SOBOL_BITS + b];
+                double v = (gi == 0) ? (double)(float)acc : (double)acc;
+                x[k] = (k < a.d) ? v * 9.31322574615478515625e-10 : 0.0;
+            }
+        }
+        for (int k = 0; k < DP; ++k) xs_c[k] = x[k] * a.hyp.inv_ls[k];
+    }
+    __syncthreads();
+    double mu = 0.0;
+    for (int j = tid; j < a.np; j += 256) {
+        double v = 0.0;
+        if (j < a.n) {
+            double sq = 0.0;
+            for (int k = 0; k < DP; ++k) { double df = xs_c[k] - a.Xs[(size_t)j * BO_MAX_DIM + k]; sq = fma(df, df, sq); }
+            v = kernel_value(a.hyp.kind, sq, a.hyp.outputscale);
+            mu = fma(v, a.alpha[j], mu);
+        }
+        ks[j] = v;
+    }
+    __syncthreads();
+    double ss = 0.0;
+    for (int i = warp; i < a.n; i += 8) {
+        const double* row = Li + (size_t)i * ld;
+        double s = 0.0;
+        for (int j = lane; j <= i; j += 32) s = fma(row[j], ks[j], s);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss = fma(s, s, ss);        // identical in every lane
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    double sst = 0.0;
+    for (int w = 0; w < 8; ++w) sst += red[w];
+    __syncthreads();
+    if (lane == 0) red[warp] = mu;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int w = 0; w < 8; ++w) m += red[w];
+        const double var = fmax(a.hyp.outputscale - sst, a.min_var);
+        const double mean = a.hyp.mean + m;
+        a.mean_out[li] = mean;
+        a.var_out[li] = var;
+        a.acq_out[li] = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
+    }
+}
+
+// scan of a dense score array into per-block top-k lists (reference path only)
+__global__ void __launch_bounds__(256) score_topk_kernel(const double* __restrict__ acq, long long N, long long first_index,
+                                                         int topk, double* __restrict__ pv, long long* __restrict__ pi) {
+    __shared__ double tkv[BO_MAX_TOPK];
+    __shared__ long long tki[BO_MAX_TOPK];
+    if (threadIdx.x < BO_MAX_TOPK) { tkv[threadIdx.x] = -INFINITY; tki[threadIdx.x] = IDX_EMPTY; }
+    __syncthreads();
+    if (threadIdx.x == 0 && topk > 0) {
+        for (long long li = blockIdx.x; li < N; li += gridDim.x) {
+            double v = acq[li]; if (!(v == v)) v = -INFINITY;
+            const long long gi = first_index + li;
+            if (!tk_better(v, gi, tkv[topk - 1], tki[topk - 1])) continue;
+            int p = topk - 1;
+            while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
+            tkv[p] = v; tki[p] = gi;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < BO_MAX_TOPK) {
+        pv[(size_t)blockIdx.x * BO_MAX_TOPK + threadIdx.x] = tkv[threadIdx.x];
+        pi[(size_t)blockIdx.x * BO_MAX_TOPK + threadIdx.x] = tki[threadIdx.x];
+    }
+}
+
+template <int DP>
+__global__ void sobol_points_kernel(const bo_sobol* __restrict__ sob, const long long* __restrict__ idx, long long N, int d,
+                                    double* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double x[DP];
+    sobol_point<DP>(&sob->direction[0][0], sob->shift, d, idx[i], x);
+    for (int k = 0; k < d; ++k) out[i * d + k] = x[k];
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static int ensure_sweep_ws(bo_handle* h, int grid) {
+    const size_t need = (size_t)grid * (h->np / SW_BK) * SW_TILE * sizeof(double);
+    if (need > h->panel_bytes) {
+        if (h->panel) cudaFree(h->panel);
+        h->panel = nullptr; h->panel_bytes = 0;
+        BO_CUDA(h, cudaMalloc(&h->panel, need));
+        h->panel_bytes = need;
+    }
+    if (grid > h->part_grid) {
+        if (h->part_val) cudaFree(h->part_val);
+        if (h->part_idx) cudaFree(h->part_idx);
+        h->part_val = nullptr; h->part_idx = nullptr; h->part_grid = 0;
+        BO_CUDA(h, cudaMalloc(&h->part_val, (size_t)grid * BO_MAX_TOPK * sizeof(double)));
+        BO_CUDA(h, cudaMalloc(&h->part_idx, (size_t)grid * BO_MAX_TOPK * sizeof(int64_t)));
+        h->part_grid = grid;
+    }
+    return 0;
+}
+
+template <int DP>
+static int launch_sweep(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
+        attr_set = true;
+    }
+    sweep_kernel<DP><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+template <int DP>
+static int launch_sweep_ref(bo_handle* h, const SweepArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t sm = (size_t)a.np * sizeof(double);
+    if (!attr_set) {
+        BO_CUDA(h, cudaFuncSetAttribute(sweep_reference_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    sweep_reference_kernel<DP><<<(unsigned)a.N, 256, sm, st>>>(a, h->Li, h->cap_np);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+template <int DP>
+static int launch_sobol_points(bo_handle* h, const int64_t* idx, int64_t N, double* out, cudaStream_t st) {
+    sobol_points_kernel<DP><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->sobol_dev, (const long long*)idx, N, h->d, out);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+#define BO_DISPATCH_DP(dp, fn, ...)                                   \
+    ((dp) == 2 ? fn<2>(__VA_ARGS__) : (dp) == 4 ? fn<4>(__VA_ARGS__) :  \
+     (dp) == 6 ? fn<6>(__VA_ARGS__) : (dp) == 8 ? fn<8>(__VA_ARGS__) :  \
+     (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
+
+static int upload_sobol(bo_handle* h, const bo_sobol* sobol_host, cudaStream_t st) {
+    if (sobol_host->d < h->d) return fail(h, BO_E_INVALID, "sobol state has fewer dimensions than the fitted model");
+    if (!h->sobol_dev) BO_CUDA(h, cudaMalloc(&h->sobol_dev, sizeof(bo_sobol)));
+    BO_CUDA(h, cudaMemcpyAsync(h->sobol_dev, sobol_host, sizeof(bo_sobol), cudaMemcpyHostToDevice, st));
+    BO_CUDA(h, cudaStreamSynchronize(st));     // caller's struct is pageable and borrowed for the call only
+    return 0;
+}
+
+int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
+               const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
+               int topk, double* vals_dev, int64_t* idx_dev, double* mean_dev, double* var_dev,
+               double* acq_dev, cudaStream_t st) {
+    if (!h->fitted) return fail(h, BO_E_NOTFIT, "sweep before a successful bo_fit");
+    if (N < 0 || first_index < 0 || topk < 0) return fail(h, BO_E_INVALID, "bo_sweep: negative size");
+    if (topk > BO_MAX_TOPK) return fail(h, BO_E_CAPACITY, "bo_sweep: topk exceeds BO_MAX_TOPK");
+    if (acq_kind < BO_ACQ_EI || acq_kind > BO_ACQ_MEAN) return fail(h, BO_E_INVALID, "bo_sweep: unknown acquisition kind");
+    if (!cand_dev && !sobol_host) return fail(h, BO_E_INVALID, "bo_sweep: neither candidates nor a Sobol state given");
+    if (topk > 0 && (!vals_dev || !idx_dev)) return fail(h, BO_E_INVALID, "bo_sweep: topk outputs missing");
+    if (!(beta >= 0.0)) return fail(h, BO_E_INVALID, "bo_sweep: beta must be >= 0");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if (!cand_dev && (rc = upload_sobol(h, sobol_host, st))) return rc;
+
+    SweepArgs a{};
+    a.Xs = h->Xs; a.alpha = h->alpha; a.Lp = h->Lp;
+    a.cand = cand_dev; a.sobol = cand_dev ? nullptr : h->sobol_dev;
+    a.first_index = first_index; a.N = N; a.nblocks = (N + SW_BN - 1) / SW_BN;
+    a.n = h->n; a.np = h->np; a.d = h->d; a.hyp = h->hyp;
+    a.acq = acq_kind; a.best_f = best_f; a.sqrt_beta = sqrt(beta); a.min_var = min_var;
+    a.topk = topk; a.mean_out = mean_dev; a.var_out = var_dev; a.acq_out = acq_dev;
+
+    if (N == 0) {
+        if (topk > 0) {
+            if ((rc = ensure_sweep_ws(h, 1))) return rc;
+            score_topk_kernel<<<1, 256, 0, st>>>(nullptr, 0, first_index, topk, h->part_val, (long long*)h->part_idx);
+            BO_LAUNCH_CHECK(h);
+            topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, BO_MAX_TOPK, topk, vals_dev, (long long*)idx_dev);
+            BO_LAUNCH_CHECK(h);
+        }
+        return 0;
+    }
+
+    const char* impl = getenv("BO_B200_SWEEP_IMPL");
+    if (impl && strcmp(impl, "reference") == 0) {
+        // slow independent path: needs dense outputs; borrow temporaries if the caller passed none
+        double *tm = nullptr, *tv = nullptr, *ta = nullptr;
+        if (!a.mean_out) { BO_CUDA(h, cudaMalloc(&tm, N * 8)); a.mean_out = tm; }
+        if (!a.var_out)  { BO_CUDA(h, cudaMalloc(&tv, N * 8)); a.var_out = tv; }
+        if (!a.acq_out)  { BO_CUDA(h, cudaMalloc(&ta, N * 8)); a.acq_out = ta; }
+        const int grid = (int)(N < 64 ? N : 64);
+        if ((rc = ensure_sweep_ws(h, grid))) return rc;
+        if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep_ref, h, a, st))) return rc;
+        if (topk > 0) {
+            score_topk_kernel<<<grid, 256, 0, st>>>(a.acq_out, N, first_index, topk, h->part_val, (long long*)h->part_idx);
+            BO_LAUNCH_CHECK(h);
+            topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, topk, vals_dev, (long long*)idx_dev);
+            BO_LAUNCH_CHECK(h);
+        }
+        BO_CUDA(h, cudaStreamSynchronize(st));
+        if (tm) cudaFree(tm); if (tv) cudaFree(tv); if (ta) cudaFree(ta);
+        return 0;
+    }
+
+    const int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
+    if ((rc = ensure_sweep_ws(h, grid))) return rc;
+    a.panel = h->panel; a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
+    BO_CUDA(h, cudaEventRecord(h->ev0, st));
+    if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep, h, a, grid, st))) return rc;
+    BO_CUDA(h, cudaEventRecord(h->ev1, st));
+    h->sweep_timed = true;
+    if (topk > 0) {
+        topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, topk, vals_dev, (long long*)idx_dev);
+        BO_LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,
+                      double* out_dev, cudaStream_t st) {
+    if (!sobol_host || !idx_dev || !out_dev || N < 0) return fail(h, BO_E_INVALID, "bo_sobol_points: bad argument");
+    if (h->d <= 0) return fail(h, BO_E_NOTFIT, "bo_sobol_points: dimension unknown before bo_fit");
+    if (N == 0) return 0;
+    BO_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload_sobol(h, sobol_host, st))) return rc;
+    return BO_DISPATCH_DP(pad_dim(h->d), launch_sobol_points, h, idx_dev, N, out_dev, st);
+}
+
+}  // namespace bo

@@ -1,0 +1,177 @@
+/*
+ * bo_b200.h -- C ABI of the B200-native GP surrogate + acquisition hot path.
+ *
+ * Drop-in boundary for billbearhunter/BayesianOptimizer's surrogate/acquisition seam.  The
+ * reference has no FFI of its own: the path sits behind Python calls into botorch/gpytorch
+ * (SURVEY.md section 8b).  Each entry point below names the reference call site it replaces.
+ * The Python host (bayesianoptimizer_b200/engine.py) binds these with ctypes and passes
+ * `tensor.data_ptr()` of contiguous float64 CUDA tensors plus the current CUDA stream.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the ABI; every call returns a status.
+ *   - status 0 = ok; status k > 0 (bo_fit, bo_append only) = matrix not positive definite at
+ *     1-based pivot k (the caller retries with a larger jitter, as optimization/Bayesian6.py:482-488
+ *     does); status < 0 = one of the BO_E_* codes, text via bo_last_error().
+ *   - "_dev" pointers are device pointers on the handle's device, borrowed for the call only;
+ *     "_host" pointers are host pointers.  All matrices are row-major float64.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - the handle owns all device workspaces (L, packed L^-1, alpha, scaled X, sweep panels) and
+ *     frees them in bo_destroy(); bo_release_workspace() drops the sweep scratch early so that a
+ *     co-resident simulator (simulation/taichi.py:10) gets its HBM back.
+ *   - there is no CPU fallback: every compute entry point fails with BO_E_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef BO_B200_H
+#define BO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define BO_ABI_VERSION 1
+
+/* kernel kinds: gpytorch MaternKernel(nu=2.5, ard) (optimization/Bayesian6.py:471-473,
+ * optimization/Bayesian7.py:162-166) and RBFKernel(ard) (botorch>=0.12 SingleTaskGP default,
+ * optimization/Bayesian.py:91), both under an (optional) ScaleKernel outputscale. */
+#define BO_KERNEL_MATERN52 0
+#define BO_KERNEL_RBF      1
+
+/* acquisition kinds (analytic closed forms; maximisation as in optimization/Bayesian.py:98) */
+#define BO_ACQ_EI    0   /* expected improvement                                  (Bayesian.py:100-101) */
+#define BO_ACQ_LOGEI 1   /* log expected improvement, erfcx tails                 (Bayesian.py:9,101)   */
+#define BO_ACQ_UCB   2   /* mean + sqrt(beta) * sigma                                                   */
+#define BO_ACQ_VAR   3   /* posterior variance score (active-learning sweep,      Bayesian7.py:670-671) */
+#define BO_ACQ_MEAN  4   /* posterior mean                                                              */
+
+/* error codes (negative statuses) */
+#define BO_E_INVALID  (-1)  /* bad argument                                  */
+#define BO_E_CUDA     (-2)  /* CUDA runtime error / no usable device         */
+#define BO_E_NOMEM    (-3)  /* device allocation failed                      */
+#define BO_E_NOTFIT   (-4)  /* posterior/sweep/refine/append before bo_fit   */
+#define BO_E_CAPACITY (-5)  /* n or d or topk beyond the compiled limits     */
+
+#define BO_MAX_DIM   16     /* input dimension limit (reference: d = 5)      */
+#define BO_MAX_TOPK  64     /* in-kernel top-k limit                         */
+#define BO_SOBOL_BITS 30    /* torch.quasirandom.SobolEngine.MAXBIT          */
+
+typedef struct bo_handle bo_handle;
+
+/* Scrambled-Sobol generator state: direction numbers and digital shift of a fresh
+ * torch.quasirandom.SobolEngine(d, scramble=True, seed) (`.sobolstate`, `.shift`).  Candidate i of
+ * the pool is generated inside the sweep kernel from its GLOBAL index, bit-identical to row i of
+ * SobolEngine.draw(dtype=float64); no candidate bytes cross HBM.  Replaces the host-side pool
+ * construction of optimization/Bayesian7.py:650-655 and optimize_acqf's raw samples
+ * (optimization/Bayesian.py:105-112). */
+typedef struct bo_sobol {
+    int32_t  d;
+    uint32_t direction[BO_MAX_DIM][BO_SOBOL_BITS];
+    uint32_t shift[BO_MAX_DIM];
+} bo_sobol;
+
+/* library / device ------------------------------------------------------------------------- */
+int         bo_abi_version(void);
+int         bo_device_count(void);
+int         bo_create(bo_handle** out, int device);
+void        bo_destroy(bo_handle* h);
+const char* bo_last_error(const bo_handle* h);
+int         bo_release_workspace(bo_handle* h);
+
+/* GP fit: K = k(X,X) + (noise + jitter) I, L = chol(K), alpha = K^-1 (y - mean), explicit L^-1.
+ * Replaces SingleTaskGP(train_X, train_Y) + the prediction caches built inside model.posterior
+ * (optimization/Bayesian.py:89-94; SURVEY.md 3.3: mean_cache -> alpha, covar_cache -> L^-1).
+ * X_dev[n,d], y_dev[n]; lengthscale_host[d].  Synchronises the stream (the pivot status is read back). */
+int bo_fit(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d,
+           int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
+           double mean, double jitter, void* stream);
+
+/* Same with HOST X/y (copies inside) -- the entry the end-to-end benchmark times. */
+int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_t n, int32_t d,
+                int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
+                double mean, double jitter, void* stream);
+
+/* introspection of the fitted state (device outputs; any may be NULL):
+ *   alpha_dev[n], chol_dev[n,n] (lower triangle, upper zero), linv_dev[n,n] (lower, upper zero) */
+int bo_get_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, void* stream);
+int bo_num_obs(const bo_handle* h);
+
+/* Posterior mean / variance at Xs_dev[N,d]: mean = m + k*^T alpha ; var = max(s2 - ||L^-1 k*||^2,
+ * min_variance).  Replaces model.posterior(X).mean/.variance
+ * (optimization/Bayesian2.py:168-171, optimization/Bayesian6.py:615-617, Bayesian7.py:666-671). */
+int bo_posterior(bo_handle* h, const double* Xs_dev, int64_t N, double min_variance,
+                 double* mean_dev, double* var_dev, void* stream);
+
+/* Acquisition sweep over candidates [first_index, first_index + N) of a pool:
+ *   cand_dev != NULL : explicit pool, cand_dev[N,d] holds exactly this shard's rows;
+ *   cand_dev == NULL : in-kernel scrambled Sobol from `sobol_host` keyed by the global index.
+ * Fused on device: K(X*,X) panel -> mean -> variance (FP64 DMMA contraction with packed L^-1) ->
+ * EI/LogEI/UCB -> top-k by (value desc, global index asc).  Outputs (device): vals_dev[topk],
+ * idx_dev[topk] (entries beyond N are -inf / -1); optional per-candidate mean_dev/var_dev/acq_dev[N].
+ * Replaces the chunked pool scan + CPU topk of optimization/Bayesian7.py:664-682 and the
+ * raw-sample scoring inside optimize_acqf (optimization/Bayesian.py:105-112). */
+int bo_sweep(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+             const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
+             int32_t topk, double* vals_dev, int64_t* idx_dev,
+             double* mean_dev, double* var_dev, double* acq_dev, void* stream);
+
+/* Same with HOST outputs vals_host[topk], idx_host[topk] (and host candidates when cand_host != NULL);
+ * synchronises.  The end-to-end entry: host buffers in, host buffers out. */
+int bo_sweep_host(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+                  const double* cand_host, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
+                  int32_t topk, double* vals_host, int64_t* idx_host, void* stream);
+
+/* Materialise pool points [first_index, first_index+N) of the Sobol stream into out_dev[N,d]
+ * (used to turn winning indices back into coordinates; Bayesian7.py:682 `cand_unit_cpu[idxs_big]`). */
+int bo_sobol_points(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,
+                    double* out_dev, void* stream);
+
+/* Batched projected-gradient-ascent refinement of k starts inside [0,1]^d with analytic gradients
+ * of the acquisition; replaces gen_candidates_scipy (L-BFGS-B, autograd) inside optimize_acqf
+ * (optimization/Bayesian.py:105-112).  starts_dev[k,d] -> x_dev[k,d], val_dev[k]. */
+int bo_refine(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+              const double* starts_dev, int32_t k, int32_t iters, double* x_dev, double* val_dev,
+              void* stream);
+
+/* Acquisition value and gradient at Xq_dev[k,d] (building block of bo_refine; the autograd
+ * backward of acq(X) in the reference). val_dev[k], grad_dev[k,d]. */
+int bo_acq_grad(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,
+                const double* Xq_dev, int32_t k, double* val_dev, double* grad_dev, void* stream);
+
+/* Kriging-believer / observation append: border L and L^-1 with one row.
+ * use_believer != 0 appends y = mu(x) (alpha' = [alpha; 0]); otherwise appends the observed y.
+ * Replaces the refit that the torch.cat register step triggers (optimization/Bayesian.py:143-148)
+ * and the greedy set_X_pending loop (optimization/Bayesian6.py:908-919). x_dev[d]. */
+int bo_append(bo_handle* h, const double* x_dev, double y, int32_t use_believer, void* stream);
+
+/* Batched exact log marginal likelihood and gradient over R hyper-parameter restarts on the
+ * fitted X/y.  theta_host[R, d+2] = log lengthscale[d], log outputscale, log noise.
+ * lml_host[R]; grad_host[R, d+2] (w.r.t. the log parameters); status_host[R] (0 or pivot).
+ * Replaces the ExactMarginalLogLikelihood closure fit_gpytorch_mll evaluates
+ * (optimization/Bayesian.py:92-93, optimization/Bayesian6.py:480-488). */
+int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d,
+                        int32_t kernel_kind, double mean, const double* theta_host, int32_t R,
+                        double* lml_host, double* grad_host, int32_t* status_host, void* stream);
+
+/* FP64 peak probe (DMMA.8x8x4 register-resident loop): the roofline denominator that
+ * MEASURED_PEAKS.json lacks.  Returns TFLOP/s in *tflops_host. */
+int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_host);
+
+/* Kernel-launch counter (own kernels launched through this handle since creation). */
+int64_t bo_launch_count(const bo_handle* h);
+
+/* Device time of the last bo_sweep's fused kernel in milliseconds (CUDA events on the sweep's
+ * stream; synchronises on the stop event). Negative if no sweep has run. */
+double bo_last_sweep_ms(bo_handle* h);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BO_B200_H */

@@ -1,0 +1,220 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the committed
+golden fixtures.  Tolerances are BASELINE.json:north_star's: mean/variance 1e-8 rel, acquisition 1e-6 rel,
+identical arg-max / top-k unless the gap is below tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_acq_close, assert_posterior_close, load_golden, synth_problem
+from oracle import gp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from bayesianoptimizer_b200 import GPEngine
+    assert torch.cuda.is_available(), "the gpu tier needs a B200"
+    eng = GPEngine(torch.device("cuda", 0))
+    yield eng
+    eng.close()
+
+
+def _kname(kind):
+    return "matern52" if int(kind) == o.KERNEL_MATERN52 else "rbf"
+
+
+def _fit_golden(engine, g):
+    engine.fit(torch.from_numpy(g["X"]).cuda(), torch.from_numpy(g["y"]).cuda(), _kname(g["kind"]),
+               g["lengthscale"], float(g["outputscale"]), float(g["noise"]))
+
+
+def test_fit_state_against_golden(engine, golden):
+    g = golden
+    _fit_golden(engine, g)
+    alpha, L, Li = (t.cpu().numpy() for t in engine.state())
+    # Cholesky factor: backward-stable, compare the diagonal tightly and L L^T against K
+    np.testing.assert_allclose(np.diag(L), g["chol_diag"], rtol=1e-9)
+    n = g["X"].shape[0]
+    K = o.kernel_matrix(g["X"], g["X"], int(g["kind"]), g["lengthscale"], float(g["outputscale"]))
+    K[np.diag_indices(n)] = float(g["outputscale"]) + float(g["noise"])
+    assert np.abs(L @ L.T - K).max() <= 1e-12 * np.abs(K).max() * n
+    assert np.abs(Li @ L - np.eye(n)).max() <= 1e-9
+    assert np.all(np.triu(L, 1) == 0) and np.all(np.triu(Li, 1) == 0)
+    # alpha: forward error scales with cond(K); the mean it produces is what the 1e-8 gate is on
+    scale = np.abs(g["alpha"]).max()
+    assert np.abs(alpha - g["alpha"]).max() <= 1e-7 * scale
+
+
+def test_posterior_and_acquisition_against_golden(engine, golden):
+    g = golden
+    _fit_golden(engine, g)
+    cand = torch.from_numpy(g["cand"]).cuda()
+    mu, var = engine.posterior(cand)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), g["mu"], g["var"])
+    bf = float(g["best_f"])
+    for kind, key in (("ei", "ei"), ("logei", "logei"), ("ucb", "ucb")):
+        vals, idx, m2, v2, av = engine.sweep(kind, bf, 2.0, candidates=cand, topk=8, return_all=True)
+        assert_acq_close(kind, av.cpu().numpy(), g[key])
+        tv, ti = o.topk(g[key], 8)
+        if kind == "logei":
+            assert idx.cpu().tolist() == g["topk_idx"].tolist()
+        # identical winners unless the oracle's own gap is below tolerance
+        got = idx.cpu().numpy()
+        for r in range(8):
+            if got[r] != ti[r]:
+                assert abs(g[key][got[r]] - tv[r]) <= 1e-6 * max(abs(tv[r]), 1e-300) + (1e-6 if kind == "logei" else 0)
+        np.testing.assert_allclose(vals.cpu().numpy(), av.cpu().numpy()[got], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("n,d,N,kind", [(512, 5, 4133, o.KERNEL_MATERN52), (1000, 8, 2048, o.KERNEL_MATERN52),
+                                        (129, 3, 777, o.KERNEL_RBF), (1, 2, 130, o.KERNEL_MATERN52),
+                                        (300, 16, 515, o.KERNEL_RBF), (2048, 10, 640, o.KERNEL_MATERN52)])
+def test_sobol_sweep_against_oracle(engine, n, d, N, kind):
+    """In-kernel scrambled-Sobol pool (ragged N, n not a multiple of the tile) vs the oracle on the same points."""
+    from bayesianoptimizer_b200 import sobol_state
+    X, y = synth_problem(n, d, 1, 2)
+    ls = np.linspace(0.5, 0.9, d)
+    gp = o.fit(X, y, kind, ls, 1.2, 1e-3, mean=0.1)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), _kname(kind), ls, 1.2, 1e-3, mean=0.1)
+    seed, first = 3, 1000
+    eng = torch.quasirandom.SobolEngine(d, scramble=True, seed=seed)
+    pts = o.sobol_points(eng.sobolstate.numpy(), eng.shift.numpy(), first, N)
+    st = sobol_state(d, seed)
+    bf = float(y.max())
+    for acq, ak in (("ei", o.ACQ_EI), ("logei", o.ACQ_LOGEI), ("ucb", o.ACQ_UCB), ("var", o.ACQ_VAR)):
+        tv, ti, mu, var, av = o.sweep(gp, pts, ak, bf, 2.0, k=16, first_index=first)
+        vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, sobol=st, first_index=first, count=N, topk=16, return_all=True)
+        assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
+        assert_acq_close(acq, ga.cpu().numpy(), av)
+        got = idx.cpu().numpy()
+        k = min(16, N)
+        for r in range(k):
+            if got[r] != ti[r]:
+                tol = 1e-6 * max(abs(tv[r]), 1e-300) + (1e-6 if acq == "logei" else 0)
+                assert abs(av[got[r] - first] - tv[r]) <= tol
+    # the generated points themselves are bit-identical to torch's SobolEngine rows
+    got_pts = engine.sobol_points(st, torch.arange(first, first + N)).cpu().numpy()
+    assert np.array_equal(got_pts, pts)
+    if first == 1000:
+        p0 = engine.sobol_points(st, torch.tensor([0, 1, 2])).cpu().numpy()
+        ref0 = torch.quasirandom.SobolEngine(d, scramble=True, seed=seed).draw(3, dtype=torch.float64).numpy()
+        assert np.array_equal(p0, ref0)
+
+
+def test_fused_path_equals_independent_reference_path(engine):
+    """TMA + DMMA fused kernel vs the plain-load, row-major-L^-1 kernel: two independent GPU formulations."""
+    g = load_golden("csv_n512_matern")
+    _fit_golden(engine, g)
+    cand = torch.from_numpy(g["cand"]).cuda()
+    v1, i1, m1, s1, a1 = engine.sweep("ei", float(g["best_f"]), candidates=cand, topk=8, return_all=True)
+    os.environ["BO_B200_SWEEP_IMPL"] = "reference"
+    try:
+        v2, i2, m2, s2, a2 = engine.sweep("ei", float(g["best_f"]), candidates=cand, topk=8, return_all=True)
+    finally:
+        del os.environ["BO_B200_SWEEP_IMPL"]
+    assert_posterior_close(m1.cpu().numpy(), s1.cpu().numpy(), m2.cpu().numpy(), s2.cpu().numpy())
+    assert i1.cpu().tolist() == i2.cpu().tolist()
+
+
+def test_topk_ties_resolve_to_lowest_index(engine):
+    X, y = synth_problem(200, 4, 5, 6)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", 0.6, 1.0, 1e-3)
+    base = np.random.default_rng(0).random((40, 4))
+    cand = np.tile(base, (8, 1))            # every candidate appears 8 times -> exact ties
+    vals, idx, _, _, av = engine.sweep("ucb", 0.0, 2.0, candidates=torch.from_numpy(cand).cuda(), topk=12, return_all=True)
+    av = av.cpu().numpy()
+    tv, ti = o.topk(av, 12)
+    assert idx.cpu().tolist() == ti.tolist()
+    assert np.array_equal(vals.cpu().numpy(), tv)
+    assert idx[0].item() < 40                 # the first copy wins
+
+
+def test_edge_sizes(engine):
+    X, y = synth_problem(64, 2, 7, 8)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "rbf", 0.4, 1.0, 1e-2)
+    gp = o.fit(X, y, o.KERNEL_RBF, 0.4, 1.0, 1e-2)
+    # empty pool
+    vals, idx = engine.sweep("ei", 0.0, candidates=torch.empty(0, 2, dtype=torch.float64).cuda(), topk=4)
+    assert idx.cpu().tolist() == [-1] * 4 and np.all(np.isneginf(vals.cpu().numpy()))
+    # single candidate, topk larger than the pool
+    c = np.array([[0.25, 0.75]])
+    vals, idx, m, v, a = engine.sweep("ei", 0.0, candidates=torch.from_numpy(c).cuda(), topk=3, return_all=True)
+    mu, var = o.posterior(gp, c)
+    assert_posterior_close(m.cpu().numpy(), v.cpu().numpy(), mu, var)
+    assert idx.cpu().tolist() == [0, -1, -1]
+    # a candidate exactly on a training point: variance stays >= the clamp and finite
+    m, v = engine.posterior(torch.from_numpy(X[:5]).cuda())
+    mu, var = o.posterior(gp, X[:5])
+    assert_posterior_close(m.cpu().numpy(), v.cpu().numpy(), mu, var)
+    # host-buffer entry gives the same answer as the device entry
+    pool = np.random.default_rng(1).random((1000, 2))
+    hv, hi = engine.sweep_host("logei", 0.2, candidates=pool, topk=5)
+    dv, di = engine.sweep("logei", 0.2, candidates=torch.from_numpy(pool).cuda(), topk=5)
+    assert hi.tolist() == di.cpu().tolist() and np.array_equal(hv.numpy(), dv.cpu().numpy())
+    # host fit entry
+    engine.fit(torch.from_numpy(X), torch.from_numpy(y), "rbf", 0.4, 1.0, 1e-2)
+    hv2, hi2 = engine.sweep_host("logei", 0.2, candidates=pool, topk=5)
+    assert hi2.tolist() == hi.tolist() and np.array_equal(hv2.numpy(), hv.numpy())
+
+
+def test_not_positive_definite_status_and_jitter_retry(engine):
+    """Duplicate CSV rows with zero noise: bo_fit returns the pivot status; jitter 1e-2 rescues it
+    (optimization/Bayesian6.py:482-488)."""
+    from bayesianoptimizer_b200 import NotPositiveDefiniteError
+    g = load_golden("csv_n3000_matern")
+    X, y = torch.from_numpy(g["X"][:400]).cuda(), torch.from_numpy(g["y"][:400]).cuda()
+    with pytest.raises(NotPositiveDefiniteError) as ei:
+        engine.fit(X, y, "rbf", 2.0, 1.0, 0.0)
+    assert 1 <= ei.value.pivot <= 400
+    from bayesianoptimizer_b200 import BoError
+    with pytest.raises(BoError):
+        engine.posterior(X[:4])                      # a failed fit leaves no usable model
+    engine.fit(X, y, "rbf", 2.0, 1.0, 0.0, jitter=1e-2)
+    gp = o.fit(g["X"][:400], g["y"][:400], o.KERNEL_RBF, 2.0, 1.0, 0.0, jitter=1e-2)
+    m, v = engine.posterior(torch.from_numpy(g["cand"]).cuda())
+    mu, var = o.posterior(gp, g["cand"])
+    assert_posterior_close(m.cpu().numpy(), v.cpu().numpy(), mu, var)
+
+
+def test_shard_merge_equals_single_sweep(engine):
+    """Candidate sharding invariant: merging per-shard top-k lists reproduces the G=1 result."""
+    from bayesianoptimizer_b200 import sobol_state
+    X, y = synth_problem(384, 6, 21, 22)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", 0.7, 1.0, 1e-3)
+    st = sobol_state(6, 17)
+    N, k = 50_000, 8
+    v1, i1 = engine.sweep("ei", float(y.max()), sobol=st, first_index=0, count=N, topk=k)
+    for G in (2, 3, 8):
+        per = -(-N // G)
+        vs, is_ = [], []
+        for r in range(G):
+            lo = r * per
+            cnt = max(0, min(per, N - lo))
+            v, i = engine.sweep("ei", float(y.max()), sobol=st, first_index=lo, count=cnt, topk=k)
+            vs.append(v.cpu().numpy()); is_.append(i.cpu().numpy())
+        mv, mi = o.merge_topk(vs, is_, k)
+        assert mi.tolist() == i1.cpu().tolist()
+        assert np.array_equal(mv, v1.cpu().numpy())
+
+
+def test_full_size_c3_sample_against_oracle(engine):
+    """BASELINE config 3 shape (n_obs=4096, d=8): fit + a 512-candidate prefix of the Sobol stream vs the oracle."""
+    from bayesianoptimizer_b200 import sobol_state
+    n, d, N = 4096, 8, 512
+    X, y = synth_problem(n, d, 4, 5)
+    gp = o.fit(X, y, o.KERNEL_MATERN52, 0.7, 1.0, 1e-3)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", 0.7, 1.0, 1e-3)
+    eng = torch.quasirandom.SobolEngine(d, scramble=True, seed=6)
+    pts = o.sobol_points(eng.sobolstate.numpy(), eng.shift.numpy(), 0, N)
+    st = sobol_state(d, 6)
+    bf = float(y.max())
+    for acq, ak in (("ei", o.ACQ_EI), ("ucb", o.ACQ_UCB)):
+        tv, ti, mu, var, av = o.sweep(gp, pts, ak, bf, 2.0, k=4)
+        vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, sobol=st, count=N, topk=4, return_all=True)
+        assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
+        assert_acq_close(acq, ga.cpu().numpy(), av)
+        assert idx.cpu().tolist() == ti.tolist()

@@ -1,0 +1,158 @@
+"""CPU tier: the oracle against the golden fixtures and against independently written implementations
+(scikit-learn GPR, scipy.stats.norm, finite differences, torch's SobolEngine)."""
+import numpy as np
+import pytest
+import scipy.stats as sst
+
+from conftest import assert_acq_close, assert_posterior_close, load_golden, synth_problem
+from oracle import gp_oracle as o
+
+
+def test_oracle_reproduces_golden(golden):
+    g = golden
+    gp = o.fit(g["X"], g["y"], int(g["kind"]), g["lengthscale"], float(g["outputscale"]), float(g["noise"]))
+    np.testing.assert_allclose(gp.alpha, g["alpha"], rtol=1e-9, atol=1e-9 * np.abs(g["alpha"]).max())
+    np.testing.assert_allclose(np.diag(gp.L), g["chol_diag"], rtol=1e-11)
+    mu, var = o.posterior(gp, g["cand"])
+    assert_posterior_close(mu, var, g["mu"], g["var"])
+    bf = float(g["best_f"])
+    assert_acq_close("ei", o.acquisition(mu, var, o.ACQ_EI, bf), g["ei"])
+    assert_acq_close("logei", o.acquisition(mu, var, o.ACQ_LOGEI, bf), g["logei"])
+    assert_acq_close("ucb", o.acquisition(mu, var, o.ACQ_UCB, bf, 2.0), g["ucb"])
+    tv, ti = o.topk(o.acquisition(mu, var, o.ACQ_LOGEI, bf), 8)
+    assert ti.tolist() == g["topk_idx"].tolist()
+    lml, grad = o.lml_and_grad(g["X"], g["y"], int(g["kind"]), g["lengthscale"], float(g["outputscale"]), float(g["noise"]))
+    assert abs(lml - float(g["lml"])) <= 1e-9 * abs(float(g["lml"]))
+    np.testing.assert_allclose(grad, g["lml_grad"], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["csv_n64_matern", "csv_n512_matern"])
+def test_oracle_matches_sklearn_gpr(name):
+    """Independent exact-GP implementation (direct-difference distances, cho_solve, solve_triangular)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern
+    g = load_golden(name)
+    kern = ConstantKernel(float(g["outputscale"])) * Matern(g["lengthscale"], nu=2.5)
+    gpr = GaussianProcessRegressor(kernel=kern, alpha=float(g["noise"]), optimizer=None).fit(g["X"], g["y"])
+    m, s = gpr.predict(g["cand"], return_std=True)
+    far = g["var"] > 1e-2          # sklearn loses digits in std**2 near the data; compare where it is well conditioned
+    np.testing.assert_allclose(g["mu"], m, rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(g["var"][far], (s ** 2)[far], rtol=1e-7)
+    assert abs(gpr.log_marginal_likelihood_value_ - float(g["lml"])) <= 1e-8 * abs(float(g["lml"]))
+
+
+def test_rbf_matches_sklearn_gpr():
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF
+    g = load_golden("csv_n512_rbf")
+    gpr = GaussianProcessRegressor(kernel=RBF(g["lengthscale"]), alpha=float(g["noise"]), optimizer=None).fit(g["X"], g["y"])
+    m = gpr.predict(g["cand"])
+    np.testing.assert_allclose(g["mu"], m, rtol=1e-6, atol=1e-7)
+
+
+def test_ei_ucb_closed_forms_against_scipy():
+    rng = np.random.default_rng(0)
+    mu = rng.standard_normal(2000)
+    var = rng.random(2000) * 2 + 1e-6
+    sig = np.sqrt(var)
+    bf = 0.3
+    u = (mu - bf) / sig
+    ei_ref = sig * (sst.norm.pdf(u) + u * sst.norm.cdf(u))
+    ei = o.acquisition(mu, var, o.ACQ_EI, bf)
+    ok = ei_ref > 1e-12
+    np.testing.assert_allclose(ei[ok], ei_ref[ok], rtol=1e-9)
+    np.testing.assert_allclose(o.acquisition(mu, var, o.ACQ_UCB, bf, 4.0), mu + 2.0 * sig, rtol=1e-14)
+    # LogEI agrees with log(EI) where EI is representable, and stays finite far in the tail
+    le = o.acquisition(mu, var, o.ACQ_LOGEI, bf)
+    np.testing.assert_allclose(le[ok], np.log(ei_ref[ok]), rtol=1e-8, atol=1e-8)
+    tail = o.acquisition(np.array([-40.0, -300.0]), np.array([1.0, 1.0]), o.ACQ_LOGEI, 0.0)
+    assert np.all(np.isfinite(tail)) and tail[1] < tail[0] < -700
+    # asymptote: log h(u) ~ -u^2/2 - log(sqrt(2 pi)) - 2 log|u|
+    assert abs(tail[1] - (-0.5 * 300.0 ** 2 - 0.5 * np.log(2 * np.pi) - 2 * np.log(300.0))) < 1e-3
+
+
+def test_lml_gradient_against_finite_differences():
+    X, y = synth_problem(120, 4, 11, 12)
+    for kind in (o.KERNEL_MATERN52, o.KERNEL_RBF):
+        theta = np.log(np.array([0.5, 0.4, 0.6, 0.8, 1.3, 1e-2]))
+
+        def f(t):
+            return o.lml_and_grad(X, y, kind, np.exp(t[:4]), np.exp(t[4]), np.exp(t[5]))[0]
+
+        _, grad = o.lml_and_grad(X, y, kind, np.exp(theta[:4]), np.exp(theta[4]), np.exp(theta[5]))
+        fd = np.array([(f(theta + 1e-6 * e) - f(theta - 1e-6 * e)) / 2e-6 for e in np.eye(6)])
+        np.testing.assert_allclose(grad, fd, rtol=2e-6, atol=1e-6)
+
+
+def test_acquisition_gradient_against_finite_differences():
+    X, y = synth_problem(150, 5, 1, 2)
+    rng = np.random.default_rng(5)
+    for kind in (o.KERNEL_MATERN52, o.KERNEL_RBF):
+        gp = o.fit(X, y, kind, [0.5, 0.4, 0.6, 0.8, 0.7], 1.3, 1e-3)
+        x0 = rng.random(5)
+        for ak in (o.ACQ_EI, o.ACQ_LOGEI, o.ACQ_UCB, o.ACQ_VAR, o.ACQ_MEAN):
+            _, gd = o.acquisition_with_grad(gp, x0, ak, 1.0, 2.0)
+            fd = np.array([(o.acquisition_with_grad(gp, x0 + 1e-6 * e, ak, 1.0, 2.0)[0]
+                            - o.acquisition_with_grad(gp, x0 - 1e-6 * e, ak, 1.0, 2.0)[0]) / 2e-6 for e in np.eye(5)])
+            np.testing.assert_allclose(gd, fd, rtol=2e-5, atol=1e-9)
+
+
+def test_row_append_identities():
+    """believer append keeps alpha' = [alpha; 0] and the mean, and shrinks the variance."""
+    X, y = synth_problem(100, 3, 3, 4)
+    gp = o.fit(X, y, o.KERNEL_MATERN52, 0.6, 1.0, 1e-3)
+    xs = np.random.default_rng(9).random((50, 3))
+    mu0, var0 = o.posterior(gp, xs, min_variance=0.0)
+    xnew = np.array([0.31, 0.62, 0.17])
+    gp2 = o.append_point(gp, xnew)
+    np.testing.assert_allclose(gp2.alpha[:-1], gp.alpha, rtol=1e-6, atol=1e-8)
+    assert abs(gp2.alpha[-1]) < 1e-8
+    mu1, var1 = o.posterior(gp2, xs, min_variance=0.0)
+    np.testing.assert_allclose(mu1, mu0, rtol=1e-8, atol=1e-9)
+    assert np.all(var1 <= var0 + 1e-12)
+    # an observed append equals a refit on the extended data
+    gp3 = o.append_point(gp, xnew, 0.5)
+    ref = o.fit(np.vstack([X, xnew]), np.concatenate([y, [0.5]]), o.KERNEL_MATERN52, 0.6, 1.0, 1e-3)
+    np.testing.assert_allclose(gp3.alpha, ref.alpha, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(gp3.L, ref.L, rtol=1e-9, atol=1e-12)
+
+
+def test_not_positive_definite_and_jitter_retry():
+    """Exact duplicate rows + zero noise -> Cholesky failure with a pivot; jitter 1e-2 rescues it
+    (the convention of optimization/Bayesian6.py:482-488)."""
+    g = load_golden("csv_n3000_matern")
+    X, y = g["X"][:400], g["y"][:400]
+    with pytest.raises(o.NotPositiveDefinite) as ei:
+        o.fit(X, y, o.KERNEL_RBF, 2.0, 1.0, 0.0)
+    assert 1 <= ei.value.pivot <= 400
+    o.fit(X, y, o.KERNEL_RBF, 2.0, 1.0, 0.0, jitter=1e-2)
+
+
+def test_topk_order_ties_and_nan():
+    v = np.array([1.0, 3.0, np.nan, 3.0, 2.0, 3.0])
+    tv, ti = o.topk(v, 4, first_index=100)
+    assert ti.tolist() == [101, 103, 105, 104]
+    assert tv.tolist() == [3.0, 3.0, 3.0, 2.0]
+    mv, mi = o.merge_topk([tv[:2], np.array([3.0, 0.5])], [ti[:2], np.array([7, 9])], 3)
+    assert mi.tolist() == [7, 101, 103]
+
+
+def test_sobol_restatement_matches_torch():
+    import torch
+    for d, seed in ((8, 6), (5, 3), (16, 1)):
+        eng = torch.quasirandom.SobolEngine(d, scramble=True, seed=seed)
+        st, sh = eng.sobolstate.numpy().copy(), eng.shift.numpy().copy()
+        ref = eng.draw(3000, dtype=torch.float64).numpy()
+        assert np.array_equal(o.sobol_points(st, sh, 0, 3000), ref)
+        assert np.array_equal(o.sobol_points(st, sh, 1234, 100), ref[1234:1334])
+
+
+def test_transforms():
+    b = np.array([(0.3, 1.0), (0.001, 300.0)]).T
+    X = np.array([[0.3, 300.0], [0.65, 150.0005]])
+    U = o.normalize(X, b)
+    np.testing.assert_allclose(U, [[0.0, 1.0], [0.5, 0.5]], atol=1e-12)
+    np.testing.assert_allclose(o.unnormalize(U, b), X, rtol=1e-14)
+    ys, m, s = o.standardize(np.array([1.0, 2.0, 3.0, 4.0]))
+    assert abs(m - 2.5) < 1e-15 and abs(s - np.std([1, 2, 3, 4], ddof=1)) < 1e-15
+    assert abs(ys.mean()) < 1e-15
