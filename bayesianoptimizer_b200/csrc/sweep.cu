@@ -515,12 +515,12 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     if (N < 0 || first_index < 0 || topk < 0) return fail(h, BO_E_INVALID, "bo_sweep: negative size");
     if (topk > BO_MAX_TOPK) return fail(h, BO_E_CAPACITY, "bo_sweep: topk exceeds BO_MAX_TOPK");
     if (acq_kind < BO_ACQ_EI || acq_kind > BO_ACQ_MEAN) return fail(h, BO_E_INVALID, "bo_sweep: unknown acquisition kind");
-    if (!cand_dev && !sobol_host) return fail(h, BO_E_INVALID, "bo_sweep: neither candidates nor a Sobol state given");
+    if (!cand_dev && !sobol_host && N > 0) return fail(h, BO_E_INVALID, "bo_sweep: neither candidates nor a Sobol state given");
     if (topk > 0 && (!vals_dev || !idx_dev)) return fail(h, BO_E_INVALID, "bo_sweep: topk outputs missing");
     if (!(beta >= 0.0)) return fail(h, BO_E_INVALID, "bo_sweep: beta must be >= 0");
     BO_CUDA(h, cudaSetDevice(h->device));
     int rc;
-    if (!cand_dev && (rc = upload_sobol(h, sobol_host, st))) return rc;
+    if (!cand_dev && N > 0 && (rc = upload_sobol(h, sobol_host, st))) return rc;
 
     SweepArgs a{};
     a.Xs = h->Xs; a.alpha = h->alpha; a.Lp = h->Lp;

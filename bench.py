@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the GP surrogate + acquisition hot path (contract: see the task's bench.py section).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic d=8, n_obs=4096,
+Matern-5/2 ARD, 10^7 EI candidates from a scrambled-Sobol pool generated in-kernel, sharded contiguously by
+global index over the N GPUs of one box (strong scaling: the pool is fixed at 10^7).  One step = one pass
+of the sweep over the whole pool + the single (value, index) exchange; `value` is timed with the fitted
+model resident in HBM, `e2e` goes through the host-buffer C-ABI entries (bo_fit_host + bo_sweep_host:
+X/y copied host->device and refit every step, winner copied device->host).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N > 1 is launched by torchrun (one rank per GPU, NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_OBS, DIM, POOL = 4096, 8, 10_000_000
+LENGTHSCALE, OUTPUTSCALE, NOISE = 0.7, 1.0, 1e-3
+SEED_X, SEED_Y, SEED_POOL = 4, 5, 6
+TOPK = 1
+METRIC = "EI candidates scored/s (n_obs=4096,d=8)"
+UNIT = "candidates/s"
+
+
+def flops_per_candidate(n, d):
+    """Algorithmic FP64 work per candidate: n^2 triangular contraction + n(3d+12) kernel row."""
+    return n * n + n * (3 * d + 12.0)
+
+
+def synth_problem():
+    X = np.random.default_rng(SEED_X).random((N_OBS, DIM))
+    y = np.sin(3.0 * X).sum(axis=1) + 0.05 * np.random.default_rng(SEED_Y).standard_normal(N_OBS)
+    y = (y - y.mean()) / y.std(ddof=1)
+    return X, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        # samples taken under load: the upper half of the observed SM clocks
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(n_cand, threads_note=True):
+    """Time the CPU oracle (port of the reference's exact-GP path) on a bounded sample of the workload."""
+    import torch
+    from oracle import gp_oracle as o
+    X, y = synth_problem()
+    t0 = time.perf_counter()
+    gp = o.fit(X, y, o.KERNEL_MATERN52, LENGTHSCALE, OUTPUTSCALE, NOISE)
+    t_fit = time.perf_counter() - t0
+    eng = torch.quasirandom.SobolEngine(DIM, scramble=True, seed=SEED_POOL)
+    st, sh = eng.sobolstate.numpy(), eng.shift.numpy()
+    t0 = time.perf_counter()
+    pts = o.sobol_points(st, sh, 0, n_cand)
+    tv, ti, _, _, _ = o.sweep(gp, pts, o.ACQ_EI, float(y.max()), k=TOPK)
+    t_sweep = time.perf_counter() - t0
+    return {"fit_s": t_fit, "sweep_s": t_sweep, "cand_per_s": n_cand / t_sweep, "argmax": int(ti[0]), "value": float(tv[0])}
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port; the reference's botorch/gpytorch stack is not installable)
+    timed on the host cores with all BLAS threads, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 20_000
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_oracle_run(2_000)
+    times = []
+    for _ in range(args.steps):
+        r = cpu_oracle_run(sample)
+        times.append(r["sweep_s"])
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: synthetic d=8 n_obs=4096 Matern-5/2, EI over a Sobol pool (10^7 in the GPU arm)",
+                       "n_obs": N_OBS, "d": DIM, "pool": POOL, "acq": "EI"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample}-candidate prefix of the same Sobol pool per step (NumPy/SciPy FP64 oracle, "
+                                       f"threaded BLAS, chunk 2048 like Bayesian7.py:63); the reference's botorch/gpytorch "
+                                       f"stack is not installable offline"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pool", type=int, default=POOL, help="candidate pool size (default: the BASELINE 10^7)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bayesianoptimizer_b200 import GPEngine, sobol_state
+    from bayesianoptimizer_b200.dist import allgather_topk, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pool = int(args.pool)
+
+    X, y = synth_problem()
+    best_f = float(y.max())
+    Xh, yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    eng = GPEngine(dev)
+    sob = sobol_state(DIM, SEED_POOL)
+    first, count = shard_range(pool, rank, world)
+    W = max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- refit timing (device-resident inputs) ----
+    eng.fit(Xd, yd, "matern52", LENGTHSCALE, OUTPUTSCALE, NOISE)
+    torch.cuda.synchronize()
+    fit_ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        eng.fit(Xd, yd, "matern52", LENGTHSCALE, OUTPUTSCALE, NOISE)
+        torch.cuda.synchronize()
+        fit_ms.append((time.perf_counter() - t0) * 1e3)
+    refit_ms = float(np.median(fit_ms))
+
+    peak_tflops = eng.fp64_peak_tflops(True, 0.5)     # FP64 DMMA roof, measured live (MEASURED_PEAKS.json has no FP64 entry)
+
+    def step_resident():
+        v, i = eng.sweep("ei", best_f, 2.0, sobol=sob, first_index=first, count=count, topk=TOPK)
+        if world > 1:
+            v, i = allgather_topk(v, i, TOPK)
+        return v, i
+
+    def step_e2e():
+        eng.fit(Xh, yh, "matern52", LENGTHSCALE, OUTPUTSCALE, NOISE)          # bo_fit_host: H2D of X, y inside
+        v, i = eng.sweep_host("ei", best_f, 2.0, sobol=sob, first_index=first, count=count, topk=TOPK)   # D2H inside
+        if world > 1:
+            v, i = allgather_topk(v.to(dev), i.to(dev), TOPK)
+            v, i = v.cpu(), i.cpu()
+        return v, i
+
+    # ---- resident arm: W warm-up steps, then exactly K timed steps ----
+    for _ in range(W):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    kernel_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        v, i = step_resident()
+        kernel_ms.append(eng.last_sweep_ms())      # CUDA events on the launch stream around the fused kernel
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    winner = (float(v[0].item()), int(i[0].item()))
+
+    # ---- e2e arm: host buffers through the C-ABI host entries ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ve, ie = step_e2e()
+    torch.cuda.synchronize()
+    e2e_local_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
+    t = torch.tensor([elapsed_ms, e2e_local_ms, float(np.mean(kernel_ms)), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_ms, kern_ms = tmax[0].item(), tmax[1].item(), tmax[2].item()
+        launches = int(tsum[3].item())
+    else:
+        e2e_ms, kern_ms = e2e_local_ms, float(np.mean(kernel_ms))
+
+    if rank == 0:
+        ms_per_step = elapsed_ms / args.steps
+        value = pool / (ms_per_step * 1e-3)
+        e2e_value = pool / (e2e_ms / args.steps * 1e-3)
+        fpc = flops_per_candidate(N_OBS, DIM)
+        # dominant kernel = the fused sweep kernel of rank 0's shard
+        achieved = count * fpc / (float(np.mean(kernel_ms)) * 1e-3) * 1e-12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: synthetic d=8 n_obs=4096 Matern-5/2 ARD, EI over a 10^7 in-kernel scrambled-Sobol "
+                                   "pool sharded contiguously over the GPUs, top-1 + one (value,index) all-gather",
+                       "n_obs": N_OBS, "d": DIM, "pool": pool, "acq": "EI", "parallelism": f"candidate-shard x{world}",
+                       "l2": "inputs larger than L2: 67 MB packed L^-1 + 620 MB K* panels streamed every wave"},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(world * (N_OBS * DIM * 8 + N_OBS * 8 + 2052)),
+                    "d2h_bytes_per_step": int(world * TOPK * 16),
+                    "includes": "bo_fit_host (H2D X,y + refit) + bo_sweep_host (sweep + D2H winner) + all-gather"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tflops, "traffic": traffic,
+                         "kernel": "sweep_kernel<8> (FP64 DMMA.8x8x4 pipe)",
+                         "peak_source": "FP64 DMMA peak measured live by bo_fp64_peak (register-resident DMMA.8x8x4 loop); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flop_per_candidate": fpc, "kernel_ms": float(np.mean(kernel_ms))},
+            "refit_ms": refit_ms, "suggest_ms": ms_per_step,
+            "argmax": {"value": winner[0], "index": winner[1]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sample = 20_000
+            r = cpu_oracle_run(sample)
+            line["cpu_baseline"] = {"value": r["cand_per_s"], "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                                    "sample": f"{sample}-candidate prefix of the same Sobol pool, NumPy/SciPy FP64 oracle "
+                                              f"(fit {r['fit_s']:.2f} s, sweep {r['sweep_s']:.2f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
