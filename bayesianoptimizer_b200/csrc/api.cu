@@ -16,17 +16,8 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
              cudaStream_t st);
 }
 
-extern "C" {
-
-int bo_abi_version(void) { return BO_ABI_VERSION; }
-
-int bo_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-}
-
-int bo_create(bo_handle** out, int device) {
+namespace bo {
+int create_handle(bo_handle** out, int device) {
     if (!out) return BO_E_INVALID;
     *out = nullptr;
     int ndev = 0;
@@ -53,6 +44,19 @@ int bo_create(bo_handle** out, int device) {
     *out = h;
     return 0;
 }
+}  // namespace bo
+
+extern "C" {
+
+int bo_abi_version(void) { return BO_ABI_VERSION; }
+
+int bo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bo_create(bo_handle** out, int device) { return create_handle(out, device); }
 
 int bo_release_workspace(bo_handle* h) {
     if (!h) return BO_E_INVALID;
@@ -70,7 +74,8 @@ void bo_destroy(bo_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     bo_release_workspace(h);
-    void* ptrs[] = {h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2,
+    if (h->lml_sub) { bo_destroy(h->lml_sub); h->lml_sub = nullptr; }
+    void* ptrs[] = {h->qbuf, h->lml_part, h->Kw, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
                     h->out_stage_val, h->out_stage_idx};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -83,7 +88,7 @@ void bo_destroy(bo_handle* h) {
 
 const char* bo_last_error(const bo_handle* h) { return h ? h->err.c_str() : "null handle"; }
 int bo_num_obs(const bo_handle* h) { return (h && h->fitted) ? h->n : 0; }
-int64_t bo_launch_count(const bo_handle* h) { return h ? h->launches : 0; }
+int64_t bo_launch_count(const bo_handle* h) { return h ? h->launches + (h->lml_sub ? h->lml_sub->launches : 0) : 0; }
 
 int bo_fit(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d, int32_t kernel_kind,
            const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,

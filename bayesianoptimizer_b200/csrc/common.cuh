@@ -91,6 +91,12 @@ struct bo_handle {
     double* out_stage_val = nullptr; int64_t* out_stage_idx = nullptr;  // device top-k staging for *_host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool sweep_timed = false;
+
+    // K5-K7 workspaces
+    double* qbuf = nullptr; size_t qbuf_elems = 0;      // refinement / acq-grad scratch
+    bo_handle* lml_sub = nullptr;                       // private engine for the batched LML restarts
+    double* lml_part = nullptr; size_t lml_part_elems = 0;
+    double* Kw = nullptr; size_t Kw_elems = 0;          // K^-1 of the current restart [np, cap_np]
 };
 
 namespace bo {
@@ -208,5 +214,8 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
 int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,
                       double* out_dev, cudaStream_t st);
 int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);
-int refit_factor(bo_handle* h, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv
+int refit_factor(bo_handle* h, cudaStream_t st);
+int create_handle(bo_handle** out, int device);
+int pack_row_block(bo_handle* h, int ib, cudaStream_t st);
+int run_gemm_once(bo_handle* h, const GemmProblem* probs_host, int count, int tiles, int cfg, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv
 }  // namespace bo

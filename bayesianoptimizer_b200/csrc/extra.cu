@@ -68,18 +68,589 @@ int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops) {
     return 0;
 }
 
-int acq_grad_impl(bo_handle* h, int, double, double, double, const double*, int, double*, double*, cudaStream_t) {
-    return fail(h, BO_E_INVALID, "bo_acq_grad: not implemented yet");
+
+#define BO_DISPATCH_DP(dp, fn, ...)                                   \
+    ((dp) == 2 ? fn<2>(__VA_ARGS__) : (dp) == 4 ? fn<4>(__VA_ARGS__) :  \
+     (dp) == 6 ? fn<6>(__VA_ARGS__) : (dp) == 8 ? fn<8>(__VA_ARGS__) :  \
+     (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
+
+// =================================================================================================
+// K6: acquisition value + analytic gradient at k query points, and batched refinement of starts.
+// Replaces the autograd backward of acq(X) and gen_candidates_scipy inside optimize_acqf
+// (optimization/Bayesian.py:105-112).
+// =================================================================================================
+
+// kv[q][j] = k(x_q, X_j), gv[q][j] = "g" with dk/dx = g * (x~ - X~_j) * inv_ls   (0 for j >= n)
+template <int DP>
+__global__ void __launch_bounds__(256) kq_build_kernel(const double* __restrict__ Xs, int n, int np, Hyper hyp,
+                                                       const double* __restrict__ Xq, int d,
+                                                       double* __restrict__ kv, double* __restrict__ gv) {
+    const int j = blockIdx.x * 256 + threadIdx.x, qi = blockIdx.y;
+    if (j >= np) return;
+    double kval = 0.0, g = 0.0;
+    if (j < n) {
+        double sq = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            const double xq = (k < d) ? Xq[(size_t)qi * d + k] * hyp.inv_ls[k] : 0.0;
+            const double df = xq - Xs[(size_t)j * BO_MAX_DIM + k];
+            sq = fma(df, df, sq);
+        }
+        if (hyp.kind == BO_KERNEL_MATERN52) {
+            const double s5 = 2.23606797749978969640917366873128;
+            const double r = sqrt(sq), e = exp(-s5 * r);
+            kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, r, 1.0)) * e;
+            g = -hyp.outputscale * (5.0 / 3.0) * fma(s5, r, 1.0) * e;
+        } else {
+            kval = hyp.outputscale * exp(-0.5 * sq);
+            g = -kval;
+        }
+    }
+    kv[(size_t)qi * np + j] = kval;
+    if (gv) gv[(size_t)qi * np + j] = g;
 }
-int refine_impl(bo_handle* h, int, double, double, double, const double*, int, int, double*, double*, cudaStream_t) {
-    return fail(h, BO_E_INVALID, "bo_refine: not implemented yet");
+
+// V[q][i] = sum_{j<=i} Li[i][j] rhs[q][j] for QB right-hand sides at once (warp per row)
+template <int QB>
+__global__ void __launch_bounds__(256) trmm_lower_skinny_kernel(const double* __restrict__ Li, int ld, int np,
+                                                                const double* __restrict__ rhs, int k,
+                                                                double* __restrict__ out) {
+    __shared__ double sh[QB][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 8 + warp, q0 = blockIdx.y * QB;
+    const int last = blockIdx.x * 8 + 7;
+    double acc[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) acc[q] = 0.0;
+    for (int j0 = 0; j0 <= last; j0 += 256) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < QB; ++q)
+            sh[q][threadIdx.x] = (q0 + q < k && j0 + threadIdx.x < np) ? rhs[(size_t)(q0 + q) * np + j0 + threadIdx.x] : 0.0;
+        __syncthreads();
+        for (int jj = lane; jj < 256; jj += 32) {
+            const int j = j0 + jj;
+            if (j <= row) {
+                const double a = Li[(size_t)row * ld + j];
+#pragma unroll
+                for (int q = 0; q < QB; ++q) acc[q] = fma(a, sh[q][jj], acc[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && q0 + q < k) out[(size_t)(q0 + q) * np + row] = v;
+    }
 }
-int append_impl(bo_handle* h, const double*, double, int, cudaStream_t) {
-    return fail(h, BO_E_INVALID, "bo_append: not implemented yet");
+
+// W[q][j] = sum_{i>=j} Li[i][j] V[q][i] for QB right-hand sides (block per 32 columns, 8 row lanes)
+template <int QB>
+__global__ void __launch_bounds__(256) trmm_lower_t_skinny_kernel(const double* __restrict__ Li, int ld, int np,
+                                                                  const double* __restrict__ V, int k,
+                                                                  double* __restrict__ out) {
+    __shared__ double red[8][QB][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx, q0 = blockIdx.y * QB;
+    double acc[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) acc[q] = 0.0;
+    for (int i = blockIdx.x * 32 + ty; i < np; i += 8) {
+        if (i >= j) {
+            const double a = Li[(size_t)i * ld + j];
+#pragma unroll
+            for (int q = 0; q < QB; ++q)
+                if (q0 + q < k) acc[q] = fma(a, V[(size_t)(q0 + q) * np + i], acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) red[ty][q][tx] = acc[q];
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += red[r][q][tx];
+            if (q0 + q < k) out[(size_t)(q0 + q) * np + j] = t;
+        }
+    }
 }
-int lml_impl(bo_handle* h, const double*, const double*, int, int, int, double, const double*, int, double*, double*, int*,
-             cudaStream_t) {
-    return fail(h, BO_E_INVALID, "bo_lml_grad_batched: not implemented yet");
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+}
+
+__device__ __forceinline__ double log1mexp_e(double x) {
+    return (x > -0.69314718055994530942) ? log(-expm1(x)) : log1p(-exp(x));
+}
+
+// per query: mu, var, grad mu, grad var -> acquisition value and gradient (block per query)
+template <int DP>
+__global__ void __launch_bounds__(256) acq_grad_finalize_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha,
+                                                                int n, int np, Hyper hyp, const double* __restrict__ Xq, int d,
+                                                                const double* __restrict__ kv, const double* __restrict__ gv,
+                                                                const double* __restrict__ V, const double* __restrict__ W,
+                                                                int acq, double best_f, double sqrt_beta, double min_var,
+                                                                double* __restrict__ val, double* __restrict__ grad) {
+    __shared__ double red[8];
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    double xq[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xq[k] = (k < d) ? Xq[(size_t)qi * d + k] * hyp.inv_ls[k] : 0.0;
+    double mu = 0.0, ss = 0.0, gm[DP], gs[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) gm[k] = gs[k] = 0.0;
+    for (int j = tid; j < np; j += 256) {
+        const double v = V[(size_t)qi * np + j];
+        ss = fma(v, v, ss);
+        if (j < n) {
+            const double a = alpha[j], w = W[(size_t)qi * np + j], g = gv[(size_t)qi * np + j];
+            mu = fma(kv[(size_t)qi * np + j], a, mu);
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const double t = g * (xq[k] - Xs[(size_t)j * BO_MAX_DIM + k]) * hyp.inv_ls[k];
+                gm[k] = fma(a, t, gm[k]);
+                gs[k] = fma(w, t, gs[k]);
+            }
+        }
+    }
+    mu = block_sum_256(mu, red);
+    ss = block_sum_256(ss, red);
+#pragma unroll
+    for (int k = 0; k < DP; ++k) { gm[k] = block_sum_256(gm[k], red); gs[k] = block_sum_256(gs[k], red); }
+    if (tid != 0) return;
+    const double mean = hyp.mean + mu;
+    double var = hyp.outputscale - ss;
+    double dvar[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) dvar[k] = -2.0 * gs[k];
+    if (var < min_var) {
+        var = min_var;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) dvar[k] = 0.0;
+    }
+    const double sigma = sqrt(var);
+    double value, cm, cs;          // gradient = cm * dmu + cs * dsigma, dsigma = dvar / (2 sigma)
+    const double inv_sqrt2 = 0.70710678118654752440, inv_sqrt_2pi = 0.39894228040143267794;
+    if (acq == BO_ACQ_VAR) { value = var; cm = 0.0; cs = 2.0 * sigma; }
+    else if (acq == BO_ACQ_MEAN) { value = mean; cm = 1.0; cs = 0.0; }
+    else if (acq == BO_ACQ_UCB) { value = fma(sqrt_beta, sigma, mean); cm = 1.0; cs = sqrt_beta; }
+    else {
+        const double u = (mean - best_f) / sigma;
+        const double phi = inv_sqrt_2pi * exp(-0.5 * u * u);
+        const double Phi = 0.5 * erfc(-u * inv_sqrt2);
+        if (acq == BO_ACQ_EI) {
+            value = sigma * fma(u, Phi, phi); cm = Phi; cs = phi;
+        } else {
+            double lh, dlh;      // log h(u), d log h / du
+            if (u > -1.0) {
+                const double hh = fma(u, Phi, phi);
+                lh = log(hh); dlh = Phi / hh;
+            } else {
+                const double ex = erfcx(-u * inv_sqrt2);
+                const double t = 1.2533141373155002512 * ex;                 // sqrt(pi/2) erfcx(|u|/sqrt2) = Phi/phi
+                const double w = log(ex * fabs(u)) + 0.22579135264472743236;
+                lh = -0.5 * u * u - 0.91893853320467274178 + log1mexp_e(w);
+                dlh = t / (-expm1(w));                                        // Phi / (phi + u Phi)
+            }
+            value = log(sigma) + lh;
+            // d/dx = dsigma/sigma + dlh * (dmu - u dsigma)/sigma
+            cm = dlh / sigma; cs = (1.0 - dlh * u) / sigma;
+        }
+    }
+    val[qi] = value;
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
+        if (k < d) grad[(size_t)qi * d + k] = cm * gm[k] + cs * dvar[k] / (2.0 * sigma);
+}
+
+static int ensure_qbuf(bo_handle* h, size_t elems) {
+    if (elems <= h->qbuf_elems) return 0;
+    if (h->qbuf) cudaFree(h->qbuf);
+    h->qbuf = nullptr; h->qbuf_elems = 0;
+    BO_CUDA(h, cudaMalloc(&h->qbuf, elems * sizeof(double)));
+    h->qbuf_elems = elems;
+    return 0;
+}
+
+constexpr int QB = 8;
+
+template <int DP>
+static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, double min_var, const double* Xq, int k,
+                         double* val, double* grad, double* ws, cudaStream_t st) {
+    const int np = h->np, ld = h->cap_np;
+    double* kv = ws; double* gv = kv + (size_t)k * np; double* V = gv + (size_t)k * np; double* W = V + (size_t)k * np;
+    kq_build_kernel<DP><<<dim3(np / 256 + (np % 256 != 0), k), 256, 0, st>>>(h->Xs, h->n, np, h->hyp, Xq, h->d, kv, gv);
+    BO_LAUNCH_CHECK(h);
+    const int qg = (k + QB - 1) / QB;
+    trmm_lower_skinny_kernel<QB><<<dim3(np / 8, qg), 256, 0, st>>>(h->Li, ld, np, kv, k, V);
+    BO_LAUNCH_CHECK(h);
+    trmm_lower_t_skinny_kernel<QB><<<dim3(np / 32, qg), 256, 0, st>>>(h->Li, ld, np, V, k, W);
+    BO_LAUNCH_CHECK(h);
+    acq_grad_finalize_kernel<DP><<<k, 256, 0, st>>>(h->Xs, h->alpha, h->n, np, h->hyp, Xq, h->d, kv, gv, V, W, acq, best_f,
+                                                   sqrt(beta), min_var, val, grad);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+static int check_query_args(bo_handle* h, int acq_kind, double beta, const void* a, const void* b, const void* c, int k) {
+    if (!h->fitted) return fail(h, BO_E_NOTFIT, "acquisition gradient / refinement before a successful bo_fit");
+    if (acq_kind < BO_ACQ_EI || acq_kind > BO_ACQ_MEAN) return fail(h, BO_E_INVALID, "unknown acquisition kind");
+    if (!a || !b || !c || k < 1) return fail(h, BO_E_INVALID, "bad query arguments");
+    if (k > 4096) return fail(h, BO_E_CAPACITY, "at most 4096 query points per call");
+    if (!(beta >= 0.0)) return fail(h, BO_E_INVALID, "beta must be >= 0");
+    return 0;
+}
+
+int acq_grad_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var, const double* Xq_dev, int k,
+                  double* val_dev, double* grad_dev, cudaStream_t st) {
+    int rc = check_query_args(h, acq_kind, beta, Xq_dev, val_dev, grad_dev, k);
+    if (rc) return rc;
+    BO_CUDA(h, cudaSetDevice(h->device));
+    if ((rc = ensure_qbuf(h, (size_t)4 * k * h->np + 64))) return rc;
+    return BO_DISPATCH_DP(h->dp, eval_acq_grad, h, acq_kind, best_f, beta, min_var, Xq_dev, k, val_dev, grad_dev, h->qbuf, st);
+}
+
+// ---- refinement state machine (per start; projected ascent with Barzilai-Borwein steps) ---------
+__global__ void refine_init_kernel(int k, int d, const double* __restrict__ g, double* __restrict__ step) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    double gmax = 0.0;
+    for (int c = 0; c < d; ++c) gmax = fmax(gmax, fabs(g[(size_t)s * d + c]));
+    step[s] = (gmax > 0.0 && isfinite(gmax)) ? 0.05 / gmax : 0.0;
+}
+__global__ void refine_propose_kernel(int k, int d, const double* __restrict__ x, const double* __restrict__ g,
+                                      const double* __restrict__ step, double* __restrict__ xn) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= k * d) return;
+    const int s = e / d;
+    double gv = g[e];
+    if (!isfinite(gv)) gv = 0.0;
+    xn[e] = fmin(1.0, fmax(0.0, fma(step[s], gv, x[e])));
+}
+__global__ void refine_update_kernel(int k, int d, double* __restrict__ x, double* __restrict__ f, double* __restrict__ g,
+                                     const double* __restrict__ xn, const double* __restrict__ fn,
+                                     const double* __restrict__ gn, double* __restrict__ step) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    const double f_new = fn[s];
+    if (f_new > f[s] && isfinite(f_new)) {
+        double ss = 0.0, sy = 0.0;
+        for (int c = 0; c < d; ++c) {
+            const double sd = xn[(size_t)s * d + c] - x[(size_t)s * d + c];
+            const double yd = gn[(size_t)s * d + c] - g[(size_t)s * d + c];
+            ss = fma(sd, sd, ss); sy = fma(sd, yd, sy);
+            x[(size_t)s * d + c] = xn[(size_t)s * d + c];
+            g[(size_t)s * d + c] = gn[(size_t)s * d + c];
+        }
+        f[s] = f_new;
+        double st = step[s];
+        st = (sy < 0.0) ? -ss / sy : st * 2.0;           // BB1 step on negative curvature, else expand
+        step[s] = fmin(fmax(st, 1e-12), 1e6);
+    } else {
+        step[s] *= 0.25;                                   // reject: shrink and retry from the same point
+    }
+}
+
+int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var, const double* starts_dev, int k,
+                int iters, double* x_dev, double* val_dev, cudaStream_t st) {
+    int rc = check_query_args(h, acq_kind, beta, starts_dev, x_dev, val_dev, k);
+    if (rc) return rc;
+    if (iters < 0) return fail(h, BO_E_INVALID, "bo_refine: iters must be >= 0");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const int d = h->d, np = h->np;
+    const size_t ws_elems = (size_t)4 * k * np;
+    // layout: [acq-grad scratch | g | xn | fn | gn | step]
+    if ((rc = ensure_qbuf(h, ws_elems + (size_t)k * (3 * d + 2) + 64))) return rc;
+    double* ws = h->qbuf;
+    double* g = ws + ws_elems; double* xn = g + (size_t)k * d; double* gn = xn + (size_t)k * d;
+    double* fn = gn + (size_t)k * d; double* step = fn + k;
+    BO_CUDA(h, cudaMemcpyAsync(x_dev, starts_dev, (size_t)k * d * 8, cudaMemcpyDeviceToDevice, st));
+    if ((rc = BO_DISPATCH_DP(h->dp, eval_acq_grad, h, acq_kind, best_f, beta, min_var, x_dev, k, val_dev, g, ws, st))) return rc;
+    refine_init_kernel<<<(k + 127) / 128, 128, 0, st>>>(k, d, g, step);
+    BO_LAUNCH_CHECK(h);
+    for (int it = 0; it < iters; ++it) {
+        refine_propose_kernel<<<(k * d + 127) / 128, 128, 0, st>>>(k, d, x_dev, g, step, xn);
+        BO_LAUNCH_CHECK(h);
+        if ((rc = BO_DISPATCH_DP(h->dp, eval_acq_grad, h, acq_kind, best_f, beta, min_var, xn, k, fn, gn, ws, st))) return rc;
+        refine_update_kernel<<<(k + 127) / 128, 128, 0, st>>>(k, d, x_dev, val_dev, g, xn, fn, gn, step);
+        BO_LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+// =================================================================================================
+// K5: row append (Kriging believer / new observation) by bordering L and L^-1
+// =================================================================================================
+__global__ void pad_identity_kernel(double* __restrict__ Lm, double* __restrict__ Li, int ld, int row0, int rows,
+                                    double* __restrict__ Xs, double* __restrict__ Xraw, double* __restrict__ yv,
+                                    double* __restrict__ alpha) {
+    // rows [row0, row0+rows): zero + unit diagonal; auxiliary vectors zero
+    const int r = row0 + blockIdx.x;
+    for (int c = threadIdx.x; c < row0 + rows; c += blockDim.x) {
+        const double v = (c == r) ? 1.0 : 0.0;
+        Lm[(size_t)r * ld + c] = v;
+        Li[(size_t)r * ld + c] = v;
+    }
+    if (threadIdx.x < BO_MAX_DIM) { Xs[(size_t)r * BO_MAX_DIM + threadIdx.x] = 0.0; Xraw[(size_t)r * BO_MAX_DIM + threadIdx.x] = 0.0; }
+    if (threadIdx.x == 0) { yv[r] = 0.0; alpha[r] = 0.0; }
+}
+
+__global__ void __launch_bounds__(1024) append_finalize_kernel(int n, int np, int ld, Hyper hyp, const double* __restrict__ x, int d,
+                                                               double y, int believer, const double* __restrict__ kv,
+                                                               const double* __restrict__ l, const double* __restrict__ u,
+                                                               double* __restrict__ Lm, double* __restrict__ Li,
+                                                               double* __restrict__ alpha, double* __restrict__ Xs,
+                                                               double* __restrict__ Xraw, double* __restrict__ yv,
+                                                               int* __restrict__ info) {
+    __shared__ double red[2][32];
+    __shared__ double bc[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double ss = 0.0, ka = 0.0;
+    for (int j = tid; j < n; j += 1024) { ss = fma(l[j], l[j], ss); ka = fma(kv[j], alpha[j], ka); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); ka += __shfl_xor_sync(0xffffffffu, ka, o); }
+    if (lane == 0) { red[0][warp] = ss; red[1][warp] = ka; }
+    __syncthreads();
+    if (warp == 0) {
+        ss = red[0][lane]; ka = red[1][lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); ka += __shfl_xor_sync(0xffffffffu, ka, o); }
+        if (lane == 0) { bc[0] = ss; bc[1] = ka; }
+    }
+    __syncthreads();
+    ss = bc[0]; ka = bc[1];
+    const double lam2 = hyp.outputscale + hyp.noise + hyp.jitter - ss;
+    if (!(lam2 > 0.0)) { if (tid == 0) *info = n + 1; return; }
+    const double lam = sqrt(lam2), ilam = 1.0 / lam;
+    const double ynew = believer ? hyp.mean + ka : y;
+    const double znew = (ynew - hyp.mean - ka) * ilam;
+    for (int j = tid; j < n; j += 1024) {
+        Lm[(size_t)n * ld + j] = l[j];
+        Li[(size_t)n * ld + j] = -u[j] * ilam;
+        alpha[j] = fma(-u[j] * ilam, znew, alpha[j]);
+    }
+    if (tid == 0) {
+        Lm[(size_t)n * ld + n] = lam;
+        Li[(size_t)n * ld + n] = ilam;
+        alpha[n] = znew * ilam;
+        yv[n] = ynew;
+    }
+    if (tid < BO_MAX_DIM) {
+        const double xv = (tid < d) ? x[tid] : 0.0;
+        Xraw[(size_t)n * BO_MAX_DIM + tid] = xv;
+        Xs[(size_t)n * BO_MAX_DIM + tid] = xv * hyp.inv_ls[tid];
+    }
+}
+
+// kernels defined in fit.cu, re-declared here through small host wrappers
+int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st);
+int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st);
+
+template <int DP>
+static int launch_kq1(bo_handle* h, const double* x, double* kv, cudaStream_t st) {
+    kq_build_kernel<DP><<<dim3(h->np / 256 + (h->np % 256 != 0), 1), 256, 0, st>>>(h->Xs, h->n, h->np, h->hyp, x, h->d, kv, nullptr);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st) {
+    if (!h->fitted) return fail(h, BO_E_NOTFIT, "bo_append before a successful bo_fit");
+    if (!x_dev) return fail(h, BO_E_INVALID, "bo_append: null point");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if (h->n == h->np) {
+        // open a new padded block row: identity on the diagonal, zeros elsewhere
+        const int np_new = h->np + PAD;
+        if ((rc = ensure_capacity(h, np_new, st))) return rc;
+        pad_identity_kernel<<<PAD, 256, 0, st>>>(h->Lm, h->Li, h->cap_np, h->np, PAD, h->Xs, h->Xraw, h->yv, h->alpha);
+        BO_LAUNCH_CHECK(h);
+        h->np = np_new;
+        h->plan_np = -1;
+    }
+    if ((rc = ensure_qbuf(h, (size_t)3 * h->np + 64))) return rc;
+    double* kv = h->qbuf; double* l = kv + h->np; double* u = l + h->np;
+    if ((rc = BO_DISPATCH_DP(h->dp, launch_kq1, h, x_dev, kv, st))) return rc;
+    if ((rc = launch_trmv_lower(h, kv, l, st))) return rc;
+    if ((rc = launch_trmv_lower_t(h, l, u, 0, st))) return rc;
+    BO_CUDA(h, cudaMemsetAsync(h->info_dev, 0, sizeof(int), st));
+    append_finalize_kernel<<<1, 1024, 0, st>>>(h->n, h->np, h->cap_np, h->hyp, x_dev, h->d, y, use_believer, kv, l, u, h->Lm, h->Li,
+                                              h->alpha, h->Xs, h->Xraw, h->yv, h->info_dev);
+    BO_LAUNCH_CHECK(h);
+    BO_CUDA(h, cudaMemcpyAsync(h->info_host, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if ((rc = pack_row_block(h, h->n / SW_BM, st))) return rc;
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    if (*h->info_host != 0) {
+        h->err = "bo_append: bordered matrix not positive definite (duplicate point with zero noise?)";
+        // the padded row was left untouched (identity) by the finalize kernel; repacked tiles are unchanged
+        return *h->info_host;
+    }
+    h->n += 1;
+    return 0;
+}
+
+// =================================================================================================
+// K7: batched exact log marginal likelihood + gradient over R hyper-parameter restarts
+// (ExactMarginalLogLikelihood closure of fit_gpytorch_mll, optimization/Bayesian.py:92-93).
+// =================================================================================================
+// per 32x32 tile of the strict lower triangle (+ diagonal): partial sums of
+//   W_ij dK_ij/dlog l_k (k < DP), W_ij K_ij, and on the diagonal W_ii ; also log L_ii and r_i alpha_i
+template <int DP>
+__global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha,
+                                                            const double* __restrict__ Kinv, const double* __restrict__ Lm,
+                                                            const double* __restrict__ yv, int ld, int n, Hyper hyp,
+                                                            double* __restrict__ part /*[tiles][DP+4]*/) {
+    __shared__ double red[8];
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    const int tile = bi * gridDim.x + bj;
+    double acc[DP + 4];
+#pragma unroll
+    for (int k = 0; k < DP + 4; ++k) acc[k] = 0.0;
+    if (bj <= bi) {
+        const int j = bj * 32 + (threadIdx.x & 31);
+        double xj[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) xj[k] = (j < n) ? Xs[(size_t)j * BO_MAX_DIM + k] : 0.0;
+        const double aj = (j < n) ? alpha[j] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = bi * 32 + (threadIdx.x >> 5) + r * 8;
+            if (i >= n || j >= n || j > i) continue;
+            const double w = alpha[i] * aj - Kinv[(size_t)i * ld + j];
+            if (i == j) {
+                acc[DP + 1] += w;                                   // trace(W)
+                acc[DP + 2] += log(Lm[(size_t)i * ld + i]);         // log det / 2
+                acc[DP + 3] += (yv[i] - hyp.mean) * alpha[i];       // quadratic form
+                continue;
+            }
+            double sq = 0.0, df2[DP];
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const double df = Xs[(size_t)i * BO_MAX_DIM + k] - xj[k];
+                df2[k] = df * df;
+                sq += df2[k];
+            }
+            double kval, G;
+            if (hyp.kind == BO_KERNEL_MATERN52) {
+                const double s5 = 2.23606797749978969640917366873128;
+                const double rr = sqrt(sq), e = exp(-s5 * rr);
+                kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, rr, 1.0)) * e;
+                G = hyp.outputscale * (5.0 / 3.0) * fma(s5, rr, 1.0) * e;
+            } else {
+                kval = hyp.outputscale * exp(-0.5 * sq);
+                G = kval;
+            }
+            const double wg = w * G;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) acc[k] = fma(wg, df2[k], acc[k]);
+            acc[DP] = fma(w, kval, acc[DP]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DP + 4; ++k) {
+        const double t = block_sum_256(acc[k], red);
+        if (threadIdx.x == 0) part[(size_t)tile * (DP + 4) + k] = t;
+    }
+}
+
+// deterministic final reduction: one block sums the tile partials column by column
+template <int DP>
+__global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restrict__ part, int tiles, int n, int d, Hyper hyp,
+                                                         double* __restrict__ out /*[d+3]: lml, grad[d+2]*/) {
+    __shared__ double red[8];
+    double tot[DP + 4];
+#pragma unroll
+    for (int k = 0; k < DP + 4; ++k) {
+        double s = 0.0;
+        for (int t = threadIdx.x; t < tiles; t += 256) s += part[(size_t)t * (DP + 4) + k];
+        tot[k] = block_sum_256(s, red);
+    }
+    if (threadIdx.x != 0) return;
+    const double trW = tot[DP + 1], logdet_half = tot[DP + 2], quad = tot[DP + 3];
+    out[0] = -0.5 * quad - logdet_half - 0.5 * n * 1.83787706640934548356;        // log(2 pi)
+    for (int k = 0; k < d; ++k) out[1 + k] = tot[k];                               // pairs i>j count twice in 1/2 sum
+    out[1 + d] = tot[DP] + 0.5 * hyp.outputscale * trW;                            // d/d log outputscale
+    out[2 + d] = 0.5 * hyp.noise * trW;                                            // d/d log noise
+}
+
+template <int DP>
+static int launch_lml_grad(bo_handle* s, double* part, double* out, cudaStream_t st) {
+    const int nt = s->np / 32;
+    lml_grad_tile_kernel<DP><<<dim3(nt, nt), 256, 0, st>>>(s->Xs, s->alpha, s->Kw, s->Lm, s->yv, s->cap_np, s->n, s->hyp, part);
+    BO_LAUNCH_CHECK(s);
+    lml_reduce_kernel<DP><<<1, 256, 0, st>>>(part, nt * nt, s->n, s->d, s->hyp, out);
+    BO_LAUNCH_CHECK(s);
+    return 0;
+}
+
+int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
+             const double* theta_host, int R, double* lml_host, double* grad_host, int* status_host, cudaStream_t st) {
+    if (!X_dev || !y_dev || !theta_host || !lml_host || !grad_host || !status_host || n < 1 || d < 1 || R < 1)
+        return fail(h, BO_E_INVALID, "bo_lml_grad_batched: bad argument");
+    if (d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_lml_grad_batched: d exceeds BO_MAX_DIM");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if (!h->lml_sub && (rc = create_handle(&h->lml_sub, h->device))) return fail(h, rc, "bo_lml_grad_batched: cannot create the restart engine");
+    bo_handle* s = h->lml_sub;
+    const int np = round_up(n, PAD);
+    const int dp = pad_dim(d);
+    const size_t part_elems = (size_t)(np / 32) * (np / 32) * (dp + 4) + (size_t)(BO_MAX_DIM + 3);
+    if (part_elems > h->lml_part_elems) {
+        if (h->lml_part) cudaFree(h->lml_part);
+        h->lml_part = nullptr; h->lml_part_elems = 0;
+        BO_CUDA(h, cudaMalloc(&h->lml_part, part_elems * sizeof(double)));
+        h->lml_part_elems = part_elems;
+    }
+    double* out_dev = h->lml_part + (size_t)(np / 32) * (np / 32) * (dp + 4);
+    std::vector<double> out(d + 3);
+    for (int r = 0; r < R; ++r) {
+        const double* th = theta_host + (size_t)r * (d + 2);
+        double ls[BO_MAX_DIM];
+        for (int k = 0; k < d; ++k) ls[k] = exp(th[k]);
+        const double s2 = exp(th[d]), noise = exp(th[d + 1]);
+        rc = fit_impl(s, X_dev, y_dev, n, d, kind, ls, s2, noise, mean, 0.0, st);
+        if (rc < 0) { h->err = "bo_lml_grad_batched: " + s->err; return rc; }
+        status_host[r] = rc;
+        if (rc > 0) {
+            lml_host[r] = -INFINITY;
+            for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = 0.0;
+            continue;
+        }
+        // K^-1 = L^-T L^-1 (lower tiles) on the DMMA path
+        {
+            const int ld = s->cap_np;
+            const size_t need = (size_t)np * ld;
+            if (need > s->Kw_elems) {
+                if (s->Kw) cudaFree(s->Kw);
+                s->Kw = nullptr; s->Kw_elems = 0;
+                BO_CUDA(h, cudaMalloc(&s->Kw, need * sizeof(double)));
+                s->Kw_elems = need;
+            }
+            GemmProblem p{};
+            p.A = s->Li; p.B = s->Li; p.C = s->Kw; p.M = np; p.N = np; p.K = np; p.lda = ld; p.ldb = ld; p.ldc = ld;
+            p.alpha = 1.0; p.beta = 0.0; p.transB = 0; p.mode = GEMM_TRANS_A | GEMM_LOWER_C | GEMM_K_FROM_MAX;
+            const int tile = (np % 128 == 0 && (long)(np / 128) * (np / 128 + 1) / 2 >= s->sm_count) ? 128 : 64;
+            p.tiles_n = np / tile; p.tile_begin = 0; p.tile_end = (np / tile) * (np / tile);
+            if ((rc = run_gemm_once(s, &p, 1, p.tile_end, tile == 128 ? 1 : 0, st))) { h->err = s->err; return rc; }
+        }
+        if ((rc = BO_DISPATCH_DP(s->dp, launch_lml_grad, s, h->lml_part, out_dev, st))) { h->err = s->err; return rc; }
+        BO_CUDA(h, cudaMemcpyAsync(out.data(), out_dev, (d + 3) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        BO_CUDA(h, cudaStreamSynchronize(st));
+        lml_host[r] = out[0];
+        for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = out[1 + k];
+    }
+    return 0;
 }
 
 }  // namespace bo

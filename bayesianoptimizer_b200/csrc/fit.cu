@@ -214,9 +214,9 @@ __global__ void __launch_bounds__(256) gram_residual_kernel(const double* __rest
 //   DMMA.8x8x4 A fragments of two consecutive k4 steps.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_linv_kernel(const double* __restrict__ Li, int ld, int np,
-                                                        double* __restrict__ Lp) {
+                                                        double* __restrict__ Lp, int ib0) {
     constexpr int KCH = SW_BM / SW_BK;
-    const int ib = blockIdx.y;
+    const int ib = ib0 + blockIdx.y;
     const int kc = blockIdx.x;
     if (kc >= (ib + 1) * KCH) return;
     double* dst = Lp + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * SW_TILE;
@@ -458,7 +458,7 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
         if ((rc = gemm_launch(h, h->plan_launches[li], st))) return rc;
     {
         dim3 grid(np / SW_BK, np / SW_BM);
-        pack_linv_kernel<<<grid, 256, 0, st>>>(h->Li, ld, np, h->Lp);
+        pack_linv_kernel<<<grid, 256, 0, st>>>(h->Li, ld, np, h->Lp, 0);
         BO_LAUNCH_CHECK(h);
     }
     if ((rc = solve_alpha(h, st))) return rc;
@@ -472,6 +472,40 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
         return info > h->n ? h->n : info;
     }
     h->fitted = true;
+    return 0;
+}
+
+int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st) {
+    trmv_lower_kernel<<<h->np / 8, 256, 0, st>>>(h->Li, h->cap_np, h->np, v, z);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st) {
+    trmv_lower_t_kernel<<<h->np / 32, 256, 0, st>>>(h->Li, h->cap_np, h->np, z, out, accumulate);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+int pack_row_block(bo_handle* h, int ib, cudaStream_t st) {
+    dim3 grid(h->np / SW_BK, 1);
+    pack_linv_kernel<<<grid, 256, 0, st>>>(h->Li, h->cap_np, h->np, h->Lp, ib);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// one-off grouped GEMM outside the fit plan (descriptors staged through plan_dev's tail)
+int run_gemm_once(bo_handle* h, const GemmProblem* probs_host, int count, int tiles, int cfg, cudaStream_t st) {
+    static GemmProblem* dev = nullptr; static int cap = 0;     // tiny, process-lifetime staging buffer
+    if (count > cap) {
+        if (dev) cudaFree(dev);
+        BO_CUDA(h, cudaMalloc(&dev, sizeof(GemmProblem) * (count + 16)));
+        cap = count + 16;
+    }
+    BO_CUDA(h, cudaMemcpyAsync(dev, probs_host, sizeof(GemmProblem) * count, cudaMemcpyHostToDevice, st));
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    if (cfg == 1) dgemm_grouped_kernel<128, 128><<<tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(dev, count);
+    else dgemm_grouped_kernel<64, 64><<<tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(dev, count);
+    BO_LAUNCH_CHECK(h);
     return 0;
 }
 

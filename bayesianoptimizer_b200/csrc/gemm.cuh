@@ -12,6 +12,8 @@ enum : int {
     GEMM_A_LOWER    = 2,   // A (M x K, square) is lower triangular: k < (tile_m + 1) * BM
     GEMM_B_LOWER_NN = 4,   // B (K x N, square) is lower triangular: k >= tile_n * BN
     GEMM_B_LOWER_NT = 8,   // B given as [N][K] lower triangular (k <= n): k < (tile_n + 1) * BN
+    GEMM_TRANS_A    = 16,  // A given as [K][M] (column access): C = alpha * A^T * op(B) + beta * C
+    GEMM_K_FROM_MAX = 32,  // both operands vanish for k < max(tile_m * BM, tile_n * BN) (L^-T L^-1 products)
 };
 
 constexpr int GEMM_BK = 16;
@@ -20,7 +22,9 @@ constexpr int GEMM_LDK = GEMM_BK + 4;     // [row][k] layout stride (conflict-fr
 
 template <int BM, int BN>
 struct GemmSmem {
-    static constexpr int A_ELEMS = BM * GEMM_LDK;
+    static constexpr int A_N = BM * GEMM_LDK;
+    static constexpr int A_T = GEMM_BK * (BM + 4);
+    static constexpr int A_ELEMS = A_N > A_T ? A_N : A_T;
     static constexpr int B_NT = BN * GEMM_LDK;
     static constexpr int B_NN = GEMM_BK * (BN + 4);
     static constexpr int B_ELEMS = B_NT > B_NN ? B_NT : B_NN;
@@ -48,23 +52,33 @@ __global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* _
     if (P.mode & GEMM_A_LOWER)    k_end = min(k_end, (tm + 1) * BM);
     if (P.mode & GEMM_B_LOWER_NN) k_begin = max(k_begin, tn * BN);
     if (P.mode & GEMM_B_LOWER_NT) k_end = min(k_end, (tn + 1) * BN);
+    if (P.mode & GEMM_K_FROM_MAX) k_begin = max(k_begin, max(tm * BM, tn * BN));
+    const bool transA = (P.mode & GEMM_TRANS_A) != 0;
     const int nk = (k_end - k_begin) / GEMM_BK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, q = lane & 3;
 
-    const double* Ag = P.A + (size_t)(tm * BM) * P.lda;
+    const double* Ag = transA ? P.A + tm * BM : P.A + (size_t)(tm * BM) * P.lda;
     const double* Bg = P.transB ? P.B + (size_t)(tn * BN) * P.ldb : P.B + tn * BN;
 
     auto load_stage = [&](int s, int kt) {
         double* As = gsm + s * SM::STAGE;
         double* Bs = As + SM::A_ELEMS;
         const int k0 = k_begin + kt * GEMM_BK;
+        if (transA) {
 #pragma unroll
-        for (int c = tid; c < BM * (GEMM_BK / 2); c += 256) {
-            int row = c >> 3, kq = c & 7;
-            cp_async16(As + row * GEMM_LDK + kq * 2, Ag + (size_t)row * P.lda + k0 + kq * 2);
+            for (int c = tid; c < GEMM_BK * (BM / 2); c += 256) {
+                int kr = c / (BM / 2), mq = c % (BM / 2);
+                cp_async16(As + kr * (BM + 4) + mq * 2, Ag + (size_t)(k0 + kr) * P.lda + mq * 2);
+            }
+        } else {
+#pragma unroll
+            for (int c = tid; c < BM * (GEMM_BK / 2); c += 256) {
+                int row = c >> 3, kq = c & 7;
+                cp_async16(As + row * GEMM_LDK + kq * 2, Ag + (size_t)row * P.lda + k0 + kq * 2);
+            }
         }
         if (P.transB) {
 #pragma unroll
@@ -105,8 +119,13 @@ __global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* _
 #pragma unroll
         for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
             double a[MT], b[NT];
+            if (transA) {
 #pragma unroll
-            for (int i = 0; i < MT; ++i) a[i] = As[(wm * WM + i * 8 + g) * GEMM_LDK + kk * 4 + q];
+                for (int i = 0; i < MT; ++i) a[i] = As[(kk * 4 + q) * (BM + 4) + wm * WM + i * 8 + g];
+            } else {
+#pragma unroll
+                for (int i = 0; i < MT; ++i) a[i] = As[(wm * WM + i * 8 + g) * GEMM_LDK + kk * 4 + q];
+            }
             if (P.transB) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) b[j] = Bs[(wn * WN + j * 8 + g) * GEMM_LDK + kk * 4 + q];
