@@ -49,7 +49,7 @@ def allgather_topk(vals: torch.Tensor, idx: torch.Tensor, k: int, group=None) ->
         return merge_topk(vals, idx, k)
     world = dist.get_world_size(group)
     packed = torch.stack([vals.contiguous().view(torch.int64), idx.contiguous()], dim=1)      # [k, 2] int64
-    out = torch.empty((world,) + tuple(packed.shape), dtype=torch.int64, device=packed.device)
+    out = torch.empty((world * packed.shape[0], 2), dtype=torch.int64, device=packed.device)   # concatenated layout
     dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
     return merge_topk(out[..., 0].contiguous().view(torch.float64), out[..., 1].contiguous(), k)
 

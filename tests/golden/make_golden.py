@@ -55,7 +55,15 @@ def make(name, n, kind, ls, s2, noise, n_cand=256, seed=0):
     print(name, "n", n, "var range", var.min(), var.max(), "ei max", ei.max(), "lml", lml)
 
 
+def make_cache(n=600):
+    """Physical parameter rows + 8 displacements: the cached objective of BASELINE config 1 (float32 outputs)."""
+    raw = np.loadtxt(os.path.join(REF, "results", "optimization_results.csv"), delimiter=",", skiprows=1)
+    np.savez_compressed(os.path.join(OUT, "csv_cache_rows.npz"), params=raw[:n, :5], outputs=raw[:n, 5:13].astype(np.float32))
+    print("csv_cache_rows", n)
+
+
 if __name__ == "__main__":
+    make_cache()
     LS = (0.5, 0.4, 0.6, 0.8, 0.7)
     make("csv_n64_matern", 64, o.KERNEL_MATERN52, LS, 1.3, 1e-3)
     make("csv_n512_matern", 512, o.KERNEL_MATERN52, LS, 1.3, 1e-3)

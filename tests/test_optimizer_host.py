@@ -1,0 +1,152 @@
+"""CPU tier: host-side logic of the BayesianOptimizer drop-in (constructor surface, CSV / resume contract,
+LHS init, batch loop, failure conventions) with the oracle-backed engine double, and the sharding helpers."""
+import inspect
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle_engine import OracleEngine
+
+from bayesianoptimizer_b200.optimizer import BayesianOptimizer, GPConfig
+from bayesianoptimizer_b200.simulators import DEFAULT_BOUNDS, CachedCSVSimulator
+
+
+def _sim():
+    z = np.load(os.path.join(GOLDEN_DIR, "csv_cache_rows.npz"))
+    return CachedCSVSimulator(z["params"], z["outputs"])
+
+
+def _cfg(**kw):
+    base = dict(candidates_pool_size=512, num_restarts=3, refine_iters=5, hyper_restarts=2, hyper_maxiter=3, seed=0)
+    base.update(kw)
+    return GPConfig(**base)
+
+
+def _opt(tmp_path, **kw):
+    args = dict(simulator=_sim(), bounds_list=DEFAULT_BOUNDS, output_dir=str(tmp_path), n_initial_points=12, n_batches=2,
+                batch_size=2, gp_config=_cfg(), engine_factory=OracleEngine, device=torch.device("cpu"))
+    args.update(kw)
+    return BayesianOptimizer(**args)
+
+
+def test_constructor_is_superset_of_reference_signatures():
+    """Bayesian7.py:202-218 keyword set (the call at scripts/run_optimization.py:116-127) + Bayesian.py:24 positional order."""
+    params = list(inspect.signature(BayesianOptimizer.__init__).parameters)
+    assert params[1:7] == ["simulator", "bounds_list", "output_dir", "n_initial_points", "n_batches", "batch_size"]
+    for name in ("num_outputs", "svgp_threshold", "resume", "target_total", "device", "gp_config", "test_csv_path", "kwargs"):
+        assert name in params
+    for m in ("optimize", "fit_gp_model", "optimize_acquisition_function", "collect_initial_points", "run_simulation",
+              "return_best_result", "_save_iteration_data", "suggest", "register", "maximize"):
+        assert callable(getattr(BayesianOptimizer, m))
+
+
+def test_bayesian_py_loop_and_csv_contract(tmp_path):
+    opt = _opt(tmp_path)
+    assert opt.bounds.shape == (2, 5) and opt.bounds.dtype == torch.float64           # Bayesian.py:42
+    best_params, best_disp = opt.optimize()
+    n_total = 12 + 2 * 2
+    assert opt.train_X.shape == (n_total, 5) and opt.train_Y.shape == (n_total, 1)
+    assert float(opt.train_X.min()) >= 0.0 and float(opt.train_X.max()) <= 1.0
+    lines = open(opt.results_file).read().strip().split("\n")
+    assert lines[0] == "n,eta,sigma_y,width,height,x_01,x_02,x_03,x_04,x_05,x_06,x_07,x_08"    # Bayesian7.py:269
+    assert len(lines) == 1 + n_total                                                           # run_optimization.py:26-29
+    row = np.array(lines[1].split(","), dtype=np.float64)
+    assert row.shape == (13,) and len(lines[1].split(",")[0].split(".")[1]) == 16               # %.16f, Bayesian.py:66
+    lo, hi = np.array(DEFAULT_BOUNDS).T
+    assert np.all(row[:5] >= lo - 1e-12) and np.all(row[:5] <= hi + 1e-12)                      # physical units
+    # objective = mean of the 8 displacements, maximised (Bayesian.py:140,98)
+    objs = np.array([np.mean(d) for d in opt.displacements_list])
+    np.testing.assert_allclose(opt.train_Y.reshape(-1).numpy(), objs, rtol=1e-12)
+    assert np.allclose(best_params, opt.original_X[int(objs.argmax())])
+    assert len(best_disp) == 8
+
+
+def test_resume_and_target_total_semantics(tmp_path):
+    opt = _opt(tmp_path, n_batches=0)
+    opt.optimize()
+    assert opt.train_X.shape[0] == 12
+    # resume: rows are reloaded, no new LHS, loop runs until target_total (Bayesian7.py:271-289,635)
+    opt2 = _opt(tmp_path, n_initial_points=0, n_batches=3, batch_size=2, resume=True, target_total=17,
+                svgp_threshold=3000, test_csv_path="validation_set.csv")
+    assert opt2.train_X.shape[0] == 12
+    np.testing.assert_allclose(opt2.train_X.numpy(), opt.train_X.numpy(), atol=1e-12)
+    best_params, best_value = opt2.optimize()
+    assert opt2.train_X.shape[0] == 17 and isinstance(best_value, float)
+    assert len(open(opt2.results_file).read().strip().split("\n")) == 18
+    # without resume the file is truncated (Bayesian.py:56-60)
+    opt3 = _opt(tmp_path, n_initial_points=1, n_batches=0)
+    assert opt3.train_X.shape[0] == 0 and len(open(opt3.results_file).read().strip().split("\n")) == 1
+
+
+def test_resume_tolerates_corrupt_rows_and_legacy_headers(tmp_path):
+    """results/optimization_results2.csv:2386 has a stray space inside a number; two legacy files use disp_* headers."""
+    p = tmp_path / "optimization_results.csv"
+    hdr = "n,eta,sigma_y,width,height," + ",".join(f"disp_{i}" for i in range(1, 9))
+    good = "0.5,100.0,200.0,3.0,4.0," + ",".join(["1.5"] * 8)
+    bad = "0.5,100.0,200.067 7064061164856,3.0,4.0," + ",".join(["1.5"] * 8)
+    p.write_text("\n".join([hdr, good, bad, good]) + "\n")
+    opt = _opt(tmp_path, resume=True, n_initial_points=0, n_batches=0)
+    assert opt.train_X.shape[0] == 2
+    np.testing.assert_allclose(opt.train_Y.numpy().reshape(-1), [1.5, 1.5])
+
+
+def test_simulator_failure_conventions(tmp_path):
+    class Flaky:
+        def __init__(self): self.k = 0
+        def configure_geometry(self, w, h):
+            if not 2.0 <= w <= 7.0: raise ValueError("Width must be between 2.0 and 7.0")
+        def run_simulation(self, n, eta, s):
+            self.k += 1
+            return [None, np.array([1.0, 2.0, 3.0], dtype=np.float32), np.full(8, np.nan), np.arange(10.0)][self.k % 4]
+        def cleanup(self): pass
+    opt = _opt(tmp_path, simulator=Flaky())
+    outs = [opt.run_simulation(np.array([0.5, 1.0, 1.0, 3.0, 3.0])) for _ in range(4)]
+    assert np.array_equal(outs[0], [1, 2, 3, 0, 0, 0, 0, 0])          # short output padded (Bayesian.py:84-85)
+    assert np.array_equal(outs[1], np.zeros(8))                         # NaN -> zeros (Bayesian.py:81-82)
+    assert np.array_equal(outs[2], np.arange(8.0))                      # truncated to 8
+    assert np.array_equal(outs[3], np.zeros(8))                         # None -> zeros
+    assert np.array_equal(opt.run_simulation(np.array([0.5, 1.0, 1.0, 9.0, 3.0])), np.zeros(8))   # ValueError -> zeros
+
+
+def test_cholesky_failure_retries_with_jitter(tmp_path):
+    """Duplicate rows + ~zero noise: fit fails, the class retries with jitter 1e-2 (Bayesian6.py:482-488)."""
+    opt = _opt(tmp_path, gp_config=_cfg(fit_hyperparameters=False, noise=0.0, kernel="rbf", lengthscale=[2.0] * 5))
+    z = np.load(os.path.join(GOLDEN_DIR, "csv_cache_rows.npz"))
+    for i in list(range(60)) + [12, 17]:
+        opt._append_observation(z["params"][i], z["outputs"][i], write=False)
+    gp = opt.fit_gp_model()
+    assert gp.engine.fits == 1 and gp.engine.gp.L.shape[0] == 62      # first attempt raised, second (jitter) succeeded
+    post = gp.posterior(opt.train_X[:3])
+    assert post.mean.shape == (3, 1) and post.variance.shape == (3, 1)
+
+
+def test_large_batch_uses_topk_then_fps(tmp_path):
+    opt = _opt(tmp_path, batch_size=40, n_batches=1, gp_config=_cfg(believer_max_q=4, fit_hyperparameters=False))
+    for x in opt.collect_initial_points():
+        opt.register(x)
+    batch = opt.optimize_acquisition_function(opt.fit_gp_model())
+    assert batch.shape == (40, 5) and batch.dtype == torch.float64
+    assert len({tuple(np.round(b, 12)) for b in batch.numpy()}) == 40     # FPS picks distinct points
+
+
+def test_min_mode_flips_the_model_sign(tmp_path):
+    opt = _opt(tmp_path, n_batches=1, objective_mode="min", objective_index=0)
+    bp, bd = opt.optimize()
+    objs = np.array([d[0] for d in opt.displacements_list])
+    assert np.allclose(bp, opt.original_X[int(objs.argmin())])
+
+
+def test_cached_simulator_duck_type():
+    sim = _sim()
+    with pytest.raises(ValueError):
+        sim.configure_geometry(1.0, 3.0)                               # simulation/taichi.py:35-38
+    sim.configure_geometry(3.0, 4.0)
+    with pytest.raises(ValueError):
+        sim.run_simulation(0.1, 1.0, 1.0)                              # simulation/taichi.py:64-71
+    out = sim.run_simulation(0.5, 100.0, 200.0)
+    assert out.dtype == np.float32 and out.shape == (8,)
+    sim.cleanup()
+    assert sim.cleaned
