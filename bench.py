@@ -270,7 +270,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tpath)).get("dram_bytes_per_candidate") * count     # per launch of this shard
             except Exception:
                 traffic = None
         line = {
