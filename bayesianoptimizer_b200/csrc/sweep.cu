@@ -27,6 +27,7 @@ struct SweepArgs {
     int acq; double best_f, sqrt_beta, min_var;
     int topk; double* part_val; long long* part_idx;
     double* mean_out; double* var_out; double* acq_out;
+    int flags;      // bit1: skip the all-zero 8x8 blocks of diagonal tiles (default on)
 };
 
 // ---- analytic acquisition (botorch.acquisition.analytic semantics) ------
@@ -220,19 +221,45 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     mbar_wait(&full[stage], phase);
                     const double* As = reinterpret_cast<const double*>(smem + stage * SweepSmem::STAGE_BYTES);
                     const double* Bs = As + SW_TILE;
+                    const int kdiag = kc - ib * KCH;                      // >= 0 inside the diagonal tile
+                    if (kdiag < 0 || !(a.flags & 2)) {
 #pragma unroll
-                    for (int k8 = 0; k8 < SW_BK / 8; ++k8) {
-                        double2 b[4];
+                        for (int k8 = 0; k8 < SW_BK / 8; ++k8) {
+                            double2 b[4];
 #pragma unroll
-                        for (int ni = 0; ni < 4; ++ni)
-                            b[ni] = *reinterpret_cast<const double2*>(Bs + (((wn * 4 + ni) * (SW_BK / 8) + k8) * 64 + lane * 2));
+                            for (int ni = 0; ni < 4; ++ni)
+                                b[ni] = *reinterpret_cast<const double2*>(Bs + (((wn * 4 + ni) * (SW_BK / 8) + k8) * 64 + lane * 2));
 #pragma unroll
-                        for (int mi = 0; mi < 8; ++mi) {
-                            const double2 av = *reinterpret_cast<const double2*>(As + (((wm * 8 + mi) * (SW_BK / 8) + k8) * 64 + lane * 2));
+                            for (int mi = 0; mi < 8; ++mi) {
+                                const double2 av = *reinterpret_cast<const double2*>(As + (((wm * 8 + mi) * (SW_BK / 8) + k8) * 64 + lane * 2));
 #pragma unroll
-                            for (int ni = 0; ni < 4; ++ni) {
-                                dmma884(acc[mi][ni][0], acc[mi][ni][1], av.x, b[ni].x);
-                                dmma884(acc[mi][ni][0], acc[mi][ni][1], av.y, b[ni].y);
+                                for (int ni = 0; ni < 4; ++ni) {
+                                    dmma884(acc[mi][ni][0], acc[mi][ni][1], av.x, b[ni].x);
+                                    dmma884(acc[mi][ni][0], acc[mi][ni][1], av.y, b[ni].y);
+                                }
+                            }
+                        }
+                    } else {
+                        // diagonal tile: 8x8 blocks strictly above the diagonal hold zeros -> skip their DMMAs
+#pragma unroll
+                        for (int k8 = 0; k8 < SW_BK / 8; ++k8) {
+                            const int mi_min = kdiag * (SW_BK / 8) + k8 - wm * 8;     // first row block with data
+                            if (mi_min < 8) {
+                                double2 b[4];
+#pragma unroll
+                                for (int ni = 0; ni < 4; ++ni)
+                                    b[ni] = *reinterpret_cast<const double2*>(Bs + (((wn * 4 + ni) * (SW_BK / 8) + k8) * 64 + lane * 2));
+#pragma unroll
+                                for (int mi = 0; mi < 8; ++mi) {
+                                    if (mi >= mi_min) {
+                                        const double2 av = *reinterpret_cast<const double2*>(As + (((wm * 8 + mi) * (SW_BK / 8) + k8) * 64 + lane * 2));
+#pragma unroll
+                                        for (int ni = 0; ni < 4; ++ni) {
+                                            dmma884(acc[mi][ni][0], acc[mi][ni][1], av.x, b[ni].x);
+                                            dmma884(acc[mi][ni][0], acc[mi][ni][1], av.y, b[ni].y);
+                                        }
+                                    }
+                                }
                             }
                         }
                     }
@@ -529,6 +556,7 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     a.n = h->n; a.np = h->np; a.d = h->d; a.hyp = h->hyp;
     a.acq = acq_kind; a.best_f = best_f; a.sqrt_beta = sqrt(beta); a.min_var = min_var;
     a.topk = topk; a.mean_out = mean_dev; a.var_out = var_dev; a.acq_out = acq_dev;
+    { const char* f = getenv("BO_B200_SWEEP_FLAGS"); a.flags = f ? atoi(f) : 2; }
 
     if (N == 0) {
         if (topk > 0) {
