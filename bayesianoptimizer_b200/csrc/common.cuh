@@ -183,15 +183,63 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Matern-5/2 / RBF value from the scaled squared distance
-__device__ __forceinline__ double kernel_value(int kind, double sq, double outputscale) {
-    if (kind == BO_KERNEL_MATERN52) {
+// ---- branch-free FP64 elementary functions for the kernel evaluations --------------------------
+// CUDA's sqrt()/exp() carry slow-path branches that split every kernel evaluation into several basic
+// blocks, so independent evaluations cannot be interleaved and the panel build runs latency-bound.
+// These versions are straight-line code (MUFU seed + Newton / Cody-Waite + Taylor), accurate to ~1-2 ulp.
+
+// sqrt(x) for x >= 0 (returns ~1e-150 for x == 0, which is 0 for every use here)
+__device__ __forceinline__ double sqrt_pos(double x) {
+    const double xs = x + 1e-300;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));      // MUFU.RSQ64H, ~2^-22 relative
+    const double h = 0.5 * xs;
+    y = y * fma(-h, y * y, 1.5);
+    y = y * fma(-h, y * y, 1.5);
+    const double r = xs * y;
+    return fma(0.5 * y, fma(-r, r, xs), r);                        // Heron correction
+}
+
+// exp(-t) for t >= 0; exact zero beyond t = 700 (the true value is below 1e-304)
+__device__ __forceinline__ double exp_neg(double t) {
+    const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52: round-to-nearest-integer trick
+    const double z = fma(-t, 1.4426950408889634074, MAGIC);         // n = rint(-t * log2(e)) in the low word
+    const int n = __double2loint(z);
+    const double nf = z - MAGIC;
+    double f = fma(nf, -6.93147180369123816490e-01, -t);            // f = -t - n ln2 (Cody-Waite, hi part)
+    f = fma(nf, -1.90821492927058770002e-10, f);                    //                          (lo part)
+    double p = 1.6059043836821613e-10;                              // Taylor of exp(f), |f| <= ln2/2, degree 13
+    p = fma(p, f, 2.08767569878681e-09);
+    p = fma(p, f, 2.505210838544172e-08);
+    p = fma(p, f, 2.755731922398589e-07);
+    p = fma(p, f, 2.7557319223985893e-06);
+    p = fma(p, f, 2.48015873015873e-05);
+    p = fma(p, f, 1.984126984126984e-04);
+    p = fma(p, f, 1.388888888888889e-03);
+    p = fma(p, f, 8.333333333333333e-03);
+    p = fma(p, f, 4.1666666666666664e-02);
+    p = fma(p, f, 1.6666666666666666e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));   // * 2^n, n in [-1010, 0]
+    return (t > 700.0) ? 0.0 : r;
+}
+
+// Matern-5/2 / RBF value from the scaled squared distance (KIND known at compile time)
+template <int KIND>
+__device__ __forceinline__ double kernel_value_t(double sq, double outputscale) {
+    if (KIND == BO_KERNEL_MATERN52) {
         const double s5 = 2.23606797749978969640917366873128;
-        double r = sqrt(sq);
-        double p = fma(sq, 5.0 / 3.0, fma(s5, r, 1.0));
-        return outputscale * p * exp(-s5 * r);
+        const double r = sqrt_pos(sq);
+        const double p = fma(sq, 5.0 / 3.0, fma(s5, r, 1.0));
+        return outputscale * p * exp_neg(s5 * r);
     }
-    return outputscale * exp(-0.5 * sq);
+    return outputscale * exp_neg(0.5 * sq);
+}
+__device__ __forceinline__ double kernel_value(int kind, double sq, double outputscale) {
+    return kind == BO_KERNEL_MATERN52 ? kernel_value_t<BO_KERNEL_MATERN52>(sq, outputscale)
+                                      : kernel_value_t<BO_KERNEL_RBF>(sq, outputscale);
 }
 
 // better-than order of the top-k: value desc, index asc

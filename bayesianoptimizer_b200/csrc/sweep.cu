@@ -94,7 +94,7 @@ struct SweepSmem {
     static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
 };
 
-template <int DP>
+template <int DP, int KIND>
 __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem + SweepSmem::OFF_BAR);
@@ -147,34 +147,45 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             }
             double mu0 = 0.0, mu1 = 0.0;
             const int nj8 = a.np >> 3;
-#pragma unroll 2
-            for (int j8 = 0; j8 < nj8; ++j8) {
-                const int j0 = j8 * 8 + q, j1 = j0 + 4;
-                const double2* r0 = reinterpret_cast<const double2*>(a.Xs + (size_t)j0 * BO_MAX_DIM);
-                const double2* r1 = reinterpret_cast<const double2*>(a.Xs + (size_t)j1 * BO_MAX_DIM);
-                double x0[DP], x1[DP];
+            // two 8-row slices per iteration: 8 independent kernel evaluations per lane in flight
+            for (int j8 = 0; j8 < nj8; j8 += 2) {
+                double x[4][DP];                                  // rows j8*8+q, +4, +8, +12
+                double al[4];
 #pragma unroll
-                for (int k = 0; k < DP / 2; ++k) {
-                    double2 t0 = __ldg(r0 + k), t1 = __ldg(r1 + k);
-                    x0[2 * k] = t0.x; x0[2 * k + 1] = t0.y; x1[2 * k] = t1.x; x1[2 * k + 1] = t1.y;
-                }
-                const double a0 = __ldg(a.alpha + j0), a1 = __ldg(a.alpha + j1);
+                for (int r = 0; r < 4; ++r) {
+                    const int j = j8 * 8 + q + 4 * r;
+                    const double2* row = reinterpret_cast<const double2*>(a.Xs + (size_t)j * BO_MAX_DIM);
 #pragma unroll
-                for (int gi = 0; gi < 2; ++gi) {
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < DP; ++k) {
-                        double d0 = xc[gi][k] - x0[k], d1 = xc[gi][k] - x1[k];
-                        s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
+                    for (int k = 0; k < DP / 2; ++k) {
+                        const double2 t = __ldg(row + k);
+                        x[r][2 * k] = t.x; x[r][2 * k + 1] = t.y;
                     }
-                    double2 kv;
-                    kv.x = (j0 < a.n) ? kernel_value(a.hyp.kind, s0, a.hyp.outputscale) : 0.0;
-                    kv.y = (j1 < a.n) ? kernel_value(a.hyp.kind, s1, a.hyp.outputscale) : 0.0;
-                    if (gi == 0) mu0 = fma(kv.x, a0, fma(kv.y, a1, mu0));
-                    else         mu1 = fma(kv.x, a0, fma(kv.y, a1, mu1));
-                    double* dst = panel + (size_t)(j8 >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (j8 & 3)) * 64 + lane * 2);
-                    *reinterpret_cast<double2*>(dst) = kv;
+                    al[r] = __ldg(a.alpha + j);
                 }
+                double kv[2][4];
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        double sq = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DP; ++k) {
+                            const double df = xc[gi][k] - x[r][k];
+                            sq = fma(df, df, sq);
+                        }
+                        const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
+                        kv[gi][r] = (j8 * 8 + q + 4 * r < a.n) ? v : 0.0;
+                    }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { mu0 = fma(kv[0][r], al[r], mu0); mu1 = fma(kv[1][r], al[r], mu1); }
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int jj = j8 + hh;
+                        double* dst = panel + (size_t)(jj >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (jj & 3)) * 64 + lane * 2);
+                        *reinterpret_cast<double2*>(dst) = make_double2(kv[gi][2 * hh], kv[gi][2 * hh + 1]);
+                    }
             }
             mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
             mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
@@ -495,10 +506,12 @@ template <int DP>
 static int launch_sweep(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
+        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
+        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
         attr_set = true;
     }
-    sweep_kernel<DP><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
+    if (a.hyp.kind == BO_KERNEL_MATERN52) sweep_kernel<DP, BO_KERNEL_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
+    else sweep_kernel<DP, BO_KERNEL_RBF><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
