@@ -90,7 +90,8 @@ struct SweepSmem {
     static constexpr int OFF_TKV   = OFF_MU + SW_BN * 8;                // tk_val[64]
     static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;         // tk_idx[64]
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;         // acq[SW_BN]
-    static constexpr int OFF_SOB   = OFF_ACQ + SW_BN * 8;               // dirs[16][30] + shift[16]
+    static constexpr int OFF_CMASK = OFF_ACQ + SW_BN * 8;               // cmask[4]
+    static constexpr int OFF_SOB   = OFF_CMASK + 16;                    // dirs[16][30] + shift[16]
     static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
 };
 
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
     double* tkv     = reinterpret_cast<double*>(smem + SweepSmem::OFF_TKV);
     long long* tki  = reinterpret_cast<long long*>(smem + SweepSmem::OFF_TKI);
     double* acq_s   = reinterpret_cast<double*>(smem + SweepSmem::OFF_ACQ);
+    unsigned* cmask = reinterpret_cast<unsigned*>(smem + SweepSmem::OFF_CMASK);
     uint32_t* dirs  = reinterpret_cast<uint32_t*>(smem + SweepSmem::OFF_SOB);
     uint32_t* shift = dirs + BO_MAX_DIM * BO_SOBOL_BITS;
 
@@ -147,12 +149,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             }
             double mu0 = 0.0, mu1 = 0.0;
             const int nj8 = a.np >> 3;
-            // two 8-row slices per iteration: 8 independent kernel evaluations per lane in flight
-            for (int j8 = 0; j8 < nj8; j8 += 2) {
-                double x[4][DP];                                  // rows j8*8+q, +4, +8, +12
-                double al[4];
+            // PA_SL 8-row slices per iteration: 4 * PA_SL independent kernel evaluations per lane in flight
+            constexpr int PA_SL = 4, PA_R = 2 * PA_SL;
+            for (int j8 = 0; j8 < nj8; j8 += PA_SL) {
+                double x[PA_R][DP];                               // rows j8*8 + q + 4r
+                double al[PA_R];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < PA_R; ++r) {
                     const int j = j8 * 8 + q + 4 * r;
                     const double2* row = reinterpret_cast<const double2*>(a.Xs + (size_t)j * BO_MAX_DIM);
 #pragma unroll
@@ -162,11 +165,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     }
                     al[r] = __ldg(a.alpha + j);
                 }
-                double kv[2][4];
+                double kv[2][PA_R];
 #pragma unroll
                 for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
+                    for (int r = 0; r < PA_R; ++r) {
                         double sq = 0.0;
 #pragma unroll
                         for (int k = 0; k < DP; ++k) {
@@ -177,11 +180,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                         kv[gi][r] = (j8 * 8 + q + 4 * r < a.n) ? v : 0.0;
                     }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { mu0 = fma(kv[0][r], al[r], mu0); mu1 = fma(kv[1][r], al[r], mu1); }
+                for (int r = 0; r < PA_R; ++r) { mu0 = fma(kv[0][r], al[r], mu0); mu1 = fma(kv[1][r], al[r], mu1); }
 #pragma unroll
                 for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
+                    for (int hh = 0; hh < PA_SL; ++hh) {
                         const int jj = j8 + hh;
                         double* dst = panel + (size_t)(jj >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (jj & 3)) * 64 + lane * 2);
                         *reinterpret_cast<double2*>(dst) = make_double2(kv[gi][2 * hh], kv[gi][2 * hh + 1]);
@@ -310,24 +313,34 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                 if (a.acq_out) a.acq_out[li] = v;
             }
             if (!(v == v)) v = -INFINITY;                    // NaN ranks last
-            acq_s[tid] = (li < a.N) ? v : -INFINITY;
+            acq_s[tid] = v;
+            // only candidates that beat the current k-th entry can enter the list (the list only improves)
+            bool beats = false;
+            if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
+            const unsigned m = __ballot_sync(0xffffffffu, beats);
+            if (lane == 0) cmask[warp] = m;
         }
         __syncthreads();
         if (tid == 0 && a.topk > 0) {
             const int K = a.topk;
-            for (int c = 0; c < SW_BN; ++c) {
-                const long long li = blk * SW_BN + c;
-                if (li >= a.N) break;
-                const double v = acq_s[c];
-                const long long gi = a.first_index + li;
-                if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
-                int p = K - 1;
-                while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
-                tkv[p] = v; tki[p] = gi;
+            for (int w = 0; w < SW_BN / 32; ++w) {
+                unsigned m = cmask[w];
+                while (m) {
+                    const int c = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const double v = acq_s[c];
+                    const long long gi = a.first_index + blk * SW_BN + c;
+                    if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
+                    int p = K - 1;
+                    while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
+                    tkv[p] = v; tki[p] = gi;
+                }
             }
         }
-        __syncthreads();
+        // no barrier here: the next block's phase A touches none of tkv/tki/acq_s/cmask, and two barriers
+        // separate this insertion from the next epilogue
     }
+    __syncthreads();
     if (tid < BO_MAX_TOPK && a.part_val) {
         a.part_val[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tkv[tid];
         a.part_idx[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tki[tid];
