@@ -75,7 +75,7 @@ void bo_destroy(bo_handle* h) {
     cudaDeviceSynchronize();
     bo_release_workspace(h);
     if (h->lml_sub) { bo_destroy(h->lml_sub); h->lml_sub = nullptr; }
-    void* ptrs[] = {h->qbuf, h->lml_part, h->Kw, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2,
+    void* ptrs[] = {h->qbuf, h->lml_part, h->Kw, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
                     h->out_stage_val, h->out_stage_idx};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -71,6 +71,7 @@ struct bo_handle {
     double* Lp = nullptr;        // packed L^-1 tiles in DMMA fragment order (sweep A operand)
     double* vec1 = nullptr;      // [cap_np] scratch vectors
     double* vec2 = nullptr;
+    double* vec3 = nullptr;
     int*    info_dev = nullptr;  // pivot status
     int*    info_host = nullptr; // pinned
     // fit plan: every grouped-GEMM launch of the factorisation + inverse for the current np

@@ -7,6 +7,11 @@
 
 namespace bo {
 
+int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st);
+int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st);
+static int trmv_lower_m(bo_handle* h, const double* M, const double* v, double* z, cudaStream_t st);
+static int trmv_lower_t_m(bo_handle* h, const double* M, const double* z, double* out, int accumulate, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------
 // input staging: Xraw (unscaled, padded to BO_MAX_DIM columns), Xs = Xraw * inv_ls, y
 // ------------------------------------------------------------------------------------------
@@ -75,41 +80,72 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
                                                         double* __restrict__ Ainv, int ldi,
                                                         int* __restrict__ info, int pivot_base) {
     __shared__ double S[NB][NB + 1];
-    __shared__ double col[NB];
+    __shared__ double colS[2][NB];
     __shared__ double rdiag[NB];
     const int tid = threadIdx.x;
-    for (int e = tid; e < NB * NB; e += 256) {
-        int i = e / NB, j = e % NB;
-        S[i][j] = (j <= i) ? A[(size_t)i * lda + j] : 0.0;
+    // Right-looking Cholesky with the block held in REGISTERS: thread (ti, tk) of a 16 x 16 grid owns the
+    // 4 x 4 elements (ti + 16x, tk + 16y); per column one shared-memory broadcast of the pivot column and
+    // one barrier (double-buffered), the rank-1 update is 16 register FMAs.
+    const int ti = tid >> 4, tk = tid & 15;
+    double a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = ti + 16 * x, k = tk + 16 * y;
+            a[x][y] = (k <= i) ? A[(size_t)i * lda + k] : 0.0;
+        }
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {            // unrolled: every register index below is static
+#pragma unroll 1
+        for (int jt = 0; jt < 16; ++jt) {
+            const int j = jb * 16 + jt;
+            double* col = colS[j & 1];
+            if (tk == jt) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) col[ti + 16 * x] = a[x][jb];
+            }
+            __syncthreads();
+            double dj = col[j];
+            if (!(dj > 0.0)) {                       // also catches NaN
+                if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+                dj = 1.0;
+            }
+            double rs;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(dj));
+            const double hj = 0.5 * dj;
+            rs = rs * fma(-hj, rs * rs, 1.5);
+            rs = rs * fma(-hj, rs * rs, 1.5);
+            double li[4], lk[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { const int i = ti + 16 * x; li[x] = (i > j) ? col[i] * rs : 0.0; }
+#pragma unroll
+            for (int y = 0; y < 4; ++y) { const int k = tk + 16 * y; lk[y] = (k > j) ? col[k] * rs : 0.0; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    if (y >= jb) a[x][y] = fma(-li[x], lk[y], a[x][y]);      // column groups left of j are final
+            if (tk == jt) {
+                double sj = dj * rs;
+                sj = fma(0.5 * rs, fma(-sj, sj, dj), sj);          // sqrt(dj), Heron-corrected
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = ti + 16 * x;
+                    if (i >= j) a[x][jb] = (i > j) ? li[x] : sj;
+                }
+            }
+        }
     }
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int j = 0; j < NB; ++j) {
-        __syncthreads();
-        double dj = S[j][j];
-        if (!(dj > 0.0)) {                       // also catches NaN
-            if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
-            dj = 1.0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = ti + 16 * x, k = tk + 16 * y;
+            S[i][k] = (k <= i) ? a[x][y] : 0.0;
+            if (k <= i) A[(size_t)i * lda + k] = a[x][y];
         }
-        const double s = sqrt(dj);
-        const double inv = 1.0 / s;
-        if (tid < NB) {
-            const int i = tid;
-            double v = (i > j) ? S[i][j] * inv : (i == j ? s : 0.0);
-            col[i] = v;
-            if (i >= j) S[i][j] = v;
-        }
-        __syncthreads();
-        // rank-1 update of the trailing lower triangle
-        for (int i = j + 1 + ty; i < NB; i += 16) {
-            const double li = col[i];
-            for (int k = j + 1 + tx; k <= i; k += 16) S[i][k] = fma(-li, col[k], S[i][k]);
-        }
-    }
     __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-        int i = e / NB, j = e % NB;
-        if (j <= i) A[(size_t)i * lda + j] = S[i][j];
-    }
     if (tid < NB) rdiag[tid] = 1.0 / S[tid][tid];
     __syncthreads();
     // inverse by forward substitution: 4 threads per column c, thread q owns rows i with i % 4 == q
@@ -134,7 +170,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 vectors: triangular mat-vecs with the explicit inverse and the Gram mat-vec for refinement
+// K3 vectors: triangular mat-vecs with the explicit inverse / the factor (alpha + its refinement)
 // ------------------------------------------------------------------------------------------
 __global__ void resid_init_kernel(const double* __restrict__ y, int n, int np, double mean, double* __restrict__ r) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,15 +190,20 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
     if (lane == 0) z[row] = s;
 }
 
-// out[j] (+)= sum_{i>=j} Li[i][j] z[i]   (block per 32 columns, 8 row lanes)
+// out[j] (+)= sum_{i>=j} Li[i][j] z[i]: block (x = 32 columns, y = row split), partial sums per split, then a
+// deterministic reduction over the splits
+constexpr int TRMVT_SPLITS = 16;
 __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restrict__ Li, int ld, int np,
-                                                           const double* __restrict__ z, double* __restrict__ out,
-                                                           int accumulate) {
+                                                           const double* __restrict__ z, double* __restrict__ part) {
     __shared__ double red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + tx;
+    const int j0 = blockIdx.x * 32, j = j0 + tx;
+    // rows j0 .. np split into TRMVT_SPLITS contiguous chunks (multiples of 8)
+    const int rows = np - j0;
+    const int chunk = ((rows + TRMVT_SPLITS - 1) / TRMVT_SPLITS + 7) & ~7;
+    const int r0 = j0 + blockIdx.y * chunk, r1 = min(np, r0 + chunk);
     double s = 0.0;
-    for (int i = blockIdx.x * 32 + ty; i < np; i += 8)
+    for (int i = r0 + ty; i < r1; i += 8)
         if (i >= j) s = fma(Li[(size_t)i * ld + j], z[i], s);
     red[ty][tx] = s;
     __syncthreads();
@@ -170,40 +211,16 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restr
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][tx];
-        out[j] = accumulate ? out[j] + t : t;
+        part[(size_t)blockIdx.y * np + j] = t;
     }
 }
-
-// r2[i] = r[i] - sum_j Khat[i][j] a[j]   (one warp per row; K recomputed from the scaled inputs)
-template <int DP>
-__global__ void __launch_bounds__(256) gram_residual_kernel(const double* __restrict__ Xs, int n, int np, Hyper hyp,
-                                                            const double* __restrict__ a, const double* __restrict__ r,
-                                                            double* __restrict__ r2) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= np) return;
-    if (row >= n) { if (lane == 0) r2[row] = 0.0; return; }
-    double xi[DP];
+__global__ void trmv_reduce_kernel(const double* __restrict__ part, int np, double* __restrict__ out, int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < DP; ++k) xi[k] = Xs[(size_t)row * BO_MAX_DIM + k];
-    double s = 0.0;
-    for (int j = lane; j < n; j += 32) {
-        double kv;
-        if (j == row) {
-            kv = hyp.outputscale + hyp.noise + hyp.jitter;
-        } else {
-            double sq = 0.0;
-#pragma unroll
-            for (int k = 0; k < DP; ++k) {
-                double df = xi[k] - Xs[(size_t)j * BO_MAX_DIM + k];
-                sq = fma(df, df, sq);
-            }
-            kv = kernel_value(hyp.kind, sq, hyp.outputscale);
-        }
-        s = fma(kv, a[j], s);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) r2[row] = r[row] - s;
+    for (int s = 0; s < TRMVT_SPLITS; ++s) t += part[(size_t)s * np + j];
+    out[j] = accumulate ? out[j] + t : t;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -346,7 +363,7 @@ static int build_plan(bo_handle* h, cudaStream_t st) {
 // capacity management
 // ------------------------------------------------------------------------------------------
 static void free_fit(bo_handle* h) {
-    double** ptrs[] = {&h->Xs, &h->Xraw, &h->yv, &h->alpha, &h->Lm, &h->Li, &h->Tw, &h->Lp, &h->vec1, &h->vec2};
+    double** ptrs[] = {&h->Xs, &h->Xraw, &h->yv, &h->alpha, &h->Lm, &h->Li, &h->Tw, &h->Lp, &h->vec1, &h->vec2, &h->vec3};
     for (double** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
     h->cap_np = 0;
     h->plan_np = -1;
@@ -359,19 +376,19 @@ int ensure_capacity(bo_handle* h, int np, cudaStream_t st) {
     BO_CUDA(h, cudaStreamSynchronize(st));
     // keep the old state to preserve a fitted model across a growth (append path)
     bo_handle old = *h;
-    h->Xs = h->Xraw = h->yv = h->alpha = h->Lm = h->Li = h->Tw = h->Lp = h->vec1 = h->vec2 = nullptr;
+    h->Xs = h->Xraw = h->yv = h->alpha = h->Lm = h->Li = h->Tw = h->Lp = h->vec1 = h->vec2 = h->vec3 = nullptr;
     const size_t c = (size_t)cap;
     const size_t packed = (c / SW_BM) * (c / SW_BM + 1) / 2 * (SW_BM / SW_BK) * SW_TILE;
     struct { double** p; size_t elems; } reqs[] = {
         {&h->Xs, c * BO_MAX_DIM}, {&h->Xraw, c * BO_MAX_DIM}, {&h->yv, c}, {&h->alpha, c},
-        {&h->Lm, c * c}, {&h->Li, c * c}, {&h->Tw, c * c / 4 + 64}, {&h->Lp, packed},
-        {&h->vec1, c}, {&h->vec2, c}};
+        {&h->Lm, c * c}, {&h->Li, c * c}, {&h->Tw, c * c / 4 + 16 * c + 64}, {&h->Lp, packed},
+        {&h->vec1, c}, {&h->vec2, c}, {&h->vec3, c}};
     for (auto& r : reqs) {
         cudaError_t e = cudaMalloc(r.p, r.elems * sizeof(double));
         if (e != cudaSuccess) {
             for (auto& r2 : reqs) { if (*r2.p) cudaFree(*r2.p); *r2.p = nullptr; }
             h->Xs = old.Xs; h->Xraw = old.Xraw; h->yv = old.yv; h->alpha = old.alpha; h->Lm = old.Lm;
-            h->Li = old.Li; h->Tw = old.Tw; h->Lp = old.Lp; h->vec1 = old.vec1; h->vec2 = old.vec2;
+            h->Li = old.Li; h->Tw = old.Tw; h->Lp = old.Lp; h->vec1 = old.vec1; h->vec2 = old.vec2; h->vec3 = old.vec3;
             h->err = std::string("cudaMalloc failed growing capacity: ") + cudaGetErrorString(e);
             cudaGetLastError();
             return BO_E_NOMEM;
@@ -393,7 +410,7 @@ int ensure_capacity(bo_handle* h, int np, cudaStream_t st) {
         const size_t oldpacked = ((size_t)old.np / SW_BM) * (old.np / SW_BM + 1) / 2 * (SW_BM / SW_BK) * SW_TILE;
         BO_CUDA(h, cudaMemcpy(h->Lp, old.Lp, oldpacked * 8, cudaMemcpyDeviceToDevice));
     }
-    double* olds[] = {old.Xs, old.Xraw, old.yv, old.alpha, old.Lm, old.Li, old.Tw, old.Lp, old.vec1, old.vec2};
+    double* olds[] = {old.Xs, old.Xraw, old.yv, old.alpha, old.Lm, old.Li, old.Tw, old.Lp, old.vec1, old.vec2, old.vec3};
     for (double* p : olds) if (p) cudaFree(p);
     return 0;
 }
@@ -405,34 +422,32 @@ static int launch_gram(bo_handle* h, cudaStream_t st) {
     BO_LAUNCH_CHECK(h);
     return 0;
 }
-template <int DP>
-static int launch_resid(bo_handle* h, const double* a, const double* r, double* r2, cudaStream_t st) {
-    gram_residual_kernel<DP><<<h->np / 8, 256, 0, st>>>(h->Xs, h->n, h->np, h->hyp, a, r, r2);
-    BO_LAUNCH_CHECK(h);
-    return 0;
-}
-
 #define BO_DISPATCH_DP(dp, fn, ...)                                   \
     ((dp) == 2 ? fn<2>(__VA_ARGS__) : (dp) == 4 ? fn<4>(__VA_ARGS__) :  \
      (dp) == 6 ? fn<6>(__VA_ARGS__) : (dp) == 8 ? fn<8>(__VA_ARGS__) :  \
      (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
 
-// alpha = Khat^-1 r via the explicit inverse, plus one iterative-refinement step
+__global__ void sub_vec_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
+// alpha = (L L^T)^-1 r via the explicit inverse, plus one step of iterative refinement against the factor:
+//   alpha0 = Li^T (Li r) ; r2 = r - L (L^T alpha0) ; alpha = alpha0 + Li^T (Li r2)
+// (four HBM-bound triangular mat-vecs; makes alpha as accurate as a backward-stable cho_solve)
 static int solve_alpha(bo_handle* h, cudaStream_t st) {
-    const int np = h->np, ld = h->cap_np;
-    resid_init_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->yv, h->n, np, h->hyp.mean, h->vec1);
+    const int np = h->np;
+    int rc;
+    resid_init_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->yv, h->n, np, h->hyp.mean, h->vec1);      // vec1 = r
     BO_LAUNCH_CHECK(h);
-    trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->Li, ld, np, h->vec1, h->vec2);
+    if ((rc = trmv_lower_m(h, h->Li, h->vec1, h->vec2, st))) return rc;                              // vec2 = Li r
+    if ((rc = trmv_lower_t_m(h, h->Li, h->vec2, h->alpha, 0, st))) return rc;                        // alpha0
+    if ((rc = trmv_lower_t_m(h, h->Lm, h->alpha, h->vec2, 0, st))) return rc;                        // vec2 = L^T alpha0
+    if ((rc = trmv_lower_m(h, h->Lm, h->vec2, h->vec3, st))) return rc;                              // vec3 = L vec2
+    sub_vec_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->vec1, h->vec3, np, h->vec2);                 // vec2 = r2
     BO_LAUNCH_CHECK(h);
-    trmv_lower_t_kernel<<<np / 32, 256, 0, st>>>(h->Li, ld, np, h->vec2, h->alpha, 0);
-    BO_LAUNCH_CHECK(h);
-    // refinement: r2 = r - Khat alpha ; alpha += Li^T (Li r2)
-    int rc = BO_DISPATCH_DP(h->dp, launch_resid, h, h->alpha, h->vec1, h->vec2, st);
-    if (rc) return rc;
-    trmv_lower_kernel<<<np / 8, 256, 0, st>>>(h->Li, ld, np, h->vec2, h->vec1);
-    BO_LAUNCH_CHECK(h);
-    trmv_lower_t_kernel<<<np / 32, 256, 0, st>>>(h->Li, ld, np, h->vec1, h->alpha, 1);
-    BO_LAUNCH_CHECK(h);
+    if ((rc = trmv_lower_m(h, h->Li, h->vec2, h->vec3, st))) return rc;
+    if ((rc = trmv_lower_t_m(h, h->Li, h->vec3, h->alpha, 1, st))) return rc;
     return 0;
 }
 
@@ -475,15 +490,21 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
     return 0;
 }
 
-int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st) {
-    trmv_lower_kernel<<<h->np / 8, 256, 0, st>>>(h->Li, h->cap_np, h->np, v, z);
+static int trmv_lower_m(bo_handle* h, const double* M, const double* v, double* z, cudaStream_t st) {
+    trmv_lower_kernel<<<h->np / 8, 256, 0, st>>>(M, h->cap_np, h->np, v, z);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
-int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st) {
-    trmv_lower_t_kernel<<<h->np / 32, 256, 0, st>>>(h->Li, h->cap_np, h->np, z, out, accumulate);
+static int trmv_lower_t_m(bo_handle* h, const double* M, const double* z, double* out, int accumulate, cudaStream_t st) {
+    trmv_lower_t_kernel<<<dim3(h->np / 32, TRMVT_SPLITS), 256, 0, st>>>(M, h->cap_np, h->np, z, h->Tw);
+    BO_LAUNCH_CHECK(h);
+    trmv_reduce_kernel<<<(h->np + 255) / 256, 256, 0, st>>>(h->Tw, h->np, out, accumulate);
     BO_LAUNCH_CHECK(h);
     return 0;
+}
+int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st) { return trmv_lower_m(h, h->Li, v, z, st); }
+int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st) {
+    return trmv_lower_t_m(h, h->Li, z, out, accumulate, st);
 }
 
 int pack_row_block(bo_handle* h, int ib, cudaStream_t st) {
