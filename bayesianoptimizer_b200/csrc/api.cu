@@ -10,6 +10,7 @@ int acq_grad_impl(bo_handle* h, int acq_kind, double best_f, double beta, double
 int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
                 const double* starts_dev, int k, int iters, double* x_dev, double* val_dev, cudaStream_t st);
 int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st);
+int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops);
 int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st);
 int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
              const double* theta_host, int R, double* lml_host, double* grad_host, int* status_host,
@@ -66,6 +67,7 @@ int bo_release_workspace(bo_handle* h) {
     h->panel = nullptr; h->panel_bytes = 0;
     if (h->cand_stage) cudaFree(h->cand_stage);
     h->cand_stage = nullptr; h->cand_stage_bytes = 0;
+    lml_release(h);
     return 0;
 }
 
@@ -74,8 +76,8 @@ void bo_destroy(bo_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     bo_release_workspace(h);
-    if (h->lml_sub) { bo_destroy(h->lml_sub); h->lml_sub = nullptr; }
-    void* ptrs[] = {h->qbuf, h->lml_part, h->Kw, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
+    lml_release(h);
+    void* ptrs[] = {h->qbuf, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
                     h->out_stage_val, h->out_stage_idx};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -88,7 +90,7 @@ void bo_destroy(bo_handle* h) {
 
 const char* bo_last_error(const bo_handle* h) { return h ? h->err.c_str() : "null handle"; }
 int bo_num_obs(const bo_handle* h) { return (h && h->fitted) ? h->n : 0; }
-int64_t bo_launch_count(const bo_handle* h) { return h ? h->launches + (h->lml_sub ? h->lml_sub->launches : 0) : 0; }
+int64_t bo_launch_count(const bo_handle* h) { return h ? h->launches : 0; }
 
 int bo_fit(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d, int32_t kernel_kind,
            const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
@@ -203,6 +205,11 @@ int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, 
 int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_host) {
     if (!h || !tflops_host) return BO_E_INVALID;
     return fp64_peak_impl(h, use_dmma, seconds, tflops_host);
+}
+
+int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, int32_t reps, double* tflops_host) {
+    if (!h || !tflops_host || reps < 1) return BO_E_INVALID;
+    return gemm_probe_impl(h, m, n, k, cfg, reps, tflops_host);
 }
 
 double bo_last_sweep_ms(bo_handle* h) {

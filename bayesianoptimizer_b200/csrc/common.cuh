@@ -6,6 +6,8 @@
 #include <string.h>
 #include <math.h>
 #include <vector>
+#include <algorithm>
+#include <new>
 #include <string>
 
 #include "../../include/bo_b200.h"
@@ -95,9 +97,7 @@ struct bo_handle {
 
     // K5-K7 workspaces
     double* qbuf = nullptr; size_t qbuf_elems = 0;      // refinement / acq-grad scratch
-    bo_handle* lml_sub = nullptr;                       // private engine for the batched LML restarts
-    double* lml_part = nullptr; size_t lml_part_elems = 0;
-    double* Kw = nullptr; size_t Kw_elems = 0;          // K^-1 of the current restart [np, cap_np]
+    void* lml_batch = nullptr;                          // bo::LmlBatch: slot workspaces of the batched LML restarts (lml.cuh)
 };
 
 namespace bo {
@@ -265,6 +265,7 @@ int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* i
 int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);
 int refit_factor(bo_handle* h, cudaStream_t st);
 int create_handle(bo_handle** out, int device);
+void lml_release(bo_handle* h);
 int pack_row_block(bo_handle* h, int ib, cudaStream_t st);
 int run_gemm_once(bo_handle* h, const GemmProblem* probs_host, int count, int tiles, int cfg, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv
 }  // namespace bo

@@ -500,157 +500,4 @@ int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, c
     return 0;
 }
 
-// =================================================================================================
-// K7: batched exact log marginal likelihood + gradient over R hyper-parameter restarts
-// (ExactMarginalLogLikelihood closure of fit_gpytorch_mll, optimization/Bayesian.py:92-93).
-// =================================================================================================
-// per 32x32 tile of the strict lower triangle (+ diagonal): partial sums of
-//   W_ij dK_ij/dlog l_k (k < DP), W_ij K_ij, and on the diagonal W_ii ; also log L_ii and r_i alpha_i
-template <int DP>
-__global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha,
-                                                            const double* __restrict__ Kinv, const double* __restrict__ Lm,
-                                                            const double* __restrict__ yv, int ld, int n, Hyper hyp,
-                                                            double* __restrict__ part /*[tiles][DP+4]*/) {
-    __shared__ double red[8];
-    const int bj = blockIdx.x, bi = blockIdx.y;
-    const int tile = bi * gridDim.x + bj;
-    double acc[DP + 4];
-#pragma unroll
-    for (int k = 0; k < DP + 4; ++k) acc[k] = 0.0;
-    if (bj <= bi) {
-        const int j = bj * 32 + (threadIdx.x & 31);
-        double xj[DP];
-#pragma unroll
-        for (int k = 0; k < DP; ++k) xj[k] = (j < n) ? Xs[(size_t)j * BO_MAX_DIM + k] : 0.0;
-        const double aj = (j < n) ? alpha[j] : 0.0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int i = bi * 32 + (threadIdx.x >> 5) + r * 8;
-            if (i >= n || j >= n || j > i) continue;
-            const double w = alpha[i] * aj - Kinv[(size_t)i * ld + j];
-            if (i == j) {
-                acc[DP + 1] += w;                                   // trace(W)
-                acc[DP + 2] += log(Lm[(size_t)i * ld + i]);         // log det / 2
-                acc[DP + 3] += (yv[i] - hyp.mean) * alpha[i];       // quadratic form
-                continue;
-            }
-            double sq = 0.0, df2[DP];
-#pragma unroll
-            for (int k = 0; k < DP; ++k) {
-                const double df = Xs[(size_t)i * BO_MAX_DIM + k] - xj[k];
-                df2[k] = df * df;
-                sq += df2[k];
-            }
-            double kval, G;
-            if (hyp.kind == BO_KERNEL_MATERN52) {
-                const double s5 = 2.23606797749978969640917366873128;
-                const double rr = sqrt(sq), e = exp(-s5 * rr);
-                kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, rr, 1.0)) * e;
-                G = hyp.outputscale * (5.0 / 3.0) * fma(s5, rr, 1.0) * e;
-            } else {
-                kval = hyp.outputscale * exp(-0.5 * sq);
-                G = kval;
-            }
-            const double wg = w * G;
-#pragma unroll
-            for (int k = 0; k < DP; ++k) acc[k] = fma(wg, df2[k], acc[k]);
-            acc[DP] = fma(w, kval, acc[DP]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < DP + 4; ++k) {
-        const double t = block_sum_256(acc[k], red);
-        if (threadIdx.x == 0) part[(size_t)tile * (DP + 4) + k] = t;
-    }
-}
-
-// deterministic final reduction: one block sums the tile partials column by column
-template <int DP>
-__global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restrict__ part, int tiles, int n, int d, Hyper hyp,
-                                                         double* __restrict__ out /*[d+3]: lml, grad[d+2]*/) {
-    __shared__ double red[8];
-    double tot[DP + 4];
-#pragma unroll
-    for (int k = 0; k < DP + 4; ++k) {
-        double s = 0.0;
-        for (int t = threadIdx.x; t < tiles; t += 256) s += part[(size_t)t * (DP + 4) + k];
-        tot[k] = block_sum_256(s, red);
-    }
-    if (threadIdx.x != 0) return;
-    const double trW = tot[DP + 1], logdet_half = tot[DP + 2], quad = tot[DP + 3];
-    out[0] = -0.5 * quad - logdet_half - 0.5 * n * 1.83787706640934548356;        // log(2 pi)
-    for (int k = 0; k < d; ++k) out[1 + k] = tot[k];                               // pairs i>j count twice in 1/2 sum
-    out[1 + d] = tot[DP] + 0.5 * hyp.outputscale * trW;                            // d/d log outputscale
-    out[2 + d] = 0.5 * hyp.noise * trW;                                            // d/d log noise
-}
-
-template <int DP>
-static int launch_lml_grad(bo_handle* s, double* part, double* out, cudaStream_t st) {
-    const int nt = s->np / 32;
-    lml_grad_tile_kernel<DP><<<dim3(nt, nt), 256, 0, st>>>(s->Xs, s->alpha, s->Kw, s->Lm, s->yv, s->cap_np, s->n, s->hyp, part);
-    BO_LAUNCH_CHECK(s);
-    lml_reduce_kernel<DP><<<1, 256, 0, st>>>(part, nt * nt, s->n, s->d, s->hyp, out);
-    BO_LAUNCH_CHECK(s);
-    return 0;
-}
-
-int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
-             const double* theta_host, int R, double* lml_host, double* grad_host, int* status_host, cudaStream_t st) {
-    if (!X_dev || !y_dev || !theta_host || !lml_host || !grad_host || !status_host || n < 1 || d < 1 || R < 1)
-        return fail(h, BO_E_INVALID, "bo_lml_grad_batched: bad argument");
-    if (d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_lml_grad_batched: d exceeds BO_MAX_DIM");
-    BO_CUDA(h, cudaSetDevice(h->device));
-    int rc;
-    if (!h->lml_sub && (rc = create_handle(&h->lml_sub, h->device))) return fail(h, rc, "bo_lml_grad_batched: cannot create the restart engine");
-    bo_handle* s = h->lml_sub;
-    const int np = round_up(n, PAD);
-    const int dp = pad_dim(d);
-    const size_t part_elems = (size_t)(np / 32) * (np / 32) * (dp + 4) + (size_t)(BO_MAX_DIM + 3);
-    if (part_elems > h->lml_part_elems) {
-        if (h->lml_part) cudaFree(h->lml_part);
-        h->lml_part = nullptr; h->lml_part_elems = 0;
-        BO_CUDA(h, cudaMalloc(&h->lml_part, part_elems * sizeof(double)));
-        h->lml_part_elems = part_elems;
-    }
-    double* out_dev = h->lml_part + (size_t)(np / 32) * (np / 32) * (dp + 4);
-    std::vector<double> out(d + 3);
-    for (int r = 0; r < R; ++r) {
-        const double* th = theta_host + (size_t)r * (d + 2);
-        double ls[BO_MAX_DIM];
-        for (int k = 0; k < d; ++k) ls[k] = exp(th[k]);
-        const double s2 = exp(th[d]), noise = exp(th[d + 1]);
-        rc = fit_impl(s, X_dev, y_dev, n, d, kind, ls, s2, noise, mean, 0.0, st);
-        if (rc < 0) { h->err = "bo_lml_grad_batched: " + s->err; return rc; }
-        status_host[r] = rc;
-        if (rc > 0) {
-            lml_host[r] = -INFINITY;
-            for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = 0.0;
-            continue;
-        }
-        // K^-1 = L^-T L^-1 (lower tiles) on the DMMA path
-        {
-            const int ld = s->cap_np;
-            const size_t need = (size_t)np * ld;
-            if (need > s->Kw_elems) {
-                if (s->Kw) cudaFree(s->Kw);
-                s->Kw = nullptr; s->Kw_elems = 0;
-                BO_CUDA(h, cudaMalloc(&s->Kw, need * sizeof(double)));
-                s->Kw_elems = need;
-            }
-            GemmProblem p{};
-            p.A = s->Li; p.B = s->Li; p.C = s->Kw; p.M = np; p.N = np; p.K = np; p.lda = ld; p.ldb = ld; p.ldc = ld;
-            p.alpha = 1.0; p.beta = 0.0; p.transB = 0; p.mode = GEMM_TRANS_A | GEMM_LOWER_C | GEMM_K_FROM_MAX;
-            const int tile = (np % 128 == 0 && (long)(np / 128) * (np / 128 + 1) / 2 >= s->sm_count) ? 128 : 64;
-            p.tiles_n = np / tile; p.tile_begin = 0; p.tile_end = (np / tile) * (np / tile);
-            if ((rc = run_gemm_once(s, &p, 1, p.tile_end, tile == 128 ? 1 : 0, st))) { h->err = s->err; return rc; }
-        }
-        if ((rc = BO_DISPATCH_DP(s->dp, launch_lml_grad, s, h->lml_part, out_dev, st))) { h->err = s->err; return rc; }
-        BO_CUDA(h, cudaMemcpyAsync(out.data(), out_dev, (d + 3) * sizeof(double), cudaMemcpyDeviceToHost, st));
-        BO_CUDA(h, cudaStreamSynchronize(st));
-        lml_host[r] = out[0];
-        for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = out[1 + k];
-    }
-    return 0;
-}
-
 }  // namespace bo

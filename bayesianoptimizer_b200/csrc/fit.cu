@@ -42,8 +42,8 @@ __global__ void rescale_inputs_kernel(int np, int d, Hyper hyp, const double* __
 // K1: Gram builder, lower triangle of K = k(X,X) + (noise + jitter) I, identity on the padding
 // ------------------------------------------------------------------------------------------
 template <int DP>
-__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs, int n, int np, int ld,
-                                                   Hyper hyp, double* __restrict__ K) {
+__device__ __forceinline__ void gram_body(const double* __restrict__ Xs, int n, int np, int ld,
+                                          const Hyper& hyp, double* __restrict__ K) {
     // block = 32 (cols) x 8 (rows) threads, tile 32 x 32
     const int j = blockIdx.x * 32 + threadIdx.x;
     const int i0 = blockIdx.y * 32;
@@ -73,12 +73,36 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs
     }
 }
 
+template <int DP>
+__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs, int n, int np, int ld,
+                                                   Hyper hyp, double* __restrict__ K) {
+    gram_body<DP>(Xs, n, np, ld, hyp, K);
+}
+// per-slot variant for the batched LML restarts: blockIdx.z = slot, hyper-parameters from a device array
+template <int DP>
+__global__ void __launch_bounds__(256) gram_batched_kernel(const double* __restrict__ Xs, int n, int np, int ld,
+                                                           const Hyper* __restrict__ hyps, double* __restrict__ K) {
+    const size_t s = blockIdx.z;
+    gram_body<DP>(Xs + s * np * BO_MAX_DIM, n, np, ld, hyps[s], K + s * np * ld);
+}
+__global__ void rescale_batched_kernel(int np, int d, const Hyper* __restrict__ hyps, const double* __restrict__ Xraw,
+                                       double* __restrict__ Xs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const Hyper& hy = hyps[blockIdx.z];
+    double* dst = Xs + ((size_t)blockIdx.z * np + i) * BO_MAX_DIM;
+#pragma unroll
+    for (int k = 0; k < BO_MAX_DIM; ++k) dst[k] = (k < d) ? Xraw[(size_t)i * BO_MAX_DIM + k] * hy.inv_ls[k] : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------
 // K2 leaf: Cholesky of one NB x NB diagonal block in shared memory + its explicit inverse
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, int lda,
                                                         double* __restrict__ Ainv, int ldi,
-                                                        int* __restrict__ info, int pivot_base) {
+                                                        int* __restrict__ info, int pivot_base,
+                                                        size_t slot_stride) {
+    A += blockIdx.x * slot_stride; Ainv += blockIdx.x * slot_stride; info += blockIdx.x;     // one block per slot
     __shared__ double S[NB][NB + 1];
     __shared__ double colS[2][NB];
     __shared__ double rdiag[NB];
@@ -174,12 +198,15 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
 // ------------------------------------------------------------------------------------------
 __global__ void resid_init_kernel(const double* __restrict__ y, int n, int np, double mean, double* __restrict__ r) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    r += (size_t)blockIdx.z * np;                       // slot (y is shared by all slots)
     if (i < np) r[i] = (i < n) ? y[i] - mean : 0.0;
 }
 
 // z[i] = sum_{j<=i} Li[i][j] v[j]   (one warp per row)
 __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ Li, int ld, int np,
-                                                         const double* __restrict__ v, double* __restrict__ z) {
+                                                         const double* __restrict__ v, double* __restrict__ z,
+                                                         size_t mat_stride) {
+    Li += blockIdx.z * mat_stride; v += (size_t)blockIdx.z * np; z += (size_t)blockIdx.z * np;      // slot
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= np) return;
     const double* a = Li + (size_t)row * ld;
@@ -194,7 +221,9 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
 // deterministic reduction over the splits
 constexpr int TRMVT_SPLITS = 16;
 __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restrict__ Li, int ld, int np,
-                                                           const double* __restrict__ z, double* __restrict__ part) {
+                                                           const double* __restrict__ z, double* __restrict__ part,
+                                                           size_t mat_stride) {
+    Li += blockIdx.z * mat_stride; z += (size_t)blockIdx.z * np; part += (size_t)blockIdx.z * TRMVT_SPLITS * np;   // slot
     __shared__ double red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j0 = blockIdx.x * 32, j = j0 + tx;
@@ -215,6 +244,7 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restr
     }
 }
 __global__ void trmv_reduce_kernel(const double* __restrict__ part, int np, double* __restrict__ out, int accumulate) {
+    part += (size_t)blockIdx.z * TRMVT_SPLITS * np; out += (size_t)blockIdx.z * np;                    // slot
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= np) return;
     double t = 0.0;
@@ -263,6 +293,8 @@ int gemm_init(bo_handle* h) {
                                     (int)GemmSmem<64, 64>::BYTES));
     BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)GemmSmem<128, 128>::BYTES));
+    BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)GemmSmem<128, 64>::BYTES));
     return 0;
 }
 
@@ -284,8 +316,10 @@ static void plan_push(bo_handle* h, const GemmBatch& b) {
 
 // pick the tile: 128 when every dimension allows it and the launch still fills the GPU
 static int pick_tile(int sm, std::initializer_list<int> dims, long tiles128) {
-    for (int v : dims) if (v % 128) return 64;
-    return tiles128 >= sm ? 128 : 64;
+    // measured with bo_gemm_probe on B200 (tools/gemm_probe.py): 64x64 tiles (3 CTAs/SM hide the prologue and
+    // the C read-modify-write) beat 128x128 and 128x64 at every K from 64 to 4096 -> always 64
+    (void)sm; (void)dims; (void)tiles128;
+    return 64;
 }
 
 // Build the launch plan of the factorisation (2 GEMM launches per block column) followed by the
@@ -329,7 +363,7 @@ static int build_plan(bo_handle* h, cudaStream_t st) {
             if (p % 128 || q % 128 || (nd.lo * NB) % 128) all128 = false;
             t128 += (long)(p / 128) * (q / 128);
         }
-        const int tile = (all128 && t128 >= h->sm_count) ? 128 : 64;
+        const int tile = pick_tile(h->sm_count, {all128 ? 128 : 64}, t128);
         GemmBatch g1(tile), g2(tile);
         size_t toff = 0;
         for (const Node& nd : nodes) if (nd.depth == depth) {
@@ -428,6 +462,7 @@ static int launch_gram(bo_handle* h, cudaStream_t st) {
      (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
 
 __global__ void sub_vec_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out) {
+    a += (size_t)blockIdx.z * n; b += (size_t)blockIdx.z * n; out += (size_t)blockIdx.z * n;          // slot
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] - b[i];
 }
@@ -461,7 +496,7 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
     for (int kb = 0; kb < nb; ++kb) {
         double* D = h->Lm + (size_t)kb * NB * ld + kb * NB;
         double* Dinv = h->Li + (size_t)kb * NB * ld + kb * NB;
-        potf2_inv_kernel<<<1, 256, 0, st>>>(D, ld, Dinv, ld, h->info_dev, kb * NB);
+        potf2_inv_kernel<<<1, 256, 0, st>>>(D, ld, Dinv, ld, h->info_dev, kb * NB, 0);
         BO_LAUNCH_CHECK(h);
         if (kb + 1 < nb) {
             if ((rc = gemm_launch(h, h->plan_launches[2 * kb], st))) return rc;
@@ -491,12 +526,12 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
 }
 
 static int trmv_lower_m(bo_handle* h, const double* M, const double* v, double* z, cudaStream_t st) {
-    trmv_lower_kernel<<<h->np / 8, 256, 0, st>>>(M, h->cap_np, h->np, v, z);
+    trmv_lower_kernel<<<h->np / 8, 256, 0, st>>>(M, h->cap_np, h->np, v, z, 0);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
 static int trmv_lower_t_m(bo_handle* h, const double* M, const double* z, double* out, int accumulate, cudaStream_t st) {
-    trmv_lower_t_kernel<<<dim3(h->np / 32, TRMVT_SPLITS), 256, 0, st>>>(M, h->cap_np, h->np, z, h->Tw);
+    trmv_lower_t_kernel<<<dim3(h->np / 32, TRMVT_SPLITS), 256, 0, st>>>(M, h->cap_np, h->np, z, h->Tw, 0);
     BO_LAUNCH_CHECK(h);
     trmv_reduce_kernel<<<(h->np + 255) / 256, 256, 0, st>>>(h->Tw, h->np, out, accumulate);
     BO_LAUNCH_CHECK(h);
@@ -561,5 +596,38 @@ int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     BO_LAUNCH_CHECK(h);
     return refit_factor(h, st);
 }
+
+// GEMM throughput probe (development / roofline evidence for the fit's trailing updates): C = A * B^T, square tiles
+int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops) {
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const int bm = cfg == 0 ? 64 : 128, bn = cfg == 1 ? 128 : 64;
+    if (m % bm || n % bn || k % 16 || m < bm || n < bn || k < 16) return fail(h, BO_E_INVALID, "bo_gemm_probe: sizes must be tile multiples");
+    double *A, *B, *C; GemmProblem* pd;
+    BO_CUDA(h, cudaMalloc(&A, (size_t)m * k * 8)); BO_CUDA(h, cudaMalloc(&B, (size_t)n * k * 8)); BO_CUDA(h, cudaMalloc(&C, (size_t)m * n * 8));
+    BO_CUDA(h, cudaMalloc(&pd, sizeof(GemmProblem)));
+    BO_CUDA(h, cudaMemset(A, 0, (size_t)m * k * 8)); BO_CUDA(h, cudaMemset(B, 0, (size_t)n * k * 8)); BO_CUDA(h, cudaMemset(C, 0, (size_t)m * n * 8));
+    GemmProblem p{}; p.A = A; p.B = B; p.C = C; p.M = m; p.N = n; p.K = k; p.lda = k; p.ldb = k; p.ldc = n; p.alpha = 1.0; p.beta = 1.0;
+    p.transB = 1; p.mode = 0; p.tiles_n = n / bn; p.tile_begin = 0; p.tile_end = (m / bm) * (n / bn);
+    BO_CUDA(h, cudaMemcpy(pd, &p, sizeof p, cudaMemcpyHostToDevice));
+    auto launch = [&]() {
+        if (cfg == 1) dgemm_grouped_kernel<128, 128><<<p.tile_end, 256, GemmSmem<128, 128>::BYTES>>>(pd, 1);
+        else if (cfg == 2) dgemm_grouped_kernel<128, 64><<<p.tile_end, 256, GemmSmem<128, 64>::BYTES>>>(pd, 1);
+        else dgemm_grouped_kernel<64, 64><<<p.tile_end, 256, GemmSmem<64, 64>::BYTES>>>(pd, 1);
+        h->launches++;
+    };
+    launch(); BO_CUDA(h, cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; ++r) launch();
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    BO_CUDA(h, cudaGetLastError());
+    *tflops = 2.0 * m * n * k * reps / (ms * 1e-3) * 1e-12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(pd);
+    return 0;
+}
+
+#include "lml.cuh"
 
 }  // namespace bo

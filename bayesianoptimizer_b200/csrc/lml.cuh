@@ -1,0 +1,358 @@
+// K7: batched exact log marginal likelihood + gradient over R hyper-parameter restarts
+// (the ExactMarginalLogLikelihood closure fit_gpytorch_mll evaluates, optimization/Bayesian.py:92-93).
+//
+// Included at the end of fit.cu (same translation unit: it launches the fit kernels).  Restarts are
+// processed in lock-step groups of S slots: every stage of the factorisation is ONE launch covering all
+// slots (Gram: blockIdx.z; leaf Cholesky: one block per slot; TRSM / SYRK / inverse levels / L^-T L^-1:
+// one grouped-GEMM launch listing S problems), so the latency-bound panel chain is paid once per group
+// instead of once per restart and the trailing updates fill the GPU.
+//   lml  = -1/2 r^T alpha - sum log L_ii - n/2 log 2 pi
+//   dlml/dtheta = 1/2 tr(W dK/dtheta),  W = alpha alpha^T - K^-1,  K^-1 = L^-T L^-1
+#pragma once
+
+struct LmlBatch {
+    int S = 0, np = 0, n = 0, d = 0, dp = 0;
+    double *Xraw = nullptr, *yv = nullptr;                 // shared by all slots
+    double *Xs = nullptr, *Lm = nullptr, *Li = nullptr, *Tw = nullptr, *Kw = nullptr;   // per slot
+    double *alpha = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *tpart = nullptr, *gpart = nullptr, *out = nullptr;
+    Hyper* hyps = nullptr; int* info = nullptr;
+    Hyper* hyps_host = nullptr; double* out_host = nullptr; int* info_host = nullptr;     // pinned
+    std::vector<GemmProblem> probs; std::vector<GemmLaunch> launches; GemmProblem* plan_dev = nullptr;
+    int kinv_launch = -1;
+    size_t bytes = 0;
+};
+
+static void lml_batch_free(LmlBatch* b) {
+    if (!b) return;
+    void* dev[] = {b->Xraw, b->yv, b->Xs, b->Lm, b->Li, b->Tw, b->Kw, b->alpha, b->v1, b->v2, b->v3, b->tpart, b->gpart,
+                   b->out, b->hyps, b->info, b->plan_dev};
+    for (void* p : dev) if (p) cudaFree(p);
+    if (b->hyps_host) cudaFreeHost(b->hyps_host);
+    if (b->out_host) cudaFreeHost(b->out_host);
+    if (b->info_host) cudaFreeHost(b->info_host);
+    cudaGetLastError();
+    delete b;
+}
+void lml_release(bo_handle* h) { lml_batch_free(static_cast<LmlBatch*>(h->lml_batch)); h->lml_batch = nullptr; }
+
+// per 32x32 tile of the lower triangle: partial sums of W_ij dK_ij/dlog l_k (k < DP), W_ij K_ij, and on the
+// diagonal W_ii, log L_ii, r_i alpha_i.  blockIdx.z = slot.
+template <int DP>
+__global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __restrict__ Xs_all, const double* __restrict__ alpha_all,
+                                                            const double* __restrict__ Kinv_all, const double* __restrict__ Lm_all,
+                                                            const double* __restrict__ yv, int ld, int n, int np,
+                                                            const Hyper* __restrict__ hyps, double* __restrict__ part_all) {
+    __shared__ double red[8];
+    const size_t s = blockIdx.z;
+    const Hyper& hyp = hyps[s];
+    const double* Xs = Xs_all + s * np * BO_MAX_DIM;
+    const double* alpha = alpha_all + s * np;
+    const double* Kinv = Kinv_all + s * np * ld;
+    const double* Lm = Lm_all + s * np * ld;
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    const int tile = bi * gridDim.x + bj;
+    double* part = part_all + (s * gridDim.x * gridDim.y + tile) * (DP + 4);
+    double acc[DP + 4];
+#pragma unroll
+    for (int k = 0; k < DP + 4; ++k) acc[k] = 0.0;
+    if (bj <= bi) {
+        const int j = bj * 32 + (threadIdx.x & 31);
+        double xj[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) xj[k] = (j < n) ? Xs[(size_t)j * BO_MAX_DIM + k] : 0.0;
+        const double aj = (j < n) ? alpha[j] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = bi * 32 + (threadIdx.x >> 5) + r * 8;
+            if (i >= n || j >= n || j > i) continue;
+            const double w = alpha[i] * aj - Kinv[(size_t)i * ld + j];
+            if (i == j) {
+                acc[DP + 1] += w;                                   // trace(W)
+                acc[DP + 2] += log(Lm[(size_t)i * ld + i]);         // log det / 2
+                acc[DP + 3] += (yv[i] - hyp.mean) * alpha[i];       // quadratic form
+                continue;
+            }
+            double sq = 0.0, df2[DP];
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const double df = Xs[(size_t)i * BO_MAX_DIM + k] - xj[k];
+                df2[k] = df * df;
+                sq += df2[k];
+            }
+            double kval, G;
+            if (hyp.kind == BO_KERNEL_MATERN52) {
+                const double s5 = 2.23606797749978969640917366873128;
+                const double rr = sqrt_pos(sq), e = exp_neg(s5 * rr);
+                kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, rr, 1.0)) * e;
+                G = hyp.outputscale * (5.0 / 3.0) * fma(s5, rr, 1.0) * e;
+            } else {
+                kval = hyp.outputscale * exp_neg(0.5 * sq);
+                G = kval;
+            }
+            const double wg = w * G;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) acc[k] = fma(wg, df2[k], acc[k]);
+            acc[DP] = fma(w, kval, acc[DP]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DP + 4; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += red[w8];
+            part[k] = t;
+        }
+    }
+}
+
+// deterministic final reduction: one block per slot sums the tile partials column by column
+template <int DP>
+__global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restrict__ part_all, int tiles, int n, int d,
+                                                         const Hyper* __restrict__ hyps, double* __restrict__ out_all) {
+    __shared__ double red[8];
+    __shared__ double tot[DP + 4];
+    const size_t s = blockIdx.x;
+    const Hyper& hyp = hyps[s];
+    const double* part = part_all + s * tiles * (DP + 4);
+    double* out = out_all + s * (BO_MAX_DIM + 3);
+    for (int k = 0; k < DP + 4; ++k) {
+        double v = 0.0;
+        for (int t = threadIdx.x; t < tiles; t += 256) v += part[(size_t)t * (DP + 4) + k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w8 = 0; w8 < 8; ++w8) t += red[w8];
+            tot[k] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double trW = tot[DP + 1], logdet_half = tot[DP + 2], quad = tot[DP + 3];
+    out[0] = -0.5 * quad - logdet_half - 0.5 * n * 1.83787706640934548356;        // log(2 pi)
+    for (int k = 0; k < d; ++k) out[1 + k] = tot[k];                               // pairs i>j count twice in the 1/2 sum
+    out[1 + d] = tot[DP] + 0.5 * hyp.outputscale * trW;                            // d / d log outputscale
+    out[2 + d] = 0.5 * hyp.noise * trW;                                            // d / d log noise
+}
+
+template <int DP>
+static int lml_launch_gram(bo_handle* h, LmlBatch* b, int S, cudaStream_t st) {
+    gram_batched_kernel<DP><<<dim3(b->np / 32, b->np / 32, S), dim3(32, 8), 0, st>>>(b->Xs, b->n, b->np, b->np, b->hyps, b->Lm);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+template <int DP>
+static int lml_launch_grad(bo_handle* h, LmlBatch* b, int S, cudaStream_t st) {
+    const int nt = b->np / 32;
+    lml_grad_tile_kernel<DP><<<dim3(nt, nt, S), 256, 0, st>>>(b->Xs, b->alpha, b->Kw, b->Lm, b->yv, b->np, b->n, b->np, b->hyps, b->gpart);
+    BO_LAUNCH_CHECK(h);
+    lml_reduce_kernel<DP><<<S, 256, 0, st>>>(b->gpart, nt * nt, b->n, b->d, b->hyps, b->out);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// (re)build the slot workspace and the launch plan for (n, d, S)
+static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
+    LmlBatch* b = static_cast<LmlBatch*>(h->lml_batch);
+    const int np = round_up(n, PAD), dp = pad_dim(d);
+    if (b && b->np == np && b->S == S && b->dp == dp) { b->n = n; b->d = d; return 0; }
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    lml_batch_free(b);
+    h->lml_batch = nullptr;
+    b = new (std::nothrow) LmlBatch();
+    if (!b) return fail(h, BO_E_NOMEM, "bo_lml_grad_batched: out of host memory");
+    b->S = S; b->np = np; b->n = n; b->d = d; b->dp = dp;
+    const size_t c = np, mat = c * c, nt = c / 32;
+    struct { double** p; size_t elems; } reqs[] = {
+        {&b->Xraw, c * BO_MAX_DIM}, {&b->yv, c}, {&b->Xs, S * c * BO_MAX_DIM}, {&b->Lm, S * mat}, {&b->Li, S * mat},
+        {&b->Tw, S * (mat / 4 + 64)}, {&b->Kw, S * mat}, {&b->alpha, S * c}, {&b->v1, S * c}, {&b->v2, S * c}, {&b->v3, S * c},
+        {&b->tpart, (size_t)S * TRMVT_SPLITS * c}, {&b->gpart, S * nt * nt * (dp + 4)}, {&b->out, (size_t)S * (BO_MAX_DIM + 3)}};
+    cudaError_t e = cudaSuccess;
+    for (auto& r : reqs) if (e == cudaSuccess) e = cudaMalloc(r.p, r.elems * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->hyps, S * sizeof(Hyper));
+    if (e == cudaSuccess) e = cudaMalloc(&b->info, S * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->hyps_host, S * sizeof(Hyper));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->out_host, (size_t)S * (BO_MAX_DIM + 3) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->info_host, S * sizeof(int));
+    if (e != cudaSuccess) {
+        lml_batch_free(b);
+        cudaGetLastError();
+        return fail(h, BO_E_NOMEM, "bo_lml_grad_batched: cannot allocate the restart slots");
+    }
+    // launch plan: per block column one TRSM + one SYRK launch, per inverse level two launches, then K^-1;
+    // every launch lists the S slots' problems
+    const int ld = np, nb = np / NB;
+    auto plan_push = [&](const GemmBatch& g) {
+        GemmLaunch L{(int)b->probs.size(), (int)g.probs.size(), g.tiles, g.bm == 128 ? 1 : 0};
+        b->probs.insert(b->probs.end(), g.probs.begin(), g.probs.end());
+        b->launches.push_back(L);
+    };
+    for (int kb = 0; kb + 1 < nb; ++kb) {
+        const int r0 = (kb + 1) * NB, m = np - r0;
+        GemmBatch trsm(64);
+        long t128 = (long)(m / 128) * (m / 128 + 1) / 2 * S;
+        GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
+        for (int s = 0; s < S; ++s) {
+            double* Lm = b->Lm + (size_t)s * mat; double* Li = b->Li + (size_t)s * mat;
+            double* P = Lm + (size_t)r0 * ld + kb * NB;
+            trsm.add(P, ld, Li + (size_t)kb * NB * ld + kb * NB, ld, P, ld, m, NB, NB, 1.0, 0.0, 1, GEMM_B_LOWER_NT);
+            syrk.add(P, ld, P, ld, Lm + (size_t)r0 * ld + r0, ld, m, m, NB, -1.0, 1.0, 1, GEMM_LOWER_C);
+        }
+        plan_push(trsm);
+        plan_push(syrk);
+    }
+    struct Node { int lo, mid, hi, depth; };
+    std::vector<Node> nodes, stack;
+    int maxdepth = 0;
+    if (nb > 1) stack.push_back({0, nb / 2, nb, 0});
+    while (!stack.empty()) {
+        Node nd = stack.back(); stack.pop_back();
+        nodes.push_back(nd);
+        if (nd.depth > maxdepth) maxdepth = nd.depth;
+        if (nd.mid - nd.lo > 1) stack.push_back({nd.lo, nd.lo + (nd.mid - nd.lo) / 2, nd.mid, nd.depth + 1});
+        if (nd.hi - nd.mid > 1) stack.push_back({nd.mid, nd.mid + (nd.hi - nd.mid) / 2, nd.hi, nd.depth + 1});
+    }
+    for (int depth = maxdepth; depth >= 0 && nb > 1; --depth) {
+        bool all128 = true; long t128 = 0;
+        for (const Node& nd : nodes) if (nd.depth == depth) {
+            int p = (nd.mid - nd.lo) * NB, q = (nd.hi - nd.mid) * NB;
+            if (p % 128 || q % 128 || (nd.lo * NB) % 128) all128 = false;
+            t128 += (long)(p / 128) * (q / 128) * S;
+        }
+        const int tile = pick_tile(h->sm_count, {all128 ? 128 : 64}, t128);
+        GemmBatch g1(tile), g2(tile);
+        for (int s = 0; s < S; ++s) {
+            double* Lm = b->Lm + (size_t)s * mat; double* Li = b->Li + (size_t)s * mat;
+            size_t toff = (size_t)s * (mat / 4 + 64);
+            for (const Node& nd : nodes) if (nd.depth == depth) {
+                const int lo = nd.lo * NB, mid = nd.mid * NB, p = (nd.mid - nd.lo) * NB, q = (nd.hi - nd.mid) * NB;
+                double* T = b->Tw + toff;
+                g1.add(Lm + (size_t)mid * ld + lo, ld, Li + (size_t)lo * ld + lo, ld, T, p, q, p, p, 1.0, 0.0, 0, GEMM_B_LOWER_NN);
+                g2.add(Li + (size_t)mid * ld + mid, ld, T, p, Li + (size_t)mid * ld + lo, ld, q, p, q, -1.0, 0.0, 0, GEMM_A_LOWER);
+                toff += (size_t)q * p;
+            }
+        }
+        plan_push(g1);
+        plan_push(g2);
+    }
+    {
+        GemmBatch kinv(pick_tile(h->sm_count, {np}, (long)(np / 128) * (np / 128 + 1) / 2 * S));
+        for (int s = 0; s < S; ++s) {
+            double* Li = b->Li + (size_t)s * mat;
+            kinv.add(Li, ld, Li, ld, b->Kw + (size_t)s * mat, ld, np, np, np, 1.0, 0.0, 0, GEMM_TRANS_A | GEMM_LOWER_C | GEMM_K_FROM_MAX);
+        }
+        b->kinv_launch = (int)b->launches.size();
+        plan_push(kinv);
+    }
+    const size_t bytes = b->probs.size() * sizeof(GemmProblem);
+    if (cudaMalloc(&b->plan_dev, bytes + 256) != cudaSuccess) { lml_batch_free(b); cudaGetLastError(); return fail(h, BO_E_NOMEM, "bo_lml_grad_batched: plan allocation failed"); }
+    BO_CUDA(h, cudaMemcpy(b->plan_dev, b->probs.data(), bytes, cudaMemcpyHostToDevice));
+    h->lml_batch = b;
+    return 0;
+}
+
+static int lml_gemm(bo_handle* h, LmlBatch* b, int li, int S_active, cudaStream_t st) {
+    // a launch lists the problems slot-major with identical tile counts per slot -> a prefix covers S_active slots
+    const GemmLaunch& L = b->launches[li];
+    if (L.tiles == 0) return 0;
+    const int per_slot = L.count / b->S, tiles_per_slot = L.tiles / b->S;
+    const int count = per_slot * S_active, tiles = tiles_per_slot * S_active;
+    if (L.cfg == 1) dgemm_grouped_kernel<128, 128><<<tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(b->plan_dev + L.first, count);
+    else dgemm_grouped_kernel<64, 64><<<tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(b->plan_dev + L.first, count);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
+             const double* theta_host, int R, double* lml_host, double* grad_host, int* status_host, cudaStream_t st) {
+    if (!X_dev || !y_dev || !theta_host || !lml_host || !grad_host || !status_host || n < 1 || d < 1 || R < 1)
+        return fail(h, BO_E_INVALID, "bo_lml_grad_batched: bad argument");
+    if (d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_lml_grad_batched: d exceeds BO_MAX_DIM");
+    if (kind != BO_KERNEL_MATERN52 && kind != BO_KERNEL_RBF) return fail(h, BO_E_INVALID, "bo_lml_grad_batched: unknown kernel kind");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const int np = round_up(n, PAD);
+    // slots: as many restarts in lock step as ~6 GB of workspace allows (4 n^2 doubles per slot), at most 32
+    const size_t per_slot = (size_t)np * np * 8 * 13 / 4;
+    int S = (int)std::min<size_t>(32, std::max<size_t>(1, (6ull << 30) / per_slot));
+    if (S > R) S = R;
+    int rc = lml_prepare(h, n, d, S, st);
+    if (rc) return rc;
+    LmlBatch* b = static_cast<LmlBatch*>(h->lml_batch);
+    const int ld = np, nb = np / NB;
+    const size_t mat = (size_t)np * np;
+    Hyper zero{};   // inv_ls = 1, mean: staging of the unscaled inputs uses an identity scale
+    for (int k = 0; k < BO_MAX_DIM; ++k) zero.inv_ls[k] = 1.0;
+    stage_inputs_kernel<<<(np + 127) / 128, 128, 0, st>>>(X_dev, y_dev, n, d, np, zero, b->Xraw, b->Xs, b->yv);
+    BO_LAUNCH_CHECK(h);
+
+    for (int r0 = 0; r0 < R; r0 += S) {
+        const int Sa = std::min(S, R - r0);
+        for (int s = 0; s < Sa; ++s) {
+            const double* th = theta_host + (size_t)(r0 + s) * (d + 2);
+            Hyper& hy = b->hyps_host[s];
+            hy.kind = kind; hy.d = d; hy.dp = b->dp; hy.mean = mean; hy.jitter = 0.0;
+            for (int k = 0; k < BO_MAX_DIM; ++k) hy.inv_ls[k] = k < d ? exp(-th[k]) : 0.0;
+            hy.outputscale = exp(th[d]); hy.noise = exp(th[d + 1]);
+        }
+        BO_CUDA(h, cudaMemcpyAsync(b->hyps, b->hyps_host, Sa * sizeof(Hyper), cudaMemcpyHostToDevice, st));
+        BO_CUDA(h, cudaMemsetAsync(b->info, 0, Sa * sizeof(int), st));
+        rescale_batched_kernel<<<dim3((np + 127) / 128, 1, Sa), 128, 0, st>>>(np, d, b->hyps, b->Xraw, b->Xs);
+        BO_LAUNCH_CHECK(h);
+        if ((rc = BO_DISPATCH_DP(b->dp, lml_launch_gram, h, b, Sa, st))) return rc;
+        BO_CUDA(h, cudaMemsetAsync(b->Li, 0, (size_t)Sa * mat * sizeof(double), st));
+        for (int kb = 0; kb < nb; ++kb) {
+            const size_t off = (size_t)kb * NB * ld + kb * NB;
+            potf2_inv_kernel<<<Sa, 256, 0, st>>>(b->Lm + off, ld, b->Li + off, ld, b->info, kb * NB, mat);
+            BO_LAUNCH_CHECK(h);
+            if (kb + 1 < nb) {
+                if ((rc = lml_gemm(h, b, 2 * kb, Sa, st))) return rc;
+                if ((rc = lml_gemm(h, b, 2 * kb + 1, Sa, st))) return rc;
+            }
+        }
+        for (int li = 2 * (nb - 1); li < (int)b->launches.size(); ++li)       // inverse levels, then K^-1 = L^-T L^-1
+            if ((rc = lml_gemm(h, b, li, Sa, st))) return rc;
+        // alpha = L^-T (L^-1 r) + one refinement step against the factor (as in the single fit)
+        const dim3 gv((np + 255) / 256, 1, Sa), gr(np / 8, 1, Sa), gt(np / 32, TRMVT_SPLITS, Sa);
+        resid_init_kernel<<<gv, 256, 0, st>>>(b->yv, n, np, mean, b->v1);
+        trmv_lower_kernel<<<gr, 256, 0, st>>>(b->Li, ld, np, b->v1, b->v2, mat);
+        trmv_lower_t_kernel<<<gt, 256, 0, st>>>(b->Li, ld, np, b->v2, b->tpart, mat);
+        trmv_reduce_kernel<<<gv, 256, 0, st>>>(b->tpart, np, b->alpha, 0);
+        trmv_lower_t_kernel<<<gt, 256, 0, st>>>(b->Lm, ld, np, b->alpha, b->tpart, mat);
+        trmv_reduce_kernel<<<gv, 256, 0, st>>>(b->tpart, np, b->v2, 0);
+        trmv_lower_kernel<<<gr, 256, 0, st>>>(b->Lm, ld, np, b->v2, b->v3, mat);
+        sub_vec_kernel<<<gv, 256, 0, st>>>(b->v1, b->v3, np, b->v2);
+        trmv_lower_kernel<<<gr, 256, 0, st>>>(b->Li, ld, np, b->v2, b->v3, mat);
+        trmv_lower_t_kernel<<<gt, 256, 0, st>>>(b->Li, ld, np, b->v3, b->tpart, mat);
+        trmv_reduce_kernel<<<gv, 256, 0, st>>>(b->tpart, np, b->alpha, 1);
+        h->launches += 11;
+        BO_CUDA(h, cudaGetLastError());
+        if ((rc = BO_DISPATCH_DP(b->dp, lml_launch_grad, h, b, Sa, st))) return rc;
+        BO_CUDA(h, cudaMemcpyAsync(b->out_host, b->out, (size_t)Sa * (BO_MAX_DIM + 3) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        BO_CUDA(h, cudaMemcpyAsync(b->info_host, b->info, Sa * sizeof(int), cudaMemcpyDeviceToHost, st));
+        BO_CUDA(h, cudaStreamSynchronize(st));
+        for (int s = 0; s < Sa; ++s) {
+            const int r = r0 + s;
+            const int info = b->info_host[s];
+            status_host[r] = info > n ? n : info;
+            const double* o = b->out_host + (size_t)s * (BO_MAX_DIM + 3);
+            if (info != 0) {
+                lml_host[r] = -INFINITY;
+                for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = 0.0;
+            } else {
+                lml_host[r] = o[0];
+                for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = o[1 + k];
+            }
+        }
+    }
+    return 0;
+}

@@ -258,6 +258,11 @@ class GPEngine:
         self._check(self._lib.bo_fp64_peak(self._h, 1 if use_dmma else 0, float(seconds), C.byref(out)))
         return out.value
 
+    def gemm_probe_tflops(self, m: int, n: int, k: int, cfg: int = 1, reps: int = 10) -> float:
+        out = C.c_double(0.0)
+        self._check(self._lib.bo_gemm_probe(self._h, m, n, k, cfg, reps, C.byref(out)))
+        return out.value
+
     def launch_count(self) -> int:
         return int(self._lib.bo_launch_count(self._h))
 

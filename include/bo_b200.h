@@ -161,6 +161,10 @@ int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, 
  * MEASURED_PEAKS.json lacks.  Returns TFLOP/s in *tflops_host. */
 int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_host);
 
+/* Throughput probe of the fit's grouped FP64 DMMA GEMM (C = A B^T + C, one m x n x k problem; cfg 0: 64x64 tiles,
+ * 1: 128x128, 2: 128x64).  Returns TFLOP/s in *tflops_host.  Diagnostic only. */
+int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, int32_t reps, double* tflops_host);
+
 /* Kernel-launch counter (own kernels launched through this handle since creation). */
 int64_t bo_launch_count(const bo_handle* h);
 

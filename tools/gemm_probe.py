@@ -1,0 +1,13 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bayesianoptimizer_b200 import GPEngine
+eng = GPEngine(torch.device("cuda", 0))
+for (m, n, k) in ((4096, 4096, 64), (4096, 4096, 128), (4096, 4096, 512), (4096, 4096, 4096), (2048, 2048, 64), (2048, 2048, 2048), (8192, 64, 64)):
+    row = []
+    for cfg in (0, 1, 2):
+        try:
+            row.append(f"cfg{cfg} {eng.gemm_probe_tflops(m, n, k, cfg, 20):6.2f}")
+        except Exception as e:
+            row.append(f"cfg{cfg}   n/a")
+    print(f"m={m} n={n} k={k}: " + "  ".join(row), flush=True)
