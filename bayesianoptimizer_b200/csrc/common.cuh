@@ -266,6 +266,5 @@ int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);
 int refit_factor(bo_handle* h, cudaStream_t st);
 int create_handle(bo_handle** out, int device);
 void lml_release(bo_handle* h);
-int pack_row_block(bo_handle* h, int ib, cudaStream_t st);
-int run_gemm_once(bo_handle* h, const GemmProblem* probs_host, int count, int tiles, int cfg, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv
+int pack_row_block(bo_handle* h, int ib, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv
 }  // namespace bo

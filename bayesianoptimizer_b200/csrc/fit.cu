@@ -549,22 +549,6 @@ int pack_row_block(bo_handle* h, int ib, cudaStream_t st) {
     return 0;
 }
 
-// one-off grouped GEMM outside the fit plan (descriptors staged through plan_dev's tail)
-int run_gemm_once(bo_handle* h, const GemmProblem* probs_host, int count, int tiles, int cfg, cudaStream_t st) {
-    static GemmProblem* dev = nullptr; static int cap = 0;     // tiny, process-lifetime staging buffer
-    if (count > cap) {
-        if (dev) cudaFree(dev);
-        BO_CUDA(h, cudaMalloc(&dev, sizeof(GemmProblem) * (count + 16)));
-        cap = count + 16;
-    }
-    BO_CUDA(h, cudaMemcpyAsync(dev, probs_host, sizeof(GemmProblem) * count, cudaMemcpyHostToDevice, st));
-    BO_CUDA(h, cudaStreamSynchronize(st));
-    if (cfg == 1) dgemm_grouped_kernel<128, 128><<<tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(dev, count);
-    else dgemm_grouped_kernel<64, 64><<<tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(dev, count);
-    BO_LAUNCH_CHECK(h);
-    return 0;
-}
-
 int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st) {
     BO_CUDA(h, cudaSetDevice(h->device));
     const int n = h->n;

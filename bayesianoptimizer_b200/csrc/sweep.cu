@@ -517,25 +517,21 @@ static int ensure_sweep_ws(bo_handle* h, int grid) {
 
 template <int DP>
 static int launch_sweep(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in is per device context: set it on every launch (a process may hold handles on several GPUs)
+    if (a.hyp.kind == BO_KERNEL_MATERN52) {
         BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
+        sweep_kernel<DP, BO_KERNEL_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
+    } else {
         BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
-        attr_set = true;
+        sweep_kernel<DP, BO_KERNEL_RBF><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
     }
-    if (a.hyp.kind == BO_KERNEL_MATERN52) sweep_kernel<DP, BO_KERNEL_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
-    else sweep_kernel<DP, BO_KERNEL_RBF><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
 template <int DP>
 static int launch_sweep_ref(bo_handle* h, const SweepArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
     const size_t sm = (size_t)a.np * sizeof(double);
-    if (!attr_set) {
-        BO_CUDA(h, cudaFuncSetAttribute(sweep_reference_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    BO_CUDA(h, cudaFuncSetAttribute(sweep_reference_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     sweep_reference_kernel<DP><<<(unsigned)a.N, 256, sm, st>>>(a, h->Li, h->cap_np);
     BO_LAUNCH_CHECK(h);
     return 0;
