@@ -96,20 +96,14 @@ __global__ void rescale_batched_kernel(int np, int d, const Hyper* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// K2 leaf: Cholesky of one NB x NB diagonal block in shared memory + its explicit inverse
+// K2 panel: Cholesky of the NB x NB diagonal block fused with the triangular solve of the rows below it
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, int lda,
-                                                        double* __restrict__ Ainv, int ldi,
-                                                        int* __restrict__ info, int pivot_base,
-                                                        size_t slot_stride) {
-    A += blockIdx.x * slot_stride; Ainv += blockIdx.x * slot_stride; info += blockIdx.x;     // one block per slot
-    __shared__ double S[NB][NB + 1];
-    __shared__ double colS[2][NB];
-    __shared__ double rdiag[NB];
+// Right-looking Cholesky with the block held in REGISTERS: thread (ti, tk) of a 16 x 16 grid owns the
+// 4 x 4 elements (ti + 16x, tk + 16y); per column one shared-memory broadcast of the pivot column and one
+// barrier (double-buffered), the rank-1 update is 16 register FMAs.  Leaves L (lower, upper zero) in S.
+__device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int lda, double (*S)[NB + 1],
+                                              double (*colS)[NB], int* info, int pivot_base, bool report) {
     const int tid = threadIdx.x;
-    // Right-looking Cholesky with the block held in REGISTERS: thread (ti, tk) of a 16 x 16 grid owns the
-    // 4 x 4 elements (ti + 16x, tk + 16y); per column one shared-memory broadcast of the pivot column and
-    // one barrier (double-buffered), the rank-1 update is 16 register FMAs.
     const int ti = tid >> 4, tk = tid & 15;
     double a[4][4];
 #pragma unroll
@@ -132,7 +126,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
             __syncthreads();
             double dj = col[j];
             if (!(dj > 0.0)) {                       // also catches NaN
-                if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+                if (report && tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
                 dj = 1.0;
             }
             double rs;
@@ -167,12 +161,76 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
         for (int y = 0; y < 4; ++y) {
             const int i = ti + 16 * x, k = tk + 16 * y;
             S[i][k] = (k <= i) ? a[x][y] : 0.0;
-            if (k <= i) A[(size_t)i * lda + k] = a[x][y];
         }
+    __syncthreads();
+}
+
+// grid = slots * ctas_per_slot; CTA r of a slot: r == 0 factors the diagonal block and parks L in the (still
+// unused) diagonal block of the inverse matrix -- NOT in place, later-scheduled CTAs of this launch still read
+// the unfactored block -- and r >= 1 re-factors it (identical arithmetic, no inter-CTA wait) and solves rows
+// [64 r, 64 r + 64) of the panel below: X L^T = A by forward substitution, 4 threads per row.
+// Replaces the potrf2 + TRSM launches of a block column.
+__global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A, int lda, double* __restrict__ Lpark,
+                                                         int* __restrict__ info, int pivot_base, size_t slot_stride,
+                                                         int ctas_per_slot) {
+    __shared__ double S[NB][NB + 1];
+    __shared__ double colS[2][NB];
+    __shared__ double rdiag[NB];
+    const int slot = blockIdx.x / ctas_per_slot, r = blockIdx.x % ctas_per_slot;
+    A += slot * slot_stride; Lpark += slot * slot_stride; info += slot;
+    const int tid = threadIdx.x;
+    leaf_cholesky(A, lda, S, colS, info, pivot_base, r == 0);
+    if (r == 0) {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int i = e / NB, k = e % NB;
+            if (k <= i) Lpark[(size_t)i * lda + k] = S[i][k];
+        }
+        return;
+    }
+    if (tid < NB) rdiag[tid] = 1.0 / S[tid][tid];
+    __syncthreads();
+    double* P = A + (size_t)r * NB * lda;                  // 64 rows of the panel below the diagonal block
+    const int row = tid >> 2, q = tid & 3, lane = tid & 31;
+    double av[NB / 4], x[NB / 4];
+#pragma unroll
+    for (int m = 0; m < NB / 4; ++m) { av[m] = P[(size_t)row * lda + 4 * m + q]; x[m] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        double part = 0.0;
+#pragma unroll
+        for (int m = 0; m < NB / 4; ++m)
+            if (4 * m + q < j) part = fma(x[m], S[j][4 * m + q], part);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        const double aj = __shfl_sync(0xffffffffu, av[j >> 2], (lane & ~3) | (j & 3));
+        const double xj = (aj - part) * rdiag[j];
+        if ((j & 3) == q) x[j >> 2] = xj;
+    }
+#pragma unroll
+    for (int m = 0; m < NB / 4; ++m) P[(size_t)row * lda + 4 * m + q] = x[m];
+}
+
+// explicit inverses of all NB x NB diagonal blocks of L in one launch (grid = slots * nb), off the critical path.
+// Reads the factored block parked in Linv's diagonal block, moves it to its place in L, and overwrites the
+// parking spot with the inverse: forward substitution, 4 threads per column c, thread q owns rows i % 4 == q.
+__global__ void __launch_bounds__(256) leaf_inverse_kernel(double* __restrict__ L, int ld, double* __restrict__ Linv,
+                                                           size_t slot_stride, int nb) {
+    __shared__ double S[NB][NB + 1];
+    __shared__ double rdiag[NB];
+    const int slot = blockIdx.x / nb, kb = blockIdx.x % nb;
+    const size_t off = slot * slot_stride + (size_t)kb * NB * ld + kb * NB;
+    double* A = L + off;
+    double* Ainv = Linv + off;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e / NB, k = e % NB;
+        const double v = (k <= i) ? Ainv[(size_t)i * ld + k] : 0.0;
+        S[i][k] = v;
+        if (k <= i) A[(size_t)i * ld + k] = v;
+    }
     __syncthreads();
     if (tid < NB) rdiag[tid] = 1.0 / S[tid][tid];
     __syncthreads();
-    // inverse by forward substitution: 4 threads per column c, thread q owns rows i with i % 4 == q
     const int c = tid >> 2, q = tid & 3;
     double x[NB / 4];
 #pragma unroll
@@ -182,7 +240,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
         double part = 0.0;
 #pragma unroll
         for (int m = 0; m < NB / 4; ++m) {
-            if (4 * m + q < i) part = fma(S[i][4 * m + q], x[m], part);   // bound is warp-uniform up to q: static m
+            if (4 * m + q < i) part = fma(S[i][4 * m + q], x[m], part);
         }
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -190,7 +248,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
         if ((i & 3) == q) x[i >> 2] = xi;
     }
 #pragma unroll
-    for (int m = 0; m < NB / 4; ++m) Ainv[(size_t)(4 * m + q) * ldi + c] = x[m];
+    for (int m = 0; m < NB / 4; ++m) Ainv[(size_t)(4 * m + q) * ld + c] = x[m];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -322,9 +380,9 @@ static int pick_tile(int sm, std::initializer_list<int> dims, long tiles128) {
     return 64;
 }
 
-// Build the launch plan of the factorisation (2 GEMM launches per block column) followed by the
-// recursive inverse (2 launches per level).  Layout of plan_launches:
-//   [2*kb]   TRSM of block column kb ; [2*kb+1] SYRK trailing update      (kb = 0 .. nb-2)
+// Build the launch plan of the factorisation (one SYRK launch per block column; the panel kernel does the
+// diagonal block + triangular solve) followed by the recursive inverse (2 launches per level).
+//   plan_launches[kb] = SYRK trailing update of block column kb      (kb = 0 .. nb-2)
 //   then per inverse level (deepest first): T = C * Ainv ; Li[lower-left] = -Binv * T
 static int build_plan(bo_handle* h, cudaStream_t st) {
     const int np = h->np, ld = h->cap_np, nb = np / NB;
@@ -333,10 +391,6 @@ static int build_plan(bo_handle* h, cudaStream_t st) {
     for (int kb = 0; kb + 1 < nb; ++kb) {
         const int r0 = (kb + 1) * NB, m = np - r0;
         double* P = h->Lm + (size_t)r0 * ld + kb * NB;                 // panel below the diagonal block
-        const double* Dinv = h->Li + (size_t)kb * NB * ld + kb * NB;   // inverse of the diagonal block
-        GemmBatch trsm(64);     // in place: one CTA owns the full 64-wide row panel it overwrites
-        trsm.add(P, ld, Dinv, ld, P, ld, m, NB, NB, 1.0, 0.0, /*transB=*/1, GEMM_B_LOWER_NT);
-        plan_push(h, trsm);
         double* C = h->Lm + (size_t)r0 * ld + r0;
         long t128 = (long)(m / 128) * (m / 128 + 1) / 2;
         GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
@@ -495,16 +549,14 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
     BO_CUDA(h, cudaMemset2DAsync(h->Li, (size_t)ld * 8, 0, (size_t)np * 8, np, st));
     for (int kb = 0; kb < nb; ++kb) {
         double* D = h->Lm + (size_t)kb * NB * ld + kb * NB;
-        double* Dinv = h->Li + (size_t)kb * NB * ld + kb * NB;
-        potf2_inv_kernel<<<1, 256, 0, st>>>(D, ld, Dinv, ld, h->info_dev, kb * NB, 0);
+        chol_panel_kernel<<<nb - kb, 256, 0, st>>>(D, ld, h->Li + (size_t)kb * NB * ld + kb * NB, h->info_dev, kb * NB, 0, nb - kb);
         BO_LAUNCH_CHECK(h);
-        if (kb + 1 < nb) {
-            if ((rc = gemm_launch(h, h->plan_launches[2 * kb], st))) return rc;
-            if ((rc = gemm_launch(h, h->plan_launches[2 * kb + 1], st))) return rc;
-        }
+        if (kb + 1 < nb && (rc = gemm_launch(h, h->plan_launches[kb], st))) return rc;
     }
     BO_CUDA(h, cudaMemcpyAsync(h->info_host, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    for (size_t li = 2 * (size_t)(nb - 1); li < h->plan_launches.size(); ++li)
+    leaf_inverse_kernel<<<nb, 256, 0, st>>>(h->Lm, ld, h->Li, 0, nb);
+    BO_LAUNCH_CHECK(h);
+    for (size_t li = (size_t)(nb - 1); li < h->plan_launches.size(); ++li)
         if ((rc = gemm_launch(h, h->plan_launches[li], st))) return rc;
     {
         dim3 grid(np / SW_BK, np / SW_BM);

@@ -189,7 +189,7 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
         cudaGetLastError();
         return fail(h, BO_E_NOMEM, "bo_lml_grad_batched: cannot allocate the restart slots");
     }
-    // launch plan: per block column one TRSM + one SYRK launch, per inverse level two launches, then K^-1;
+    // launch plan: per block column one SYRK launch (the panel kernel factors + solves), per inverse level two, then K^-1;
     // every launch lists the S slots' problems
     const int ld = np, nb = np / NB;
     auto plan_push = [&](const GemmBatch& g) {
@@ -199,16 +199,13 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
     };
     for (int kb = 0; kb + 1 < nb; ++kb) {
         const int r0 = (kb + 1) * NB, m = np - r0;
-        GemmBatch trsm(64);
         long t128 = (long)(m / 128) * (m / 128 + 1) / 2 * S;
         GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
         for (int s = 0; s < S; ++s) {
-            double* Lm = b->Lm + (size_t)s * mat; double* Li = b->Li + (size_t)s * mat;
+            double* Lm = b->Lm + (size_t)s * mat;
             double* P = Lm + (size_t)r0 * ld + kb * NB;
-            trsm.add(P, ld, Li + (size_t)kb * NB * ld + kb * NB, ld, P, ld, m, NB, NB, 1.0, 0.0, 1, GEMM_B_LOWER_NT);
             syrk.add(P, ld, P, ld, Lm + (size_t)r0 * ld + r0, ld, m, m, NB, -1.0, 1.0, 1, GEMM_LOWER_C);
         }
-        plan_push(trsm);
         plan_push(syrk);
     }
     struct Node { int lo, mid, hi, depth; };
@@ -312,14 +309,13 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
         BO_CUDA(h, cudaMemsetAsync(b->Li, 0, (size_t)Sa * mat * sizeof(double), st));
         for (int kb = 0; kb < nb; ++kb) {
             const size_t off = (size_t)kb * NB * ld + kb * NB;
-            potf2_inv_kernel<<<Sa, 256, 0, st>>>(b->Lm + off, ld, b->Li + off, ld, b->info, kb * NB, mat);
+            chol_panel_kernel<<<Sa * (nb - kb), 256, 0, st>>>(b->Lm + off, ld, b->Li + off, b->info, kb * NB, mat, nb - kb);
             BO_LAUNCH_CHECK(h);
-            if (kb + 1 < nb) {
-                if ((rc = lml_gemm(h, b, 2 * kb, Sa, st))) return rc;
-                if ((rc = lml_gemm(h, b, 2 * kb + 1, Sa, st))) return rc;
-            }
+            if (kb + 1 < nb && (rc = lml_gemm(h, b, kb, Sa, st))) return rc;
         }
-        for (int li = 2 * (nb - 1); li < (int)b->launches.size(); ++li)       // inverse levels, then K^-1 = L^-T L^-1
+        leaf_inverse_kernel<<<Sa * nb, 256, 0, st>>>(b->Lm, ld, b->Li, mat, nb);
+        BO_LAUNCH_CHECK(h);
+        for (int li = nb - 1; li < (int)b->launches.size(); ++li)             // inverse levels, then K^-1 = L^-T L^-1
             if ((rc = lml_gemm(h, b, li, Sa, st))) return rc;
         // alpha = L^-T (L^-1 r) + one refinement step against the factor (as in the single fit)
         const dim3 gv((np + 255) / 256, 1, Sa), gr(np / 8, 1, Sa), gt(np / 32, TRMVT_SPLITS, Sa);
