@@ -196,10 +196,11 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A,
     for (int m = 0; m < NB / 4; ++m) { av[m] = P[(size_t)row * lda + 4 * m + q]; x[m] = 0.0; }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-        double part = 0.0;
+        double pp[4] = {0.0, 0.0, 0.0, 0.0};                  // four independent chains: FP64 latency, not issue, binds here
 #pragma unroll
         for (int m = 0; m < NB / 4; ++m)
-            if (4 * m + q < j) part = fma(x[m], S[j][4 * m + q], part);
+            if (4 * m + q < j) pp[m & 3] = fma(x[m], S[j][4 * m + q], pp[m & 3]);
+        double part = (pp[0] + pp[1]) + (pp[2] + pp[3]);
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         const double aj = __shfl_sync(0xffffffffu, av[j >> 2], (lane & ~3) | (j & 3));
@@ -237,11 +238,12 @@ __global__ void __launch_bounds__(256) leaf_inverse_kernel(double* __restrict__ 
     for (int m = 0; m < NB / 4; ++m) x[m] = 0.0;
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-        double part = 0.0;
+        double pp[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int m = 0; m < NB / 4; ++m) {
-            if (4 * m + q < i) part = fma(S[i][4 * m + q], x[m], part);
+            if (4 * m + q < i) pp[m & 3] = fma(S[i][4 * m + q], x[m], pp[m & 3]);
         }
+        double part = (pp[0] + pp[1]) + (pp[2] + pp[3]);
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         const double xi = ((i == c ? 1.0 : 0.0) - part) * rdiag[i];
