@@ -13,7 +13,7 @@ changing only its import (line 4), and ``main.py``, the Taichi objective and the
 
 What changes is only the L2 body: SingleTaskGP + fit_gpytorch_mll + qLogEI + optimize_acqf
 become GPEngine.fit / lml_grad_batched / sweep / refine / append (hand-written CUDA behind the C ABI).
-PyTorch and SciPy here are plumbing: tensors, the L-BFGS-B driver of the hyper-parameter fit, CSV I/O.
+PyTorch and NumPy here are plumbing: tensors, the lock-step L-BFGS driver of the hyper-parameter fit (hyperfit.py), CSV I/O.
 """
 from __future__ import annotations
 
@@ -44,7 +44,9 @@ class GPConfig:
     K_BIG_CAP: int = 8000                # Bayesian7.py:66
     fit_hyperparameters: bool = True     # maximise the exact LML (fit_gpytorch_mll, Bayesian.py:93)
     hyper_restarts: int = 16             # batched random restarts screened by bo_lml_grad_batched
-    hyper_maxiter: int = 50              # L-BFGS-B iterations from the best restart
+    hyper_refine: int = 4                # best screened restarts refined in lock step (one batched LML call per step)
+    hyper_maxiter: int = 50              # lock-step L-BFGS iterations
+    hyper_prior: Optional[str] = "auto"  # "auto": botorch defaults (rbf -> lognormal, matern52 -> gamma); None = max. likelihood
     lengthscale: Optional[Sequence[float]] = None   # fixed / initial ARD lengthscales (unit cube)
     outputscale: float = 1.0
     noise: float = 1e-3
@@ -243,10 +245,14 @@ class BayesianOptimizer:
         return self._engine
 
     def _fit_hyperparameters(self, eng, X, y):
-        """Exact-LML maximisation (fit_gpytorch_mll, Bayesian.py:93): R batched random restarts screened on the
-        device, then SciPy L-BFGS-B (the reference's own optimiser) from the best one, gradients from K7."""
-        import scipy.optimize as so
+        """Exact-MLL / MAP fit (fit_gpytorch_mll, Bayesian.py:93): R random restarts screened in one batched
+        K7 call, the best few refined by a lock-step box-projected L-BFGS (hyperfit.py) whose every step is one
+        batched LML+gradient evaluation on the device; warm-started from the previous refit."""
+        from .hyperfit import fit_map, log_prior_and_grad
         cfg, d = self.config, self.dim
+        prior = cfg.hyper_prior
+        if prior == "auto":
+            prior = "lognormal" if cfg.kernel == "rbf" else "gamma"
         lo = np.concatenate([np.full(d, math.log(0.025)), [math.log(1e-2)], [math.log(cfg.min_noise)]])
         hi = np.concatenate([np.full(d, math.log(20.0)), [math.log(1e2)], [math.log(1.0)]])
         if self._hyper is not None:
@@ -256,25 +262,22 @@ class BayesianOptimizer:
             s20, nz0 = cfg.outputscale, cfg.noise
         th0 = np.clip(np.concatenate([np.log(ls0), [math.log(s20)], [math.log(max(nz0, cfg.min_noise))]]), lo, hi)
         R = max(int(cfg.hyper_restarts), 1)
-        thetas = np.vstack([th0[None, :], self._rng.uniform(lo, hi, size=(R - 1, d + 2))]) if R > 1 else th0[None, :]
-        thetas[1:, :d] = self._rng.uniform(math.log(0.1), math.log(3.0), size=(R - 1, d))
-        thetas[1:, d] = self._rng.uniform(math.log(0.3), math.log(3.0), size=R - 1)
-        thetas[1:, d + 1] = self._rng.uniform(math.log(cfg.min_noise), math.log(1e-1), size=R - 1)
+        thetas = np.tile(th0, (R, 1))
+        if R > 1:
+            thetas[1:, :d] = self._rng.uniform(math.log(0.1), math.log(3.0), size=(R - 1, d))
+            thetas[1:, d] = self._rng.uniform(math.log(0.3), math.log(3.0), size=R - 1)
+            thetas[1:, d + 1] = self._rng.uniform(math.log(cfg.min_noise), math.log(1e-1), size=R - 1)
         lml, _, status = eng.lml_grad_batched(X, y, thetas, cfg.kernel)
-        lml = np.where(np.asarray(status) == 0, np.asarray(lml, dtype=np.float64), -np.inf)
-        best = int(np.argmax(lml))
-        if not np.isfinite(lml[best]):
+        score = np.asarray(lml, dtype=np.float64) + log_prior_and_grad(thetas, d, prior)[0]
+        score = np.where(np.asarray(status) == 0, score, -np.inf)
+        if not np.isfinite(score).any():
             return np.exp(th0[:d]), float(np.exp(th0[d])), float(np.exp(th0[d + 1]))
-
-        def negloglik(t):
-            l, g, s = eng.lml_grad_batched(X, y, t[None, :], cfg.kernel)
-            if int(s[0]) != 0 or not np.isfinite(float(l[0])):
-                return 1e300, np.zeros_like(t)
-            return -float(l[0]), -np.asarray(g[0], dtype=np.float64)
-
-        res = so.minimize(negloglik, thetas[best], jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)),
-                          options={"maxiter": int(cfg.hyper_maxiter)})
-        th = res.x if np.isfinite(res.fun) and -res.fun >= lml[best] else thetas[best]
+        keep = np.argsort(-score)[:max(1, int(cfg.hyper_refine))]
+        if 0 not in keep and np.isfinite(score[0]):
+            keep = np.concatenate([keep[:-1], [0]]) if len(keep) > 1 else np.array([0])      # always refine the warm start
+        th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas[keep], lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter))
+        if not np.isfinite(F) or F < score[keep].max():
+            th = thetas[keep[int(np.argmax(score[keep]))]]
         return np.exp(th[:d]), float(np.exp(th[d])), float(np.exp(th[d + 1]))
 
     def fit_gp_model(self):

@@ -164,3 +164,44 @@ def test_batched_lml_and_gradient_against_oracle(engine, n, d, kind, kname):
     engine.lml_grad_batched(_cuda(X), _cuda(y), thetas[:1], kname)
     m1, _ = engine.posterior(_cuda(X[:8]))
     assert torch.equal(m0, m1)
+
+
+def test_lockstep_map_fit_on_device_matches_oracle_scipy(engine):
+    """N1: MAP hyper-parameter fit driven by the batched device LML (one bo_lml_grad_batched per optimiser step)
+    reaches the optimum SciPy L-BFGS-B finds on the oracle's objective."""
+    import scipy.optimize as so
+    from bayesianoptimizer_b200.hyperfit import fit_map, log_prior_and_grad
+    n, d = 400, 5
+    X, y = synth_problem(n, d, 3, 4)
+    rng = np.random.default_rng(2)
+    lo = np.log(np.array([0.025] * d + [1e-2, 1e-4])); hi = np.log(np.array([20.0] * d + [1e2, 1.0]))
+    th0 = np.vstack([np.log([0.5] * d + [1.0, 1e-2]), rng.uniform(np.log(0.1), np.log(3), (7, d + 2))])
+    th0[1:, d + 1] = np.log(1e-2)
+    best, F, ths, Fs, nev = fit_map(engine, _cuda(X), _cuda(y), "matern52", th0, lo, hi, prior="gamma", maxiter=60)
+
+    def negF(t):
+        l, g = o.lml_and_grad(X, y, o.KERNEL_MATERN52, np.exp(t[:d]), np.exp(t[d]), np.exp(t[d + 1]))
+        lp, lg = log_prior_and_grad(t, d, "gamma")
+        return -(l + lp[0]), -(g + lg[0])
+    ref = max(-so.minimize(negF, t, jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)), options={"maxiter": 200}).fun
+              for t in th0[:3])
+    assert F >= ref - 1e-5 * max(1.0, abs(ref)), (F, ref)
+    # the reported objective is the oracle's objective at the reported point
+    assert abs(-negF(best)[0] - F) <= 1e-7 * max(1.0, abs(F))
+
+
+def test_lml_batch_larger_than_slot_group(engine):
+    """R > 32 restarts run as several lock-step groups; results are independent of the grouping."""
+    n, d = 256, 4
+    X, y = synth_problem(n, d, 5, 6)
+    rng = np.random.default_rng(3)
+    R = 70
+    th = np.concatenate([rng.uniform(np.log(0.2), np.log(2), (R, d)), rng.uniform(-0.5, 0.5, (R, 1)),
+                         rng.uniform(np.log(1e-3), np.log(1e-1), (R, 1))], axis=1)
+    lml, grad, st = engine.lml_grad_batched(_cuda(X), _cuda(y), th, "rbf")
+    assert st.tolist() == [0] * R
+    for r in (0, 31, 32, 69):
+        l1, g1, _ = engine.lml_grad_batched(_cuda(X), _cuda(y), th[r:r + 1], "rbf")
+        assert l1[0].item() == lml[r].item() and torch.equal(g1[0], grad[r])
+        l, g = o.lml_and_grad(X, y, o.KERNEL_RBF, np.exp(th[r, :d]), np.exp(th[r, d]), np.exp(th[r, d + 1]))
+        assert abs(lml[r].item() - l) <= 1e-8 * abs(l)

@@ -150,3 +150,40 @@ def test_cached_simulator_duck_type():
     assert out.dtype == np.float32 and out.shape == (8,)
     sim.cleanup()
     assert sim.cleaned
+
+
+def test_lockstep_lbfgs_matches_scipy_lbfgsb():
+    """hyperfit.lbfgs_lockstep (one batched LML call per step over all restarts) reaches SciPy L-BFGS-B's optimum
+    of the same MAP objective, including an active bound (fit_gpytorch_mll stand-in, Bayesian.py:93)."""
+    import scipy.optimize as so
+    from bayesianoptimizer_b200.hyperfit import fit_map, log_prior_and_grad
+    from conftest import synth_problem
+    from oracle import gp_oracle as o
+    rng = np.random.default_rng(0)
+    for n, d, prior in ((150, 3, "lognormal"), (120, 4, "gamma"), (100, 2, None)):
+        X, y = synth_problem(n, d, 1, 2)
+        lo = np.log(np.array([0.025] * d + [1e-2, 1e-4])); hi = np.log(np.array([20.0] * d + [1e2, 1.0]))
+        th0 = np.vstack([np.log([0.5] * d + [1.0, 1e-2]), rng.uniform(np.log(0.1), np.log(3), (3, d + 2))])
+        th0[1:, d + 1] = np.log(1e-2)
+        best, F, ths, Fs, nev = fit_map(OracleEngine(), X, y, "matern52", th0, lo, hi, prior=prior, maxiter=60)
+
+        def negF(t):
+            l, g = o.lml_and_grad(X, y, 0, np.exp(t[:d]), np.exp(t[d]), np.exp(t[d + 1]))
+            lp, lg = log_prior_and_grad(t, d, prior)
+            return -(l + lp[0]), -(g + lg[0])
+        ref = max(-so.minimize(negF, t, jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)), options={"maxiter": 200}).fun
+                  for t in th0)
+        assert F >= ref - 1e-5 * max(1.0, abs(ref)), (n, d, prior, F, ref)
+        assert np.all(best >= lo - 1e-12) and np.all(best <= hi + 1e-12)
+
+
+def test_prior_gradients_against_finite_differences():
+    from bayesianoptimizer_b200.hyperfit import log_prior_and_grad
+    th = np.random.default_rng(1).standard_normal((3, 7)) * 0.5
+    for prior in ("lognormal", "gamma", None):
+        lp, g = log_prior_and_grad(th, 5, prior)
+        fd = np.zeros_like(th)
+        for k in range(7):
+            e = np.zeros(7); e[k] = 1e-6
+            fd[:, k] = (log_prior_and_grad(th + e, 5, prior)[0] - log_prior_and_grad(th - e, 5, prior)[0]) / 2e-6
+        np.testing.assert_allclose(g, fd, atol=1e-6)
