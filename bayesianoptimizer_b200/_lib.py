@@ -55,6 +55,7 @@ SIGNATURES = {
     "bo_acq_grad": (C.c_int, [_vp, _i32, _f64, _f64, _f64, _vp, _i32, _vp, _vp, _vp]),
     "bo_append": (C.c_int, [_vp, _vp, _f64, _i32, _vp]),
     "bo_lml_grad_batched": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "bo_fps": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "bo_fp64_peak": (C.c_int, [_vp, _i32, _f64, _pd]),
     "bo_gemm_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _pd]),
     "bo_launch_count": (C.c_int64, [_vp]),

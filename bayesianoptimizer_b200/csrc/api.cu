@@ -10,6 +10,7 @@ int acq_grad_impl(bo_handle* h, int acq_kind, double best_f, double beta, double
 int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
                 const double* starts_dev, int k, int iters, double* x_dev, double* val_dev, cudaStream_t st);
 int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st);
+int fps_impl(bo_handle* h, const double* X_dev, int64_t N, int d, int m, int64_t start, int64_t* idx_dev, cudaStream_t st);
 int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops);
 int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st);
 int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
@@ -205,6 +206,11 @@ int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, 
 int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_host) {
     if (!h || !tflops_host) return BO_E_INVALID;
     return fp64_peak_impl(h, use_dmma, seconds, tflops_host);
+}
+
+int bo_fps(bo_handle* h, const double* X_dev, int64_t N, int32_t d, int32_t m, int64_t start, int64_t* idx_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return fps_impl(h, X_dev, N, d, m, start, idx_dev, (cudaStream_t)stream);
 }
 
 int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, int32_t reps, double* tflops_host) {

@@ -500,4 +500,67 @@ int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, c
     return 0;
 }
 
+
+// =================================================================================================
+// N3: greedy farthest-point sampling on the device (batch diversification / inducing-point selection,
+// optimization/Bayesian7.py:82-107, optimization/Bayesian6.py:88-107): m - 1 sequential rounds of
+// "distance to the newest pick -> running minimum -> arg-max (first index on ties)".  One persistent CTA;
+// the reference runs the same loop as m pairs of torch.cdist / argmax launches on the CPU.
+// =================================================================================================
+__global__ void __launch_bounds__(1024) fps_kernel(const double* __restrict__ X, long long N, int d, int m, long long start,
+                                                   double* __restrict__ dist, long long* __restrict__ idx_out) {
+    __shared__ double xp[BO_MAX_DIM];
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    __shared__ long long cur_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long cur = start;
+    if (tid == 0) idx_out[0] = start;
+    for (long long i = tid; i < N; i += 1024) dist[i] = INFINITY;
+    for (int round = 1; round < m; ++round) {
+        if (tid < d) xp[tid] = X[cur * d + tid];
+        __syncthreads();
+        double bv = -1.0; long long bi = 0x7fffffffffffffffLL;
+        for (long long i = tid; i < N; i += 1024) {
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) { const double df = X[i * d + k] - xp[k]; s = fma(df, df, s); }
+            const double dm = fmin(dist[i], s);
+            dist[i] = dm;
+            if (dm > bv) { bv = dm; bi = i; }                 // ascending i per thread: first index wins ties
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = sv[lane]; bi = si[lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { cur_s = bi; idx_out[round] = bi; }
+        }
+        __syncthreads();
+        cur = cur_s;
+    }
+}
+
+int fps_impl(bo_handle* h, const double* X_dev, int64_t N, int d, int m, int64_t start, int64_t* idx_dev, cudaStream_t st) {
+    if (!X_dev || !idx_dev || N < 1 || d < 1 || d > BO_MAX_DIM || m < 1 || start < 0 || start >= N)
+        return fail(h, BO_E_INVALID, "bo_fps: bad argument");
+    if (m > N) return fail(h, BO_E_INVALID, "bo_fps: m exceeds the number of points");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_qbuf(h, (size_t)N + 64);
+    if (rc) return rc;
+    fps_kernel<<<1, 1024, 0, st>>>(X_dev, N, d, m, start, h->qbuf, (long long*)idx_dev);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
 }  // namespace bo

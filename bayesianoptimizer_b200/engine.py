@@ -252,6 +252,14 @@ class GPEngine:
                                                   status.data_ptr(), _stream_ptr(self.device)))
         return lml, grad, status
 
+    def fps(self, X, m: int, start: int = 0) -> torch.Tensor:
+        """Indices of m farthest-point samples of X (N,d), greedy from ``start`` (Bayesian7.py:82-107)."""
+        X = self._dev64(X)
+        N, d = X.shape
+        idx = torch.empty(int(m), dtype=torch.int64, device=self.device)
+        self._check(self._lib.bo_fps(self._h, X.data_ptr(), N, d, int(m), int(start), idx.data_ptr(), _stream_ptr(self.device)))
+        return idx
+
     # -- diagnostics ------------------------------------------------------------------------------
     def fp64_peak_tflops(self, use_dmma: bool = True, seconds: float = 0.3) -> float:
         out = C.c_double(0.0)

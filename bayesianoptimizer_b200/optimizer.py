@@ -368,12 +368,7 @@ class BayesianOptimizer:
         K_big = max(K_big, min(q, N))
         idx = torch.topk(acq, K_big).indices
         pts = eng.sobol_points(sob, idx)
-        sel = [0]
-        dist = torch.cdist(pts, pts[0:1]).squeeze(1)
-        for _ in range(1, min(q, K_big)):
-            nxt = int(torch.argmax(dist).item())
-            sel.append(nxt)
-            dist = torch.minimum(dist, torch.cdist(pts, pts[nxt:nxt + 1]).squeeze(1))
+        sel = eng.fps(pts, min(q, K_big), 0)          # device FPS from the best-scoring candidate (Bayesian7.py:685)
         return pts[sel].to(self.device, dtype=torch.float64)
 
     def register(self, x_scaled, displacements=None):

@@ -157,6 +157,13 @@ int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, 
                         int32_t kernel_kind, double mean, const double* theta_host, int32_t R,
                         double* lml_host, double* grad_host, int32_t* status_host, void* stream);
 
+/* Greedy farthest-point sampling of m of the N points X_dev[N,d], starting from index `start`; picks go to
+ * idx_dev[m] in selection order (arg-max of the running min squared distance, first index on ties).
+ * Replaces farthest_point_sampling (optimization/Bayesian7.py:82-107, Bayesian6.py:88-107), which the reference
+ * runs on the CPU over the top-K pool (Bayesian7.py:679-688) and for inducing-point selection. */
+int bo_fps(bo_handle* h, const double* X_dev, int64_t N, int32_t d, int32_t m, int64_t start, int64_t* idx_dev,
+           void* stream);
+
 /* FP64 peak probe (DMMA.8x8x4 register-resident loop): the roofline denominator that
  * MEASURED_PEAKS.json lacks.  Returns TFLOP/s in *tflops_host. */
 int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_host);

@@ -388,3 +388,21 @@ def acquisition_with_grad(gp: GPFit, x, kind, best_f=0.0, beta=2.0, min_variance
         du = (dmu - u * dsig) / sigma
         return math.log(sigma) + h, dsig / sigma + dlogh * du
     raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------------------
+# farthest-point sampling (optimization/Bayesian7.py:82-107) with a fixed start index
+# --------------------------------------------------------------------------------------
+def fps(X, m, start=0):
+    """Greedy FPS: arg-max of the running minimum squared distance, first index on ties (torch.argmax)."""
+    X = np.asarray(X, dtype=np.float64)
+    idx = [int(start)]
+    dist = np.full(X.shape[0], np.inf)
+    for _ in range(1, m):
+        diff = X - X[idx[-1]]
+        s = np.zeros(X.shape[0])
+        for k in range(X.shape[1]):
+            s += diff[:, k] * diff[:, k]
+        dist = np.minimum(dist, s)
+        idx.append(int(np.argmax(dist)))
+    return np.array(idx, dtype=np.int64)

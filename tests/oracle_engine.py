@@ -93,5 +93,8 @@ class OracleEngine:
                 lml.append(-np.inf); grad.append(np.zeros(d + 2)); status.append(e.pivot)
         return torch.tensor(lml), torch.from_numpy(np.array(grad)), torch.tensor(status, dtype=torch.int32)
 
+    def fps(self, X, m, start=0):
+        return torch.from_numpy(o.fps(torch.as_tensor(X).cpu().numpy(), m, start))
+
     def close(self):
         pass

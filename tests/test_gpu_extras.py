@@ -205,3 +205,15 @@ def test_lml_batch_larger_than_slot_group(engine):
         assert l1[0].item() == lml[r].item() and torch.equal(g1[0], grad[r])
         l, g = o.lml_and_grad(X, y, o.KERNEL_RBF, np.exp(th[r, :d]), np.exp(th[r, d]), np.exp(th[r, d + 1]))
         assert abs(lml[r].item() - l) <= 1e-8 * abs(l)
+
+
+@pytest.mark.parametrize("N,d,m", [(8000, 5, 500), (1000, 3, 1000), (77, 16, 5), (5000, 5, 1)])
+def test_device_fps_matches_reference_algorithm(engine, N, d, m):
+    """bo_fps vs the greedy FPS of optimization/Bayesian7.py:82-107 (restated in the oracle), incl. duplicate points."""
+    X = np.random.default_rng(N).random((N, d))
+    X[N // 2] = X[3]                                   # an exact duplicate -> zero-distance tie handling
+    got = engine.fps(_cuda(X), m, start=7).cpu().numpy()
+    ref = o.fps(X, m, start=7)
+    assert np.array_equal(got, ref)
+    if m > 1:
+        assert len(set(got.tolist())) == min(m, N - 1) or m == N     # distinct picks until only duplicates remain
