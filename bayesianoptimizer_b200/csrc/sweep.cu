@@ -567,6 +567,8 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     if (!cand_dev && !sobol_host && N > 0) return fail(h, BO_E_INVALID, "bo_sweep: neither candidates nor a Sobol state given");
     if (topk > 0 && (!vals_dev || !idx_dev)) return fail(h, BO_E_INVALID, "bo_sweep: topk outputs missing");
     if (!(beta >= 0.0)) return fail(h, BO_E_INVALID, "bo_sweep: beta must be >= 0");
+    if (!cand_dev && N > 0 && first_index + N > (1LL << BO_SOBOL_BITS))
+        return fail(h, BO_E_CAPACITY, "bo_sweep: the 30-bit Sobol pool holds 2^30 points (torch.quasirandom.SobolEngine.MAXBIT)");
     BO_CUDA(h, cudaSetDevice(h->device));
     int rc;
     if (!cand_dev && N > 0 && (rc = upload_sobol(h, sobol_host, st))) return rc;

@@ -218,3 +218,26 @@ def test_full_size_c3_sample_against_oracle(engine):
         assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
         assert_acq_close(acq, ga.cpu().numpy(), av)
         assert idx.cpu().tolist() == ti.tolist()
+
+
+def test_n8192_fit_and_posterior_against_oracle(engine):
+    """Upper size of BASELINE config 4 (n_obs = 8192, d = 8): fit + posterior on a few candidates vs the oracle."""
+    n, d = 8192, 8
+    X, y = synth_problem(n, d, 7, 5)
+    gp = o.fit(X, y, o.KERNEL_MATERN52, 0.7, 1.0, 1e-3)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", 0.7, 1.0, 1e-3)
+    c = np.random.default_rng(3).random((130, d))
+    c[:2] = X[[5, 8000]]
+    mu, var = o.posterior(gp, c)
+    m, v = engine.posterior(torch.from_numpy(c).cuda())
+    assert_posterior_close(m.cpu().numpy(), v.cpu().numpy(), mu, var)
+    engine.release_workspace()
+
+
+def test_sobol_pool_limit_is_reported(engine):
+    from bayesianoptimizer_b200 import BoError, sobol_state
+    X, y = synth_problem(64, 2, 1, 2)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "rbf", 0.5, 1.0, 1e-2)
+    with pytest.raises(BoError) as ei:
+        engine.sweep("ei", 0.0, sobol=sobol_state(2, 1), first_index=(1 << 30) - 10, count=100, topk=1)
+    assert ei.value.code == -5
