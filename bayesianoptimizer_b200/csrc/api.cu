@@ -78,7 +78,7 @@ void bo_destroy(bo_handle* h) {
     cudaDeviceSynchronize();
     bo_release_workspace(h);
     lml_release(h);
-    void* ptrs[] = {h->qbuf, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
+    void* ptrs[] = {h->qbuf, h->split_ws, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
                     h->out_stage_val, h->out_stage_idx};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -86,6 +86,7 @@ struct bo_handle {
     // sweep workspaces
     double* panel = nullptr;     // [grid, np/SW_BK, SW_TILE] K(X*,X) panels, one per resident CTA
     size_t  panel_bytes = 0;
+    void*   split_ws = nullptr; size_t split_bytes = 0;   // small pools: per-(block, segment) partial sums + counters
     double* part_val = nullptr;  // [grid, BO_MAX_TOPK]
     int64_t* part_idx = nullptr;
     int     part_grid = 0;

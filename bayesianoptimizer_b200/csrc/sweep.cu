@@ -17,6 +17,7 @@
 namespace bo {
 
 constexpr long long IDX_EMPTY = 0x7fffffffffffffffLL;
+constexpr int SW_MAX_SEG = 16;
 
 struct SweepArgs {
     const double* Xs; const double* alpha; const double* Lp; double* panel;
@@ -28,6 +29,12 @@ struct SweepArgs {
     int topk; double* part_val; long long* part_idx;
     double* mean_out; double* var_out; double* acq_out;
     int flags;      // bit1: skip the all-zero 8x8 blocks of diagonal tiles (default on)
+    // small pools: every candidate block is split into G row segments (work items) so that all SMs are busy;
+    // segment s covers row blocks [seg[s], seg[s+1]) of L^-1, per-row-block column sums meet in global memory and the
+    // last-arriving CTA of a block runs the epilogue, adding them in ascending row-block order -- the same two
+    // chains the unsplit path keeps in registers, so the result is bit-identical for every split
+    int G; int seg[SW_MAX_SEG + 1];
+    double* part_cs; double* part_mu; int* counters;
 };
 
 // ---- analytic acquisition (botorch.acquisition.analytic semantics) ------
@@ -90,8 +97,8 @@ struct SweepSmem {
     static constexpr int OFF_TKV   = OFF_MU + SW_BN * 8;                // tk_val[64]
     static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;         // tk_idx[64]
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;         // acq[SW_BN]
-    static constexpr int OFF_CMASK = OFF_ACQ + SW_BN * 8;               // cmask[4]
-    static constexpr int OFF_SOB   = OFF_CMASK + 16;                    // dirs[16][30] + shift[16]
+    static constexpr int OFF_CMASK = OFF_ACQ + SW_BN * 8;               // cmask[4], is_last
+    static constexpr int OFF_SOB   = OFF_CMASK + 32;                    // dirs[16][30] + shift[16]
     static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
 };
 
@@ -106,6 +113,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
     long long* tki  = reinterpret_cast<long long*>(smem + SweepSmem::OFF_TKI);
     double* acq_s   = reinterpret_cast<double*>(smem + SweepSmem::OFF_ACQ);
     unsigned* cmask = reinterpret_cast<unsigned*>(smem + SweepSmem::OFF_CMASK);
+    int* is_last    = reinterpret_cast<int*>(smem + SweepSmem::OFF_CMASK + 16);
     uint32_t* dirs  = reinterpret_cast<uint32_t*>(smem + SweepSmem::OFF_SOB);
     uint32_t* shift = dirs + BO_MAX_DIM * BO_SOBOL_BITS;
 
@@ -130,7 +138,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
     int stage = 0; uint32_t phase = 0;      // consumer ring position
     int pstage = 0; uint32_t pphase = 0;    // producer ring position (thread 0 issues the TMA bulk copies)
 
-    for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+    for (long long w = blockIdx.x; w < a.nblocks * a.G; w += gridDim.x) {
+        const long long blk = w / a.G;
+        const int sg = (int)(w % a.G);
+        const int ib0 = a.seg[sg], ib1 = a.seg[sg + 1];      // row blocks of L^-1 handled by this work item
         // ================= phase A: candidates, K(X, X*) panel, posterior mean =================
         {
             double xc[2][DP];
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                 for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
             }
             double mu0 = 0.0, mu1 = 0.0;
-            const int nj8 = a.np >> 3;
+            const int nj8 = ib1 * (SW_BM / 8);               // panel rows this segment contracts over
             // PA_SL 8-row slices per iteration: 4 * PA_SL independent kernel evaluations per lane in flight
             constexpr int PA_SL = 4, PA_R = 2 * PA_SL;
             for (int j8 = 0; j8 < nj8; j8 += PA_SL) {
@@ -200,8 +211,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
 
         // ================= phase B: ||L^-1 k*||^2 on the DMMA path ============================
         {
-            const long long T = (long long)nbm * (nbm + 1) / 2 * KCH;     // pipeline stages of this block
-            int pib = 0, pkc = 0;                                          // producer position (thread 0)
+            const long long T = ((long long)ib1 * (ib1 + 1) / 2 - (long long)ib0 * (ib0 + 1) / 2) * KCH;   // pipeline stages of this item
+            int pib = ib0, pkc = 0;                                          // producer position (thread 0)
             long long issued = 0;
             auto issue = [&]() {
                 mbar_wait(&empty[pstage], pphase ^ 1);
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             double colsq[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) colsq[e] = 0.0;
-            for (int ib = 0; ib < nbm; ++ib) {
+            for (int ib = ib0; ib < ib1; ++ib) {
                 double acc[8][4][2];
 #pragma unroll
                 for (int mi = 0; mi < 8; ++mi)
@@ -281,31 +292,60 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     if (lane == 0) mbar_arrive(&empty[stage]);
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                 }
+                // canonical reduction (independent of the segment split): per row block, square-sum this thread's 8
+                // row groups, butterfly over the 8 row lanes, then add the row block's total to the running sum in
+                // ascending row-block order -- or park it in global memory for the finaliser to add in that order
 #pragma unroll
-                for (int mi = 0; mi < 8; ++mi)
+                for (int e = 0; e < 8; ++e) {
+                    double t = 0.0;
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) {
-                        colsq[ni * 2 + 0] = fma(acc[mi][ni][0], acc[mi][ni][0], colsq[ni * 2 + 0]);
-                        colsq[ni * 2 + 1] = fma(acc[mi][ni][1], acc[mi][ni][1], colsq[ni * 2 + 1]);
+                    for (int mi = 0; mi < 8; ++mi) t = fma(acc[mi][e >> 1][e & 1], acc[mi][e >> 1][e & 1], t);
+                    t += __shfl_xor_sync(0xffffffffu, t, 4);
+                    t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    if (a.G > 1) {
+                        if (g == 0)
+                            a.part_cs[(((size_t)blk * nbm + ib) * 2 + wm) * SW_BN + wn * 32 + (e >> 1) * 8 + 2 * q + (e & 1)] = t;
+                    } else {
+                        colsq[e] += t;
                     }
+                }
             }
+            if (g == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                double v = colsq[e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0) colsum[wm * SW_BN + wn * 32 + (e >> 1) * 8 + 2 * q + (e & 1)] = v;
+                for (int e = 0; e < 8; ++e) colsum[wm * SW_BN + wn * 32 + (e >> 1) * 8 + 2 * q + (e & 1)] = colsq[e];
             }
         }
         __syncthreads();
 
+        // ================= split blocks: publish partials, last arriver finalises =================
+        if (a.G > 1) {
+            if (tid < SW_BN && ib1 == nbm) a.part_mu[(size_t)blk * SW_BN + tid] = mu_s[tid];     // the last segment saw every row
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) *is_last = (atomicAdd(&a.counters[blk], 1) == a.G - 1) ? 1 : 0;
+            __syncthreads();
+            if (!*is_last) continue;                         // uniform: every thread reads the same flag
+            __threadfence();
+        }
         // ================= epilogue: variance, acquisition, CTA-local top-k =====================
         if (tid < SW_BN) {
             const long long li = blk * SW_BN + tid;
-            const double ss = colsum[tid] + colsum[SW_BN + tid];
+            double ss, mu_c;
+            if (a.G > 1) {
+                double r0 = 0.0, r1 = 0.0;                   // the same two ascending chains the unsplit path keeps in registers
+                for (int ib = 0; ib < nbm; ++ib) {
+                    r0 += __ldcg(a.part_cs + (((size_t)blk * nbm + ib) * 2 + 0) * SW_BN + tid);
+                    r1 += __ldcg(a.part_cs + (((size_t)blk * nbm + ib) * 2 + 1) * SW_BN + tid);
+                }
+                ss = r0 + r1;
+                mu_c = __ldcg(a.part_mu + (size_t)blk * SW_BN + tid);
+            } else {
+                ss = colsum[tid] + colsum[SW_BN + tid];
+                mu_c = mu_s[tid];
+            }
             const double var = fmax(a.hyp.outputscale - ss, a.min_var);
-            const double mean = a.hyp.mean + mu_s[tid];
+            const double mean = a.hyp.mean + mu_c;
             double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
             if (li < a.N) {
                 if (a.mean_out) a.mean_out[li] = mean;
@@ -496,6 +536,44 @@ __global__ void sobol_points_kernel(const bo_sobol* __restrict__ sob, const long
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// Choose the row-segment count G for a pool of `nblocks` candidate blocks: with fewer blocks than a few waves
+// of SMs, whole-block work items leave SMs idle (10^4 candidates = 79 blocks on 148 SMs), so blocks are split into
+// G stage-balanced row segments.  Cost model: waves(nblocks * G) * (1/G + panel build) + a small per-segment penalty.
+static int choose_segments(int sm, long long nblocks, int nbm, int* seg) {
+    int best = 1; double best_cost = 1e300;
+    const int gmax = nbm < SW_MAX_SEG ? nbm : SW_MAX_SEG;
+    if (nblocks >= 4LL * sm) { seg[0] = 0; seg[1] = nbm; return 1; }
+    for (int G = 1; G <= gmax; ++G) {
+        const double waves = (double)((nblocks * G + sm - 1) / sm);
+        const double cost = waves * (1.0 / G + 0.04) + 0.002 * G;   // the last segment rebuilds the whole panel (~4% of a block)
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = G; }
+    }
+    // stage-balanced boundaries: stages up to row block b  ~  b (b + 1) / 2
+    const double total = 0.5 * nbm * (nbm + 1.0);
+    seg[0] = 0;
+    for (int s2 = 1; s2 < best; ++s2) {
+        const double target = total * s2 / best;
+        int b = (int)floor((-1.0 + sqrt(1.0 + 8.0 * target)) / 2.0 + 0.5);
+        if (b <= seg[s2 - 1]) b = seg[s2 - 1] + 1;
+        if (b > nbm - (best - s2)) b = nbm - (best - s2);
+        seg[s2] = b;
+    }
+    seg[best] = nbm;
+    return best;
+}
+
+static int ensure_split_ws(bo_handle* h, long long nblocks, int G, int nbm) {
+    (void)G;
+    const size_t need = ((size_t)nblocks * nbm * 2 * SW_BN + (size_t)nblocks * SW_BN) * sizeof(double) + (size_t)nblocks * sizeof(int) + 256;
+    if (need > h->split_bytes) {
+        if (h->split_ws) cudaFree(h->split_ws);
+        h->split_ws = nullptr; h->split_bytes = 0;
+        BO_CUDA(h, cudaMalloc(&h->split_ws, need));
+        h->split_bytes = need;
+    }
+    return 0;
+}
+
 static int ensure_sweep_ws(bo_handle* h, int grid) {
     const size_t need = (size_t)grid * (h->np / SW_BK) * SW_TILE * sizeof(double);
     if (need > h->panel_bytes) {
@@ -614,8 +692,35 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
         return 0;
     }
 
-    const int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
+    {
+        const char* gs = getenv("BO_B200_SWEEP_SEGMENTS");      // test hook: force a segment count
+        a.G = choose_segments(h->sm_count, a.nblocks, h->np / SW_BM, a.seg);
+        if (gs && atoi(gs) >= 1) {
+            const int nbm = h->np / SW_BM;
+            int G = atoi(gs); if (G > nbm) G = nbm; if (G > SW_MAX_SEG) G = SW_MAX_SEG;
+            // re-use the balancing by pretending a pool that makes G optimal: simple equal-stage split
+            const double total = 0.5 * nbm * (nbm + 1.0);
+            a.seg[0] = 0;
+            for (int s2 = 1; s2 < G; ++s2) {
+                int b = (int)floor((-1.0 + sqrt(1.0 + 8.0 * total * s2 / G)) / 2.0 + 0.5);
+                if (b <= a.seg[s2 - 1]) b = a.seg[s2 - 1] + 1;
+                if (b > nbm - (G - s2)) b = nbm - (G - s2);
+                a.seg[s2] = b;
+            }
+            a.seg[G] = nbm; a.G = G;
+        }
+    }
+    const long long items = a.nblocks * a.G;
+    const int grid = (int)(items < h->sm_count ? items : h->sm_count);
     if ((rc = ensure_sweep_ws(h, grid))) return rc;
+    if (a.G > 1) {
+        const int nbm = h->np / SW_BM;
+        if ((rc = ensure_split_ws(h, a.nblocks, a.G, nbm))) return rc;
+        a.part_cs = reinterpret_cast<double*>(h->split_ws);              // [nblocks][nbm][2][128] row-block sums
+        a.part_mu = a.part_cs + (size_t)a.nblocks * nbm * 2 * SW_BN;
+        a.counters = reinterpret_cast<int*>(a.part_mu + (size_t)a.nblocks * SW_BN);
+        BO_CUDA(h, cudaMemsetAsync(a.counters, 0, (size_t)a.nblocks * sizeof(int), st));
+    }
     a.panel = h->panel; a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
     BO_CUDA(h, cudaEventRecord(h->ev0, st));
     if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep, h, a, grid, st))) return rc;
