@@ -29,15 +29,6 @@ __global__ void stage_inputs_kernel(const double* __restrict__ X, const double* 
     yv[i] = (i < n) ? y[i] : 0.0;
 }
 
-__global__ void rescale_inputs_kernel(int np, int d, Hyper hyp, const double* __restrict__ Xraw,
-                                      double* __restrict__ Xs) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
-#pragma unroll
-    for (int k = 0; k < BO_MAX_DIM; ++k)
-        Xs[(size_t)i * BO_MAX_DIM + k] = (k < d) ? Xraw[(size_t)i * BO_MAX_DIM + k] * hyp.inv_ls[k] : 0.0;
-}
-
 // ------------------------------------------------------------------------------------------
 // K1: Gram builder, lower triangle of K = k(X,X) + (noise + jitter) I, identity on the padding
 // ------------------------------------------------------------------------------------------
@@ -452,13 +443,6 @@ static int build_plan(bo_handle* h, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // capacity management
 // ------------------------------------------------------------------------------------------
-static void free_fit(bo_handle* h) {
-    double** ptrs[] = {&h->Xs, &h->Xraw, &h->yv, &h->alpha, &h->Lm, &h->Li, &h->Tw, &h->Lp, &h->vec1, &h->vec2, &h->vec3};
-    for (double** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
-    h->cap_np = 0;
-    h->plan_np = -1;
-}
-
 int ensure_capacity(bo_handle* h, int np, cudaStream_t st) {
     if (np <= h->cap_np) return 0;
     // grow geometrically past the first allocation so appends do not reallocate every time

@@ -18,8 +18,6 @@ struct LmlBatch {
     Hyper* hyps = nullptr; int* info = nullptr;
     Hyper* hyps_host = nullptr; double* out_host = nullptr; int* info_host = nullptr;     // pinned
     std::vector<GemmProblem> probs; std::vector<GemmLaunch> launches; GemmProblem* plan_dev = nullptr;
-    int kinv_launch = -1;
-    size_t bytes = 0;
 };
 
 static void lml_batch_free(LmlBatch* b) {
@@ -248,7 +246,6 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
             double* Li = b->Li + (size_t)s * mat;
             kinv.add(Li, ld, Li, ld, b->Kw + (size_t)s * mat, ld, np, np, np, 1.0, 0.0, 0, GEMM_TRANS_A | GEMM_LOWER_C | GEMM_K_FROM_MAX);
         }
-        b->kinv_launch = (int)b->launches.size();
         plan_push(kinv);
     }
     const size_t bytes = b->probs.size() * sizeof(GemmProblem);
