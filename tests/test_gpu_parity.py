@@ -275,3 +275,23 @@ def test_row_segment_split_is_deterministic_and_matches_oracle(engine, segments)
         del os.environ["BO_B200_SWEEP_SEGMENTS"]
     for t1, t2 in zip(runs[0], ref):
         assert torch.equal(t1, t2)
+
+
+def test_gpu_posterior_against_scikit_learn_gpr(engine):
+    """Independent check that does not go through our own oracle: scikit-learn's exact GPR on the reference's CSV rows."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern
+    g = load_golden("csv_n512_matern")
+    _fit_golden(engine, g)
+    kern = ConstantKernel(float(g["outputscale"])) * Matern(g["lengthscale"], nu=2.5)
+    gpr = GaussianProcessRegressor(kernel=kern, alpha=float(g["noise"]), optimizer=None).fit(g["X"], g["y"])
+    m_ref, s_ref = gpr.predict(g["cand"], return_std=True)
+    m, v = engine.posterior(torch.from_numpy(g["cand"]).cuda(), min_variance=0.0)
+    np.testing.assert_allclose(m.cpu().numpy(), m_ref, rtol=1e-7, atol=1e-8)
+    far = s_ref ** 2 > 1e-2          # sklearn's std**2 loses digits near the data
+    np.testing.assert_allclose(v.cpu().numpy()[far], (s_ref ** 2)[far], rtol=1e-7)
+    lml, _, st = engine.lml_grad_batched(torch.from_numpy(g["X"]).cuda(), torch.from_numpy(g["y"]).cuda(),
+                                         np.log(np.concatenate([g["lengthscale"], [float(g["outputscale"])], [float(g["noise"])]]))[None, :],
+                                         "matern52")
+    assert st[0].item() == 0
+    assert abs(lml[0].item() - gpr.log_marginal_likelihood_value_) <= 1e-8 * abs(gpr.log_marginal_likelihood_value_)
