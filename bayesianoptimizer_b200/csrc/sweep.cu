@@ -160,46 +160,75 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             }
             double mu0 = 0.0, mu1 = 0.0;
             const int nj8 = ib1 * (SW_BM / 8);               // panel rows this segment contracts over
-            // PA_SL 8-row slices per iteration: 4 * PA_SL independent kernel evaluations per lane in flight
+            // The scaled observations X~ and alpha are staged through the (idle) stage buffers in double-buffered
+            // chunks with cp.async, so the panel build reads them from shared memory instead of stalling on L2.
+            // PA_SL 8-row slices per iteration: 4 * PA_SL independent kernel evaluations per lane in flight.
             constexpr int PA_SL = 4, PA_R = 2 * PA_SL;
-            for (int j8 = 0; j8 < nj8; j8 += PA_SL) {
-                double x[PA_R][DP];                               // rows j8*8 + q + 4r
-                double al[PA_R];
-#pragma unroll
-                for (int r = 0; r < PA_R; ++r) {
-                    const int j = j8 * 8 + q + 4 * r;
-                    const double2* row = reinterpret_cast<const double2*>(a.Xs + (size_t)j * BO_MAX_DIM);
-#pragma unroll
-                    for (int k = 0; k < DP / 2; ++k) {
-                        const double2 t = __ldg(row + k);
-                        x[r][2 * k] = t.x; x[r][2 * k + 1] = t.y;
-                    }
-                    al[r] = __ldg(a.alpha + j);
+            constexpr int XCH = (DP <= 8) ? 1024 : 512;          // rows per chunk
+            constexpr int XP = DP + 2;                           // padded row pitch (doubles): conflict-free LDS.128 over 4 rows
+            constexpr int XBUF = XCH * XP + XCH;                 // doubles per buffer: rows + alpha
+            static_assert(2 * XBUF * 8 <= SW_STAGES * SweepSmem::STAGE_BYTES, "X~ staging must fit into the stage buffers");
+            double* xstage = reinterpret_cast<double*>(smem);
+            const int nrows = nj8 * 8;
+            const int nchunks = (nrows + XCH - 1) / XCH;
+            auto load_chunk = [&](int c) {
+                double* xb = xstage + (c & 1) * XBUF;
+                double* ab = xb + XCH * XP;
+                const int r0 = c * XCH, rows = min(XCH, nrows - r0);
+                for (int e = tid; e < rows * (DP / 2); e += SW_THREADS) {
+                    const int r = e / (DP / 2), k = e % (DP / 2);
+                    cp_async16(xb + r * XP + 2 * k, a.Xs + (size_t)(r0 + r) * BO_MAX_DIM + 2 * k);
                 }
-                double kv[2][PA_R];
-#pragma unroll
-                for (int gi = 0; gi < 2; ++gi)
+                for (int e = tid; e < rows / 2; e += SW_THREADS) cp_async16(ab + 2 * e, a.alpha + r0 + 2 * e);
+                cp_async_commit();
+            };
+            load_chunk(0);
+            for (int c = 0; c < nchunks; ++c) {
+                if (c + 1 < nchunks) { load_chunk(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+                __syncthreads();
+                const double* xb = xstage + (c & 1) * XBUF;
+                const double* ab = xb + XCH * XP;
+                const int j8_end = min(nj8, (c + 1) * (XCH / 8));
+                for (int j8 = c * (XCH / 8); j8 < j8_end; j8 += PA_SL) {
+                    double x[PA_R][DP];                               // rows j8*8 + q + 4r
+                    double al[PA_R];
 #pragma unroll
                     for (int r = 0; r < PA_R; ++r) {
-                        double sq = 0.0;
+                        const int jr = j8 * 8 + q + 4 * r - c * XCH;
+                        const double2* row = reinterpret_cast<const double2*>(xb + jr * XP);
 #pragma unroll
-                        for (int k = 0; k < DP; ++k) {
-                            const double df = xc[gi][k] - x[r][k];
-                            sq = fma(df, df, sq);
+                        for (int k = 0; k < DP / 2; ++k) {
+                            const double2 t = row[k];
+                            x[r][2 * k] = t.x; x[r][2 * k + 1] = t.y;
                         }
-                        const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
-                        kv[gi][r] = (j8 * 8 + q + 4 * r < a.n) ? v : 0.0;
+                        al[r] = ab[jr];
                     }
+                    double kv[2][PA_R];
 #pragma unroll
-                for (int r = 0; r < PA_R; ++r) { mu0 = fma(kv[0][r], al[r], mu0); mu1 = fma(kv[1][r], al[r], mu1); }
+                    for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
-                for (int gi = 0; gi < 2; ++gi)
+                        for (int r = 0; r < PA_R; ++r) {
+                            double sq = 0.0;
 #pragma unroll
-                    for (int hh = 0; hh < PA_SL; ++hh) {
-                        const int jj = j8 + hh;
-                        double* dst = panel + (size_t)(jj >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (jj & 3)) * 64 + lane * 2);
-                        *reinterpret_cast<double2*>(dst) = make_double2(kv[gi][2 * hh], kv[gi][2 * hh + 1]);
-                    }
+                            for (int k = 0; k < DP; ++k) {
+                                const double df = xc[gi][k] - x[r][k];
+                                sq = fma(df, df, sq);
+                            }
+                            const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
+                            kv[gi][r] = (j8 * 8 + q + 4 * r < a.n) ? v : 0.0;
+                        }
+#pragma unroll
+                    for (int r = 0; r < PA_R; ++r) { mu0 = fma(kv[0][r], al[r], mu0); mu1 = fma(kv[1][r], al[r], mu1); }
+#pragma unroll
+                    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+                        for (int hh = 0; hh < PA_SL; ++hh) {
+                            const int jj = j8 + hh;
+                            double* dst = panel + (size_t)(jj >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (jj & 3)) * 64 + lane * 2);
+                            *reinterpret_cast<double2*>(dst) = make_double2(kv[gi][2 * hh], kv[gi][2 * hh + 1]);
+                        }
+                }
+                __syncthreads();          // every warp is done with this buffer before chunk c + 2 overwrites it
             }
             mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
             mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
