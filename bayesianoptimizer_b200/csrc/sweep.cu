@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                 while (issued < T && issued < SW_STAGES - 1) issue();
 
             const int wm = warp >> 2, wn = warp & 3;
+            bool ready = false;              // full[stage] already observed complete by the early probe
             double colsq[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) colsq[e] = 0.0;
@@ -272,7 +273,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     // refill the slot released one iteration ago (prefetch distance SW_STAGES - 1)
                     if (tid == 0 && issued < T) issue();
                     __syncwarp();
-                    mbar_wait(&full[stage], phase);
+                    if (!ready) mbar_wait(&full[stage], phase);       // usually already probed half a stage ago
+                    const int nstage = (stage + 1 == SW_STAGES) ? 0 : stage + 1;
+                    const uint32_t nphase = (nstage == 0) ? phase ^ 1 : phase;
                     const double* As = reinterpret_cast<const double*>(smem + stage * SweepSmem::STAGE_BYTES);
                     const double* Bs = As + SW_TILE;
                     const int kdiag = kc - ib * KCH;                      // >= 0 inside the diagonal tile
@@ -283,6 +286,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
 #pragma unroll
                             for (int ni = 0; ni < 4; ++ni)
                                 b[ni] = *reinterpret_cast<const double2*>(Bs + (((wn * 4 + ni) * (SW_BK / 8) + k8) * 64 + lane * 2));
+                            // probe the next stage's barrier in the middle of this one: the ~90-cycle try_wait hides
+                            // behind the DMMA stream instead of idling the pipe at every stage boundary
+                            if (k8 == 2) ready = mbar_try_wait(&full[nstage], nphase);
 #pragma unroll
                             for (int mi = 0; mi < 8; ++mi) {
                                 const double2 av = *reinterpret_cast<const double2*>(As + (((wm * 8 + mi) * (SW_BK / 8) + k8) * 64 + lane * 2));
@@ -294,6 +300,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                             }
                         }
                     } else {
+                        ready = false;
                         // diagonal tile: 8x8 blocks strictly above the diagonal hold zeros -> skip their DMMAs
 #pragma unroll
                         for (int k8 = 0; k8 < SW_BK / 8; ++k8) {
