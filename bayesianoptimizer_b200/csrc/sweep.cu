@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
 #pragma unroll
                         for (int hh = 0; hh < PA_SL; ++hh) {
                             const int jj = j8 + hh;
-                            double* dst = panel + (size_t)(jj >> 2) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (jj & 3)) * 64 + lane * 2);
+                            double* dst = panel + (size_t)(jj / (SW_BK / 8)) * SW_TILE + (((warp + 8 * gi) * (SW_BK / 8) + (jj % (SW_BK / 8))) * 64 + lane * 2);
                             *reinterpret_cast<double2*>(dst) = make_double2(kv[gi][2 * hh], kv[gi][2 * hh + 1]);
                         }
                 }
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                                 b[ni] = *reinterpret_cast<const double2*>(Bs + (((wn * 4 + ni) * (SW_BK / 8) + k8) * 64 + lane * 2));
                             // probe the next stage's barrier in the middle of this one: the ~90-cycle try_wait hides
                             // behind the DMMA stream instead of idling the pipe at every stage boundary
-                            if (k8 == 2) ready = mbar_try_wait(&full[nstage], nphase);
+                            if (k8 == (SW_BK / 8) / 2) ready = mbar_try_wait(&full[nstage], nphase);
 #pragma unroll
                             for (int mi = 0; mi < 8; ++mi) {
                                 const double2 av = *reinterpret_cast<const double2*>(As + (((wm * 8 + mi) * (SW_BK / 8) + k8) * 64 + lane * 2));
