@@ -54,6 +54,8 @@ class GPConfig:
     cholesky_jitter: float = 1e-2        # retry value of Bayesian6.py:482-488
     standardize: bool = True             # botorch Standardize outcome transform
     seed: Optional[int] = None           # pool / LHS seed (the reference never seeds, run_optimization.py:38)
+    max_points: int = 49152              # exact-GP capacity guard (n = 32768 fits in 1 s / 25 GB on one B200); beyond it the
+                                         # model is fitted on the incumbent + a random subset (the reference switches to SVGP)
 
 
 class _Posterior:
@@ -290,6 +292,11 @@ class BayesianOptimizer:
         self._y_mean, self._y_std = mu, sd
         X = self.train_X.to(eng.device) if hasattr(eng, "device") else self.train_X
         y = y.to(X.device)
+        if X.shape[0] > int(cfg.max_points):
+            keep = self._rng.choice(X.shape[0], size=int(cfg.max_points), replace=False)
+            keep[0] = int(torch.argmax(y).item())                     # never drop the incumbent
+            keep = torch.as_tensor(np.unique(keep), device=X.device)
+            X, y = X[keep], y[keep]
         if cfg.fit_hyperparameters and self.train_X.shape[0] >= 2 * d:
             ls, s2, noise = self._fit_hyperparameters(eng, X, y)
         elif self._hyper is not None:
