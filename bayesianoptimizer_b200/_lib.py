@@ -15,7 +15,7 @@ BO_MAX_DIM = 16
 BO_MAX_TOPK = 64
 BO_SOBOL_BITS = 30
 
-KERNEL_MATERN52, KERNEL_RBF = 0, 1
+KERNEL_MATERN52, KERNEL_RBF, KERNEL_LINEAR_MATERN52 = 0, 1, 2
 ACQ_EI, ACQ_LOGEI, ACQ_UCB, ACQ_VAR, ACQ_MEAN = 0, 1, 2, 3, 4
 E_INVALID, E_CUDA, E_NOMEM, E_NOTFIT, E_CAPACITY = -1, -2, -3, -4, -5
 
@@ -43,6 +43,8 @@ SIGNATURES = {
     "bo_release_workspace": (C.c_int, [_vp]),
     "bo_fit": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _vp]),
     "bo_fit_host": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _vp]),
+    "bo_fit_ex": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _f64, _i32, _vp]),
+    "bo_posterior_multi": (C.c_int, [_vp, _vp, _i32, _pd, _vp, _i64, _f64, _vp, _vp, _vp]),
     "bo_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "bo_num_obs": (C.c_int, [_vp]),
     "bo_posterior": (C.c_int, [_vp, _vp, _i64, _f64, _vp, _vp, _vp]),

@@ -10,6 +10,8 @@ int acq_grad_impl(bo_handle* h, int acq_kind, double best_f, double beta, double
 int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
                 const double* starts_dev, int k, int iters, double* x_dev, double* val_dev, cudaStream_t st);
 int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st);
+int posterior_multi_impl(bo_handle* h, const double* Y_dev, int m, const double* means_host, const double* Xs_dev, int64_t N,
+                         double min_var, double* mean_dev, double* var_dev, cudaStream_t st);
 int fps_impl(bo_handle* h, const double* X_dev, int64_t N, int d, int m, int64_t start, int64_t* idx_dev, cudaStream_t st);
 int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops);
 int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st);
@@ -93,20 +95,14 @@ const char* bo_last_error(const bo_handle* h) { return h ? h->err.c_str() : "nul
 int bo_num_obs(const bo_handle* h) { return (h && h->fitted) ? h->n : 0; }
 int64_t bo_launch_count(const bo_handle* h) { return h ? h->launches : 0; }
 
-int bo_fit(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d, int32_t kernel_kind,
-           const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
-           void* stream) {
+int bo_fit_ex(bo_handle* h, const double* X, const double* y, int32_t n, int32_t d, int32_t kernel_kind,
+              const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
+              double linear_variance, int32_t host_inputs, void* stream) {
     if (!h) return BO_E_INVALID;
-    return fit_impl(h, X_dev, y_dev, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter,
-                    (cudaStream_t)stream);
-}
-
-int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_t n, int32_t d,
-                int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
-                double mean, double jitter, void* stream) {
-    if (!h) return BO_E_INVALID;
-    if (n < 1 || d < 1 || !X_host || !y_host) return fail(h, BO_E_INVALID, "bo_fit_host: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!host_inputs)
+        return fit_impl(h, X, y, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, linear_variance, st);
+    if (n < 1 || d < 1 || !X || !y) return fail(h, BO_E_INVALID, "bo_fit_host: bad argument");
     BO_CUDA(h, cudaSetDevice(h->device));
     const size_t need = ((size_t)n * d + n) * sizeof(double);
     if (need > h->cand_stage_bytes) {
@@ -116,9 +112,21 @@ int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_
         h->cand_stage_bytes = need;
     }
     double* Xd = h->cand_stage; double* yd = Xd + (size_t)n * d;
-    BO_CUDA(h, cudaMemcpyAsync(Xd, X_host, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
-    BO_CUDA(h, cudaMemcpyAsync(yd, y_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    return fit_impl(h, Xd, yd, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, st);
+    BO_CUDA(h, cudaMemcpyAsync(Xd, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+    BO_CUDA(h, cudaMemcpyAsync(yd, y, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    return fit_impl(h, Xd, yd, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, linear_variance, st);
+}
+
+int bo_fit(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d, int32_t kernel_kind,
+           const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
+           void* stream) {
+    return bo_fit_ex(h, X_dev, y_dev, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, 0.0, 0, stream);
+}
+
+int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_t n, int32_t d,
+                int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
+                double mean, double jitter, void* stream) {
+    return bo_fit_ex(h, X_host, y_host, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, 0.0, 1, stream);
 }
 
 int bo_get_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, void* stream) {
@@ -133,6 +141,12 @@ int bo_posterior(bo_handle* h, const double* Xs_dev, int64_t N, double min_varia
     if (!Xs_dev && N > 0) return fail(h, BO_E_INVALID, "bo_posterior: null candidates");
     return sweep_impl(h, BO_ACQ_MEAN, 0.0, 0.0, min_variance, Xs_dev, nullptr, 0, N, 0, nullptr, nullptr,
                       mean_dev, var_dev, nullptr, (cudaStream_t)stream);
+}
+
+int bo_posterior_multi(bo_handle* h, const double* Y_dev, int32_t m, const double* means_host, const double* Xs_dev,
+                       int64_t N, double min_variance, double* mean_dev, double* var_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return posterior_multi_impl(h, Y_dev, m, means_host, Xs_dev, N, min_variance, mean_dev, var_dev, (cudaStream_t)stream);
 }
 
 int bo_sweep(bo_handle* h, int32_t acq_kind, double best_f, double beta, double min_variance,

@@ -30,6 +30,8 @@ struct Hyper {
     int    d;          // true input dimension
     int    dp;         // padded dimension used by the templated kernels
     double inv_ls[BO_MAX_DIM];
+    double lin_w[BO_MAX_DIM];   // linear + Matern kind: v * l_k^2, so that v <x, x'> = sum_k lin_w[k] x~_k x~'_k on the scaled inputs
+    double lin_v;               // LinearKernel variance v (0 for the stationary kinds)
     double outputscale;
     double noise;
     double mean;
@@ -240,8 +242,14 @@ __device__ __forceinline__ double kernel_value_t(double sq, double outputscale) 
     return outputscale * exp_neg(0.5 * sq);
 }
 __device__ __forceinline__ double kernel_value(int kind, double sq, double outputscale) {
-    return kind == BO_KERNEL_MATERN52 ? kernel_value_t<BO_KERNEL_MATERN52>(sq, outputscale)
-                                      : kernel_value_t<BO_KERNEL_RBF>(sq, outputscale);
+    return kind == BO_KERNEL_RBF ? kernel_value_t<BO_KERNEL_RBF>(sq, outputscale)
+                                 : kernel_value_t<BO_KERNEL_MATERN52>(sq, outputscale);      // also the Matern part of kind 2
+}
+// full kernel from the scaled squared distance and the weighted inner product lin = sum_k lin_w[k] x~_k x~'_k
+template <int KIND>
+__device__ __forceinline__ double kernel_pair_t(double sq, double lin, double outputscale) {
+    if (KIND == BO_KERNEL_LINEAR_MATERN52) return fma(outputscale, lin, kernel_value_t<BO_KERNEL_MATERN52>(sq, outputscale));
+    return kernel_value_t<KIND>(sq, outputscale);
 }
 
 // better-than order of the top-k: value desc, index asc
@@ -255,7 +263,7 @@ __device__ __forceinline__ bool tk_better(double va, long long ia, double vb, lo
 namespace bo {
 int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
              const double* ls_host, double outputscale, double noise, double mean, double jitter,
-             cudaStream_t st);
+             double linear_variance, cudaStream_t st);
 int ensure_capacity(bo_handle* h, int np, cudaStream_t st);
 int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
                const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N,

@@ -89,14 +89,19 @@ __global__ void __launch_bounds__(256) kq_build_kernel(const double* __restrict_
     if (j >= np) return;
     double kval = 0.0, g = 0.0;
     if (j < n) {
-        double sq = 0.0;
+        double sq = 0.0, lin = 0.0;
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
             const double xq = (k < d) ? Xq[(size_t)qi * d + k] * hyp.inv_ls[k] : 0.0;
-            const double df = xq - Xs[(size_t)j * BO_MAX_DIM + k];
+            const double xj = Xs[(size_t)j * BO_MAX_DIM + k];
+            const double df = xq - xj;
             sq = fma(df, df, sq);
+            lin = fma(hyp.lin_w[k] * xq, xj, lin);
         }
-        if (hyp.kind == BO_KERNEL_MATERN52) {
+        if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+            kval = fma(hyp.outputscale, lin, kernel_value_t<BO_KERNEL_MATERN52>(sq, hyp.outputscale));
+            g = 0.0;                         // gradients are not supported for this kind (pool-based acquisition only)
+        } else if (hyp.kind == BO_KERNEL_MATERN52) {
             const double s5 = 2.23606797749978969640917366873128;
             const double r = sqrt(sq), e = exp(-s5 * r);
             kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, r, 1.0)) * e;
@@ -306,6 +311,9 @@ static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, doub
 
 static int check_query_args(bo_handle* h, int acq_kind, double beta, const void* a, const void* b, const void* c, int k) {
     if (!h->fitted) return fail(h, BO_E_NOTFIT, "acquisition gradient / refinement before a successful bo_fit");
+    if (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52)
+        return fail(h, BO_E_INVALID, "acquisition gradients / refinement are not implemented for the linear + Matern kernel "
+                                     "(the reference uses it with pool-based acquisition only, Bayesian7.py:650-688)");
     if (acq_kind < BO_ACQ_EI || acq_kind > BO_ACQ_MEAN) return fail(h, BO_E_INVALID, "unknown acquisition kind");
     if (!a || !b || !c || k < 1) return fail(h, BO_E_INVALID, "bad query arguments");
     if (k > 4096) return fail(h, BO_E_CAPACITY, "at most 4096 query points per call");
@@ -431,7 +439,13 @@ __global__ void __launch_bounds__(1024) append_finalize_kernel(int n, int np, in
     }
     __syncthreads();
     ss = bc[0]; ka = bc[1];
-    const double lam2 = hyp.outputscale + hyp.noise + hyp.jitter - ss;
+    double prior = hyp.outputscale;
+    if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+        double nn = 0.0;
+        for (int k = 0; k < d; ++k) nn = fma(hyp.lin_v * x[k], x[k], nn);
+        prior = hyp.outputscale * (nn + 1.0);
+    }
+    const double lam2 = prior + hyp.noise + hyp.jitter - ss;
     if (!(lam2 > 0.0)) { if (tid == 0) *info = n + 1; return; }
     const double lam = sqrt(lam2), ilam = 1.0 / lam;
     const double ynew = believer ? hyp.mean + ka : y;
@@ -560,6 +574,92 @@ int fps_impl(bo_handle* h, const double* X_dev, int64_t N, int d, int m, int64_t
     if (rc) return rc;
     fps_kernel<<<1, 1024, 0, st>>>(X_dev, N, d, m, start, h->qbuf, (long long*)idx_dev);
     BO_LAUNCH_CHECK(h);
+    return 0;
+}
+
+
+// =================================================================================================
+// N4: m outputs sharing the fitted kernel matrix -- one Cholesky, m right-hand sides
+// =================================================================================================
+__global__ void multi_resid_kernel(const double* __restrict__ Y, int n, int np, int m, int t, double mean, double* __restrict__ r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) r[i] = (i < n) ? Y[(size_t)i * m + t] - mean : 0.0;
+}
+
+// mean[c][t] = means[t] + sum_j k(x*_c, X_j) A[t][j]: one warp per candidate, kernel evaluations shared by the m outputs
+template <int DP, int MO>
+__global__ void __launch_bounds__(256) multi_mean_kernel(const double* __restrict__ Xs, int n, int np, Hyper hyp,
+                                                         const double* __restrict__ Xq, int d, long long N,
+                                                         const double* __restrict__ A /*[m][np]*/, int m, int t0,
+                                                         const double* __restrict__ means, double* __restrict__ out /*[N][m]*/) {
+    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= N) return;
+    double xq[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xq[k] = (k < d) ? Xq[(size_t)c * d + k] * hyp.inv_ls[k] : 0.0;
+    double acc[MO];
+#pragma unroll
+    for (int t = 0; t < MO; ++t) acc[t] = 0.0;
+    for (int j = lane; j < n; j += 32) {
+        double sq = 0.0, lin = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            const double xj = Xs[(size_t)j * BO_MAX_DIM + k];
+            const double df = xq[k] - xj;
+            sq = fma(df, df, sq);
+            lin = fma(hyp.lin_w[k] * xq[k], xj, lin);
+        }
+        double kv = kernel_value(hyp.kind, sq, hyp.outputscale);
+        if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) kv = fma(hyp.outputscale, lin, kv);
+#pragma unroll
+        for (int t = 0; t < MO; ++t)
+            if (t0 + t < m) acc[t] = fma(kv, A[(size_t)(t0 + t) * np + j], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < MO; ++t) {
+        double v = acc[t];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && t0 + t < m) out[(size_t)c * m + t0 + t] = means[t0 + t] + v;
+    }
+}
+
+int solve_alpha_rhs(bo_handle* h, const double* r, double* alpha_out, cudaStream_t st);   // fit.cu
+
+template <int DP>
+static int launch_multi_mean(bo_handle* h, const double* Xq, long long N, const double* A, int m, const double* means,
+                             double* out, cudaStream_t st) {
+    for (int t0 = 0; t0 < m; t0 += 8) {
+        multi_mean_kernel<DP, 8><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(h->Xs, h->n, h->np, h->hyp, Xq, h->d, N, A, m, t0, means, out);
+        BO_LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+int posterior_multi_impl(bo_handle* h, const double* Y_dev, int m, const double* means_host, const double* Xs_dev, int64_t N,
+                         double min_var, double* mean_dev, double* var_dev, cudaStream_t st) {
+    if (!h->fitted) return fail(h, BO_E_NOTFIT, "bo_posterior_multi before a successful bo_fit");
+    if (!Y_dev || m < 1 || m > 64 || N < 0 || (N > 0 && (!Xs_dev || !mean_dev))) return fail(h, BO_E_INVALID, "bo_posterior_multi: bad argument");
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const int np = h->np;
+    int rc = ensure_qbuf(h, (size_t)(m + 1) * np + 128);
+    if (rc) return rc;
+    double* A = h->qbuf;                         // [m][np] alphas
+    double* r = A + (size_t)m * np;              // residual staging
+    double* means_dev = r + np;                  // [m]
+    std::vector<double> means(m, 0.0);
+    if (means_host) for (int t = 0; t < m; ++t) means[t] = means_host[t];
+    BO_CUDA(h, cudaMemcpyAsync(means_dev, means.data(), m * sizeof(double), cudaMemcpyHostToDevice, st));
+    BO_CUDA(h, cudaStreamSynchronize(st));       // `means` is a pageable temporary
+    for (int t = 0; t < m; ++t) {
+        multi_resid_kernel<<<(np + 255) / 256, 256, 0, st>>>(Y_dev, h->n, np, m, t, means[t], r);
+        BO_LAUNCH_CHECK(h);
+        if ((rc = solve_alpha_rhs(h, r, A + (size_t)t * np, st))) return rc;
+    }
+    if (N > 0 && (rc = BO_DISPATCH_DP(h->dp, launch_multi_mean, h, Xs_dev, N, A, m, means_dev, mean_dev, st))) return rc;
+    if (var_dev && N > 0)
+        return sweep_impl(h, BO_ACQ_MEAN, 0.0, 0.0, min_var, Xs_dev, nullptr, 0, N, 0, nullptr, nullptr, nullptr, var_dev, nullptr, st);
     return 0;
 }
 

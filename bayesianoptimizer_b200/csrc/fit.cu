@@ -42,23 +42,25 @@ __device__ __forceinline__ void gram_body(const double* __restrict__ Xs, int n, 
     double xj[DP];
 #pragma unroll
     for (int k = 0; k < DP; ++k) xj[k] = Xs[(size_t)j * BO_MAX_DIM + k];
-    const double diag = hyp.outputscale + hyp.noise + hyp.jitter;
+    const bool lin_kind = hyp.kind == BO_KERNEL_LINEAR_MATERN52;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int i = i0 + threadIdx.y + r * 8;
         double v;
         if (i >= n || j >= n) {
             v = (i == j) ? 1.0 : 0.0;
-        } else if (i == j) {
-            v = diag;
         } else {
-            double sq = 0.0;
+            double sq = 0.0, lin = 0.0;
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                double df = Xs[(size_t)i * BO_MAX_DIM + k] - xj[k];
+                const double xi = Xs[(size_t)i * BO_MAX_DIM + k];
+                const double df = xi - xj[k];
                 sq = fma(df, df, sq);
+                lin = fma(hyp.lin_w[k] * xi, xj[k], lin);
             }
-            v = kernel_value(hyp.kind, sq, hyp.outputscale);
+            if (i == j) v = hyp.outputscale * (lin_kind ? lin + 1.0 : 1.0) + hyp.noise + hyp.jitter;   // exact diagonal
+            else v = lin_kind ? fma(hyp.outputscale, lin, kernel_value(hyp.kind, sq, hyp.outputscale))
+                              : kernel_value(hyp.kind, sq, hyp.outputscale);
         }
         if (j <= i) K[(size_t)i * ld + j] = v;
     }
@@ -510,20 +512,24 @@ __global__ void sub_vec_kernel(const double* __restrict__ a, const double* __res
 // alpha = (L L^T)^-1 r via the explicit inverse, plus one step of iterative refinement against the factor:
 //   alpha0 = Li^T (Li r) ; r2 = r - L (L^T alpha0) ; alpha = alpha0 + Li^T (Li r2)
 // (four HBM-bound triangular mat-vecs; makes alpha as accurate as a backward-stable cho_solve)
-static int solve_alpha(bo_handle* h, cudaStream_t st) {
+int solve_alpha_rhs(bo_handle* h, const double* r, double* alpha_out, cudaStream_t st) {
     const int np = h->np;
     int rc;
-    resid_init_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->yv, h->n, np, h->hyp.mean, h->vec1);      // vec1 = r
-    BO_LAUNCH_CHECK(h);
-    if ((rc = trmv_lower_m(h, h->Li, h->vec1, h->vec2, st))) return rc;                              // vec2 = Li r
-    if ((rc = trmv_lower_t_m(h, h->Li, h->vec2, h->alpha, 0, st))) return rc;                        // alpha0
-    if ((rc = trmv_lower_t_m(h, h->Lm, h->alpha, h->vec2, 0, st))) return rc;                        // vec2 = L^T alpha0
+    if ((rc = trmv_lower_m(h, h->Li, r, h->vec2, st))) return rc;                                    // vec2 = Li r
+    if ((rc = trmv_lower_t_m(h, h->Li, h->vec2, alpha_out, 0, st))) return rc;                       // alpha0
+    if ((rc = trmv_lower_t_m(h, h->Lm, alpha_out, h->vec2, 0, st))) return rc;                       // vec2 = L^T alpha0
     if ((rc = trmv_lower_m(h, h->Lm, h->vec2, h->vec3, st))) return rc;                              // vec3 = L vec2
-    sub_vec_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->vec1, h->vec3, np, h->vec2);                 // vec2 = r2
+    sub_vec_kernel<<<(np + 255) / 256, 256, 0, st>>>(r, h->vec3, np, h->vec2);                       // vec2 = r2
     BO_LAUNCH_CHECK(h);
     if ((rc = trmv_lower_m(h, h->Li, h->vec2, h->vec3, st))) return rc;
-    if ((rc = trmv_lower_t_m(h, h->Li, h->vec3, h->alpha, 1, st))) return rc;
+    if ((rc = trmv_lower_t_m(h, h->Li, h->vec3, alpha_out, 1, st))) return rc;
     return 0;
+}
+static int solve_alpha(bo_handle* h, cudaStream_t st) {
+    const int np = h->np;
+    resid_init_kernel<<<(np + 255) / 256, 256, 0, st>>>(h->yv, h->n, np, h->hyp.mean, h->vec1);      // vec1 = r
+    BO_LAUNCH_CHECK(h);
+    return solve_alpha_rhs(h, h->vec1, h->alpha, st);
 }
 
 int refit_factor(bo_handle* h, cudaStream_t st) {
@@ -599,10 +605,12 @@ int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv
 
 int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
              const double* ls_host, double outputscale, double noise, double mean, double jitter,
-             cudaStream_t st) {
+             double linear_variance, cudaStream_t st) {
     if (n < 1 || d < 1 || !X_dev || !y_dev || !ls_host) return fail(h, BO_E_INVALID, "bo_fit: bad argument");
     if (d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_fit: d exceeds BO_MAX_DIM");
-    if (kind != BO_KERNEL_MATERN52 && kind != BO_KERNEL_RBF) return fail(h, BO_E_INVALID, "bo_fit: unknown kernel kind");
+    if (kind != BO_KERNEL_MATERN52 && kind != BO_KERNEL_RBF && kind != BO_KERNEL_LINEAR_MATERN52)
+        return fail(h, BO_E_INVALID, "bo_fit: unknown kernel kind");
+    if (kind == BO_KERNEL_LINEAR_MATERN52 && !(linear_variance >= 0.0)) return fail(h, BO_E_INVALID, "bo_fit: linear variance must be >= 0");
     if (!(outputscale > 0.0) || !(noise >= 0.0) || !(jitter >= 0.0)) return fail(h, BO_E_INVALID, "bo_fit: bad hyper-parameter");
     for (int k = 0; k < d; ++k) if (!(ls_host[k] > 0.0)) return fail(h, BO_E_INVALID, "bo_fit: lengthscale must be positive");
     BO_CUDA(h, cudaSetDevice(h->device));
@@ -613,7 +621,11 @@ int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     h->n = n; h->np = np; h->d = d; h->dp = pad_dim(d);
     Hyper& hy = h->hyp;
     hy.kind = kind; hy.d = d; hy.dp = h->dp; hy.outputscale = outputscale; hy.noise = noise; hy.mean = mean; hy.jitter = jitter;
-    for (int k = 0; k < BO_MAX_DIM; ++k) hy.inv_ls[k] = k < d ? 1.0 / ls_host[k] : 0.0;
+    hy.lin_v = kind == BO_KERNEL_LINEAR_MATERN52 ? linear_variance : 0.0;
+    for (int k = 0; k < BO_MAX_DIM; ++k) {
+        hy.inv_ls[k] = k < d ? 1.0 / ls_host[k] : 0.0;
+        hy.lin_w[k] = k < d ? hy.lin_v * ls_host[k] * ls_host[k] : 0.0;
+    }
     stage_inputs_kernel<<<(np + 127) / 128, 128, 0, st>>>(X_dev, y_dev, n, d, np, hy, h->Xraw, h->Xs, h->yv);
     BO_LAUNCH_CHECK(h);
     return refit_factor(h, st);

@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __rest
     const double* Lm = Lm_all + s * np * ld;
     const int bj = blockIdx.x, bi = blockIdx.y;
     const int tile = bi * gridDim.x + bj;
-    double* part = part_all + (s * gridDim.x * gridDim.y + tile) * (DP + 4);
-    double acc[DP + 4];
+    double* part = part_all + (s * gridDim.x * gridDim.y + tile) * (DP + 6);
+    double acc[DP + 6];
 #pragma unroll
-    for (int k = 0; k < DP + 4; ++k) acc[k] = 0.0;
+    for (int k = 0; k < DP + 6; ++k) acc[k] = 0.0;
     if (bj <= bi) {
         const int j = bj * 32 + (threadIdx.x & 31);
         double xj[DP];
@@ -64,21 +64,25 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __rest
             const int i = bi * 32 + (threadIdx.x >> 5) + r * 8;
             if (i >= n || j >= n || j > i) continue;
             const double w = alpha[i] * aj - Kinv[(size_t)i * ld + j];
+            double sq = 0.0, lin = 0.0, df2[DP];
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const double xi = Xs[(size_t)i * BO_MAX_DIM + k];
+                const double df = xi - xj[k];
+                df2[k] = df * df;
+                sq += df2[k];
+                lin = fma(hyp.lin_w[k] * xi, xj[k], lin);
+            }
+            const double klin = hyp.outputscale * lin;              // s2 v <x_i, x_j>  (0 for the stationary kinds)
             if (i == j) {
                 acc[DP + 1] += w;                                   // trace(W)
                 acc[DP + 2] += log(Lm[(size_t)i * ld + i]);         // log det / 2
                 acc[DP + 3] += (yv[i] - hyp.mean) * alpha[i];       // quadratic form
+                acc[DP + 5] = fma(w, klin, acc[DP + 5]);            // sum_i W_ii s2 v |x_i|^2
                 continue;
             }
-            double sq = 0.0, df2[DP];
-#pragma unroll
-            for (int k = 0; k < DP; ++k) {
-                const double df = Xs[(size_t)i * BO_MAX_DIM + k] - xj[k];
-                df2[k] = df * df;
-                sq += df2[k];
-            }
             double kval, G;
-            if (hyp.kind == BO_KERNEL_MATERN52) {
+            if (hyp.kind != BO_KERNEL_RBF) {
                 const double s5 = 2.23606797749978969640917366873128;
                 const double rr = sqrt_pos(sq), e = exp_neg(s5 * rr);
                 kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, rr, 1.0)) * e;
@@ -90,11 +94,12 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __rest
             const double wg = w * G;
 #pragma unroll
             for (int k = 0; k < DP; ++k) acc[k] = fma(wg, df2[k], acc[k]);
-            acc[DP] = fma(w, kval, acc[DP]);
+            acc[DP] = fma(w, kval + klin, acc[DP]);
+            acc[DP + 4] = fma(w, klin, acc[DP + 4]);                // sum_{i>j} W_ij s2 v <x_i, x_j>
         }
     }
 #pragma unroll
-    for (int k = 0; k < DP + 4; ++k) {
+    for (int k = 0; k < DP + 6; ++k) {
         double v = acc[k];
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -115,14 +120,14 @@ template <int DP>
 __global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restrict__ part_all, int tiles, int n, int d,
                                                          const Hyper* __restrict__ hyps, double* __restrict__ out_all) {
     __shared__ double red[8];
-    __shared__ double tot[DP + 4];
+    __shared__ double tot[DP + 6];
     const size_t s = blockIdx.x;
     const Hyper& hyp = hyps[s];
-    const double* part = part_all + s * tiles * (DP + 4);
-    double* out = out_all + s * (BO_MAX_DIM + 3);
-    for (int k = 0; k < DP + 4; ++k) {
+    const double* part = part_all + s * tiles * (DP + 6);
+    double* out = out_all + s * (BO_MAX_DIM + 4);
+    for (int k = 0; k < DP + 6; ++k) {
         double v = 0.0;
-        for (int t = threadIdx.x; t < tiles; t += 256) v += part[(size_t)t * (DP + 4) + k];
+        for (int t = threadIdx.x; t < tiles; t += 256) v += part[(size_t)t * (DP + 6) + k];
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         __syncthreads();
@@ -139,8 +144,9 @@ __global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restric
     const double trW = tot[DP + 1], logdet_half = tot[DP + 2], quad = tot[DP + 3];
     out[0] = -0.5 * quad - logdet_half - 0.5 * n * 1.83787706640934548356;        // log(2 pi)
     for (int k = 0; k < d; ++k) out[1 + k] = tot[k];                               // pairs i>j count twice in the 1/2 sum
-    out[1 + d] = tot[DP] + 0.5 * hyp.outputscale * trW;                            // d / d log outputscale
+    out[1 + d] = tot[DP] + 0.5 * (hyp.outputscale * trW + tot[DP + 5]);            // d / d log outputscale
     out[2 + d] = 0.5 * hyp.noise * trW;                                            // d / d log noise
+    out[3 + d] = tot[DP + 4] + 0.5 * tot[DP + 5];                                  // d / d log linear variance (kind 2)
 }
 
 template <int DP>
@@ -174,13 +180,13 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
     struct { double** p; size_t elems; } reqs[] = {
         {&b->Xraw, c * BO_MAX_DIM}, {&b->yv, c}, {&b->Xs, S * c * BO_MAX_DIM}, {&b->Lm, S * mat}, {&b->Li, S * mat},
         {&b->Tw, S * (mat / 4 + 64)}, {&b->Kw, S * mat}, {&b->alpha, S * c}, {&b->v1, S * c}, {&b->v2, S * c}, {&b->v3, S * c},
-        {&b->tpart, (size_t)S * TRMVT_SPLITS * c}, {&b->gpart, S * nt * nt * (dp + 4)}, {&b->out, (size_t)S * (BO_MAX_DIM + 3)}};
+        {&b->tpart, (size_t)S * TRMVT_SPLITS * c}, {&b->gpart, S * nt * nt * (dp + 6)}, {&b->out, (size_t)S * (BO_MAX_DIM + 4)}};
     cudaError_t e = cudaSuccess;
     for (auto& r : reqs) if (e == cudaSuccess) e = cudaMalloc(r.p, r.elems * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&b->hyps, S * sizeof(Hyper));
     if (e == cudaSuccess) e = cudaMalloc(&b->info, S * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&b->hyps_host, S * sizeof(Hyper));
-    if (e == cudaSuccess) e = cudaMallocHost(&b->out_host, (size_t)S * (BO_MAX_DIM + 3) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->out_host, (size_t)S * (BO_MAX_DIM + 4) * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost(&b->info_host, S * sizeof(int));
     if (e != cudaSuccess) {
         lml_batch_free(b);
@@ -272,7 +278,9 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     if (!X_dev || !y_dev || !theta_host || !lml_host || !grad_host || !status_host || n < 1 || d < 1 || R < 1)
         return fail(h, BO_E_INVALID, "bo_lml_grad_batched: bad argument");
     if (d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_lml_grad_batched: d exceeds BO_MAX_DIM");
-    if (kind != BO_KERNEL_MATERN52 && kind != BO_KERNEL_RBF) return fail(h, BO_E_INVALID, "bo_lml_grad_batched: unknown kernel kind");
+    if (kind != BO_KERNEL_MATERN52 && kind != BO_KERNEL_RBF && kind != BO_KERNEL_LINEAR_MATERN52)
+        return fail(h, BO_E_INVALID, "bo_lml_grad_batched: unknown kernel kind");
+    const int p = d + 2 + (kind == BO_KERNEL_LINEAR_MATERN52 ? 1 : 0);          // parameters per restart
     BO_CUDA(h, cudaSetDevice(h->device));
     const int np = round_up(n, PAD);
     // slots: as many restarts in lock step as ~6 GB of workspace allows (4 n^2 doubles per slot), at most 32
@@ -292,10 +300,14 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     for (int r0 = 0; r0 < R; r0 += S) {
         const int Sa = std::min(S, R - r0);
         for (int s = 0; s < Sa; ++s) {
-            const double* th = theta_host + (size_t)(r0 + s) * (d + 2);
+            const double* th = theta_host + (size_t)(r0 + s) * p;
             Hyper& hy = b->hyps_host[s];
             hy.kind = kind; hy.d = d; hy.dp = b->dp; hy.mean = mean; hy.jitter = 0.0;
-            for (int k = 0; k < BO_MAX_DIM; ++k) hy.inv_ls[k] = k < d ? exp(-th[k]) : 0.0;
+            hy.lin_v = kind == BO_KERNEL_LINEAR_MATERN52 ? exp(th[d + 2]) : 0.0;
+            for (int k = 0; k < BO_MAX_DIM; ++k) {
+                hy.inv_ls[k] = k < d ? exp(-th[k]) : 0.0;
+                hy.lin_w[k] = k < d ? hy.lin_v * exp(2.0 * th[k]) : 0.0;
+            }
             hy.outputscale = exp(th[d]); hy.noise = exp(th[d + 1]);
         }
         BO_CUDA(h, cudaMemcpyAsync(b->hyps, b->hyps_host, Sa * sizeof(Hyper), cudaMemcpyHostToDevice, st));
@@ -330,20 +342,20 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
         h->launches += 11;
         BO_CUDA(h, cudaGetLastError());
         if ((rc = BO_DISPATCH_DP(b->dp, lml_launch_grad, h, b, Sa, st))) return rc;
-        BO_CUDA(h, cudaMemcpyAsync(b->out_host, b->out, (size_t)Sa * (BO_MAX_DIM + 3) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        BO_CUDA(h, cudaMemcpyAsync(b->out_host, b->out, (size_t)Sa * (BO_MAX_DIM + 4) * sizeof(double), cudaMemcpyDeviceToHost, st));
         BO_CUDA(h, cudaMemcpyAsync(b->info_host, b->info, Sa * sizeof(int), cudaMemcpyDeviceToHost, st));
         BO_CUDA(h, cudaStreamSynchronize(st));
         for (int s = 0; s < Sa; ++s) {
             const int r = r0 + s;
             const int info = b->info_host[s];
             status_host[r] = info > n ? n : info;
-            const double* o = b->out_host + (size_t)s * (BO_MAX_DIM + 3);
+            const double* o = b->out_host + (size_t)s * (BO_MAX_DIM + 4);
             if (info != 0) {
                 lml_host[r] = -INFINITY;
-                for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = 0.0;
+                for (int k = 0; k < p; ++k) grad_host[(size_t)r * p + k] = 0.0;
             } else {
                 lml_host[r] = o[0];
-                for (int k = 0; k < d + 2; ++k) grad_host[(size_t)r * (d + 2) + k] = o[1 + k];
+                for (int k = 0; k < p; ++k) grad_host[(size_t)r * p + k] = o[1 + k];
             }
         }
     }

@@ -34,7 +34,7 @@ struct SweepArgs {
     // last-arriving CTA of a block runs the epilogue, adding them in ascending row-block order -- the same two
     // chains the unsplit path keeps in registers, so the result is bit-identical for every split
     int G; int seg[SW_MAX_SEG + 1];
-    double* part_cs; double* part_mu; int* counters;
+    double* part_cs; double* part_mu; double* part_kss; int* counters;
 };
 
 // ---- analytic acquisition (botorch.acquisition.analytic semantics) ------
@@ -94,7 +94,8 @@ struct SweepSmem {
     static constexpr int OFF_BAR   = SW_STAGES * STAGE_BYTES;           // full[S], empty[S]
     static constexpr int OFF_COL   = OFF_BAR + 64;                      // colsum[2][SW_BN]
     static constexpr int OFF_MU    = OFF_COL + 2 * SW_BN * 8;           // mu[SW_BN]
-    static constexpr int OFF_TKV   = OFF_MU + SW_BN * 8;                // tk_val[64]
+    static constexpr int OFF_KSS   = OFF_MU + SW_BN * 8;                // kss[SW_BN]: prior variance k(x*,x*) (linear + Matern kind)
+    static constexpr int OFF_TKV   = OFF_KSS + SW_BN * 8;               // tk_val[64]
     static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;         // tk_idx[64]
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;         // acq[SW_BN]
     static constexpr int OFF_CMASK = OFF_ACQ + SW_BN * 8;               // cmask[4], is_last
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
     uint64_t* empty = full + SW_STAGES;
     double* colsum  = reinterpret_cast<double*>(smem + SweepSmem::OFF_COL);
     double* mu_s    = reinterpret_cast<double*>(smem + SweepSmem::OFF_MU);
+    double* kss_s   = reinterpret_cast<double*>(smem + SweepSmem::OFF_KSS);
     double* tkv     = reinterpret_cast<double*>(smem + SweepSmem::OFF_TKV);
     long long* tki  = reinterpret_cast<long long*>(smem + SweepSmem::OFF_TKI);
     double* acq_s   = reinterpret_cast<double*>(smem + SweepSmem::OFF_ACQ);
@@ -157,6 +159,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                 }
 #pragma unroll
                 for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
+            }
+            // linear + Matern kind: weighted copies for the inner-product term and the candidates' prior variance
+            double xw[2][KIND == BO_KERNEL_LINEAR_MATERN52 ? DP : 1];
+            if (KIND == BO_KERNEL_LINEAR_MATERN52) {
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) {
+                    double nn = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) { xw[gi][k] = a.hyp.lin_w[k] * xc[gi][k]; nn = fma(xw[gi][k], xc[gi][k], nn); }
+                    if (q == 0) kss_s[(warp + 8 * gi) * 8 + g] = a.hyp.outputscale * (nn + 1.0);
+                }
             }
             double mu0 = 0.0, mu1 = 0.0;
             const int nj8 = ib1 * (SW_BM / 8);               // panel rows this segment contracts over
@@ -208,13 +221,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     for (int gi = 0; gi < 2; ++gi)
 #pragma unroll
                         for (int r = 0; r < PA_R; ++r) {
-                            double sq = 0.0;
+                            double sq = 0.0, lin = 0.0;
 #pragma unroll
                             for (int k = 0; k < DP; ++k) {
                                 const double df = xc[gi][k] - x[r][k];
                                 sq = fma(df, df, sq);
+                                if (KIND == BO_KERNEL_LINEAR_MATERN52) lin = fma(xw[gi][k], x[r][k], lin);
                             }
-                            const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
+                            const double v = kernel_pair_t<KIND>(sq, lin, a.hyp.outputscale);
                             kv[gi][r] = (j8 * 8 + q + 4 * r < a.n) ? v : 0.0;
                         }
 #pragma unroll
@@ -356,7 +370,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
 
         // ================= split blocks: publish partials, last arriver finalises =================
         if (a.G > 1) {
-            if (tid < SW_BN && ib1 == nbm) a.part_mu[(size_t)blk * SW_BN + tid] = mu_s[tid];     // the last segment saw every row
+            if (tid < SW_BN && ib1 == nbm) {                 // the last segment saw every row
+                a.part_mu[(size_t)blk * SW_BN + tid] = mu_s[tid];
+                if (KIND == BO_KERNEL_LINEAR_MATERN52) a.part_kss[(size_t)blk * SW_BN + tid] = kss_s[tid];
+            }
             __threadfence();
             __syncthreads();
             if (tid == 0) *is_last = (atomicAdd(&a.counters[blk], 1) == a.G - 1) ? 1 : 0;
@@ -367,7 +384,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
         // ================= epilogue: variance, acquisition, CTA-local top-k =====================
         if (tid < SW_BN) {
             const long long li = blk * SW_BN + tid;
-            double ss, mu_c;
+            double ss, mu_c, prior = a.hyp.outputscale;
+            if (KIND == BO_KERNEL_LINEAR_MATERN52)
+                prior = (a.G > 1) ? __ldcg(a.part_kss + (size_t)blk * SW_BN + tid) : kss_s[tid];
             if (a.G > 1) {
                 double r0 = 0.0, r1 = 0.0;                   // the same two ascending chains the unsplit path keeps in registers
                 for (int ib = 0; ib < nbm; ++ib) {
@@ -380,7 +399,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                 ss = colsum[tid] + colsum[SW_BN + tid];
                 mu_c = mu_s[tid];
             }
-            const double var = fmax(a.hyp.outputscale - ss, a.min_var);
+            const double var = fmax(prior - ss, a.min_var);
             const double mean = a.hyp.mean + mu_c;
             double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
             if (li < a.N) {
@@ -499,9 +518,15 @@ __global__ void __launch_bounds__(256) sweep_reference_kernel(const SweepArgs a,
     for (int j = tid; j < a.np; j += 256) {
         double v = 0.0;
         if (j < a.n) {
-            double sq = 0.0;
-            for (int k = 0; k < DP; ++k) { double df = xs_c[k] - a.Xs[(size_t)j * BO_MAX_DIM + k]; sq = fma(df, df, sq); }
+            double sq = 0.0, lin = 0.0;
+            for (int k = 0; k < DP; ++k) {
+                const double xj = a.Xs[(size_t)j * BO_MAX_DIM + k];
+                const double df = xs_c[k] - xj;
+                sq = fma(df, df, sq);
+                lin = fma(a.hyp.lin_w[k] * xs_c[k], xj, lin);
+            }
             v = kernel_value(a.hyp.kind, sq, a.hyp.outputscale);
+            if (a.hyp.kind == BO_KERNEL_LINEAR_MATERN52) v = fma(a.hyp.outputscale, lin, v);
             mu = fma(v, a.alpha[j], mu);
         }
         ks[j] = v;
@@ -529,7 +554,13 @@ __global__ void __launch_bounds__(256) sweep_reference_kernel(const SweepArgs a,
     if (tid == 0) {
         double m = 0.0;
         for (int w = 0; w < 8; ++w) m += red[w];
-        const double var = fmax(a.hyp.outputscale - sst, a.min_var);
+        double prior = a.hyp.outputscale;
+        if (a.hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+            double nn = 0.0;
+            for (int k = 0; k < DP; ++k) nn = fma(a.hyp.lin_w[k] * xs_c[k], xs_c[k], nn);
+            prior = a.hyp.outputscale * (nn + 1.0);
+        }
+        const double var = fmax(prior - sst, a.min_var);
         const double mean = a.hyp.mean + m;
         a.mean_out[li] = mean;
         a.var_out[li] = var;
@@ -600,7 +631,7 @@ static int choose_segments(int sm, long long nblocks, int nbm, int* seg) {
 
 static int ensure_split_ws(bo_handle* h, long long nblocks, int G, int nbm) {
     (void)G;
-    const size_t need = ((size_t)nblocks * nbm * 2 * SW_BN + (size_t)nblocks * SW_BN) * sizeof(double) + (size_t)nblocks * sizeof(int) + 256;
+    const size_t need = ((size_t)nblocks * nbm * 2 * SW_BN + 2 * (size_t)nblocks * SW_BN) * sizeof(double) + (size_t)nblocks * sizeof(int) + 256;
     if (need > h->split_bytes) {
         if (h->split_ws) cudaFree(h->split_ws);
         h->split_ws = nullptr; h->split_bytes = 0;
@@ -635,6 +666,9 @@ static int launch_sweep(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t
     if (a.hyp.kind == BO_KERNEL_MATERN52) {
         BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
         sweep_kernel<DP, BO_KERNEL_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
+    } else if (a.hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_LINEAR_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
+        sweep_kernel<DP, BO_KERNEL_LINEAR_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
     } else {
         BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
         sweep_kernel<DP, BO_KERNEL_RBF><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
@@ -754,7 +788,8 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
         if ((rc = ensure_split_ws(h, a.nblocks, a.G, nbm))) return rc;
         a.part_cs = reinterpret_cast<double*>(h->split_ws);              // [nblocks][nbm][2][128] row-block sums
         a.part_mu = a.part_cs + (size_t)a.nblocks * nbm * 2 * SW_BN;
-        a.counters = reinterpret_cast<int*>(a.part_mu + (size_t)a.nblocks * SW_BN);
+        a.part_kss = a.part_mu + (size_t)a.nblocks * SW_BN;
+        a.counters = reinterpret_cast<int*>(a.part_kss + (size_t)a.nblocks * SW_BN);
         BO_CUDA(h, cudaMemsetAsync(a.counters, 0, (size_t)a.nblocks * sizeof(int), st));
     }
     a.panel = h->panel; a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;

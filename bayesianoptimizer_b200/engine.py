@@ -14,14 +14,15 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACQ_EI, ACQ_LOGEI, ACQ_MEAN, ACQ_UCB, ACQ_VAR, BO_MAX_TOPK, KERNEL_MATERN52, KERNEL_RBF,
-                   BoLibraryError, BoSobol)
+from ._lib import (ACQ_EI, ACQ_LOGEI, ACQ_MEAN, ACQ_UCB, ACQ_VAR, BO_MAX_TOPK, KERNEL_LINEAR_MATERN52, KERNEL_MATERN52,
+                   KERNEL_RBF, BoLibraryError, BoSobol)
 from .sobol import sobol_state
 
 MIN_VARIANCE = 1e-6   # gpytorch settings.min_variance (double)
 
 _KERNELS = {"matern52": KERNEL_MATERN52, "matern": KERNEL_MATERN52, "rbf": KERNEL_RBF,
-            KERNEL_MATERN52: KERNEL_MATERN52, KERNEL_RBF: KERNEL_RBF}
+            "linear_matern52": KERNEL_LINEAR_MATERN52, "linear+matern52": KERNEL_LINEAR_MATERN52,
+            KERNEL_MATERN52: KERNEL_MATERN52, KERNEL_RBF: KERNEL_RBF, KERNEL_LINEAR_MATERN52: KERNEL_LINEAR_MATERN52}
 _ACQS = {"ei": ACQ_EI, "logei": ACQ_LOGEI, "ucb": ACQ_UCB, "var": ACQ_VAR, "mean": ACQ_MEAN,
          ACQ_EI: ACQ_EI, ACQ_LOGEI: ACQ_LOGEI, ACQ_UCB: ACQ_UCB, ACQ_VAR: ACQ_VAR, ACQ_MEAN: ACQ_MEAN}
 
@@ -93,8 +94,11 @@ class GPEngine:
         return t
 
     # -- fit ----------------------------------------------------------------------------------
-    def fit(self, X, y, kernel="matern52", lengthscale=1.0, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0):
-        """K = k(X,X) + (noise+jitter) I ; L ; alpha ; explicit L^-1 (optimization/Bayesian.py:89-94)."""
+    def fit(self, X, y, kernel="matern52", lengthscale=1.0, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0,
+            linear_variance=0.0):
+        """K = k(X,X) + (noise+jitter) I ; L ; alpha ; explicit L^-1 (optimization/Bayesian.py:89-94).
+        ``kernel="linear_matern52"`` is ScaleKernel(Linear + Matern-5/2) of Bayesian6.py:471-473 / Bayesian7.py:162-166
+        with LinearKernel variance ``linear_variance``.  CPU tensors go through the host-buffer entry."""
         X = torch.as_tensor(X)
         n, d = X.shape
         ls = torch.as_tensor(lengthscale, dtype=torch.float64).reshape(-1).cpu()
@@ -103,21 +107,19 @@ class GPEngine:
         if ls.numel() != d:
             raise ValueError("lengthscale must be a scalar or have d entries")
         ls_arr = (C.c_double * d)(*ls.tolist())
-        args = (n, d, _KERNELS[kernel], ls_arr, float(outputscale), float(noise), float(mean), float(jitter))
-        if X.device.type == "cpu":
-            Xh = X.to(torch.float64).contiguous()
-            yh = torch.as_tensor(y, dtype=torch.float64).reshape(-1).contiguous()
-            if yh.numel() != n:
-                raise ValueError("y must have n entries")
-            with torch.cuda.device(self.device):
-                rc = self._lib.bo_fit_host(self._h, Xh.data_ptr(), yh.data_ptr(), *args, _stream_ptr(self.device))
+        host = X.device.type == "cpu"
+        if host:
+            Xb = X.to(torch.float64).contiguous()
+            yb = torch.as_tensor(y, dtype=torch.float64).reshape(-1).contiguous()
         else:
-            Xd = self._dev64(X)
-            yd = self._dev64(y, (-1,))
-            if yd.numel() != n:
-                raise ValueError("y must have n entries")
-            with torch.cuda.device(self.device):
-                rc = self._lib.bo_fit(self._h, Xd.data_ptr(), yd.data_ptr(), *args, _stream_ptr(self.device))
+            Xb = self._dev64(X)
+            yb = self._dev64(y, (-1,))
+        if yb.numel() != n:
+            raise ValueError("y must have n entries")
+        with torch.cuda.device(self.device):
+            rc = self._lib.bo_fit_ex(self._h, Xb.data_ptr(), yb.data_ptr(), n, d, _KERNELS[kernel], ls_arr, float(outputscale),
+                                     float(noise), float(mean), float(jitter), float(linear_variance), 1 if host else 0,
+                                     _stream_ptr(self.device))
         self._check(rc)
         if rc > 0:
             raise NotPositiveDefiniteError(rc)
@@ -142,6 +144,22 @@ class GPEngine:
         var = torch.empty(N, dtype=torch.float64, device=self.device)
         self._check(self._lib.bo_posterior(self._h, Xs.data_ptr(), N, float(min_variance), mean.data_ptr(),
                                            var.data_ptr(), _stream_ptr(self.device)))
+        return mean, var
+
+    def posterior_multi(self, Y, Xs, means=None, min_variance: float = MIN_VARIANCE, with_variance: bool = True):
+        """(mean[N,m], variance[N]) of m outputs Y (n,m) sharing the fitted kernel matrix (one Cholesky, m right-hand sides)."""
+        Y = self._dev64(Y).reshape(self.n, -1)
+        m = Y.shape[1]
+        Xs = self._dev64(Xs).reshape(-1, self.d)
+        N = Xs.shape[0]
+        mean = torch.empty(N, m, dtype=torch.float64, device=self.device)
+        var = torch.empty(N, dtype=torch.float64, device=self.device) if with_variance else None
+        mh = None
+        if means is not None:
+            mv = [float(v) for v in torch.as_tensor(means, dtype=torch.float64).reshape(-1).tolist()]
+            mh = (C.c_double * m)(*mv)
+        self._check(self._lib.bo_posterior_multi(self._h, Y.data_ptr(), m, mh, Xs.data_ptr(), N, float(min_variance),
+                                                 mean.data_ptr(), _ptr(var), _stream_ptr(self.device)))
         return mean, var
 
     # -- sweep ----------------------------------------------------------------------------------
@@ -238,14 +256,15 @@ class GPEngine:
         return self
 
     def lml_grad_batched(self, X, y, thetas, kernel="matern52", mean: float = 0.0):
-        """Batched exact LML and gradient w.r.t. log(lengthscale[d]), log(outputscale), log(noise)."""
+        """Batched exact LML and gradient w.r.t. log(lengthscale[d]), log(outputscale), log(noise) [, log(linear variance)]."""
         X = self._dev64(X)
         n, d = X.shape
         y = self._dev64(y, (-1,))
-        th = torch.as_tensor(thetas, dtype=torch.float64, device="cpu").contiguous().reshape(-1, d + 2)
+        p = d + 2 + (1 if _KERNELS[kernel] == KERNEL_LINEAR_MATERN52 else 0)      # + log linear variance
+        th = torch.as_tensor(thetas, dtype=torch.float64, device="cpu").contiguous().reshape(-1, p)
         R = th.shape[0]
         lml = torch.empty(R, dtype=torch.float64)
-        grad = torch.empty(R, d + 2, dtype=torch.float64)
+        grad = torch.empty(R, p, dtype=torch.float64)
         status = torch.empty(R, dtype=torch.int32)
         self._check(self._lib.bo_lml_grad_batched(self._h, X.data_ptr(), y.data_ptr(), n, d, _KERNELS[kernel],
                                                   float(mean), th.data_ptr(), R, lml.data_ptr(), grad.data_ptr(),

@@ -6,7 +6,8 @@ step; here R restarts advance in LOCK STEP, so every optimiser step is ONE ``bo_
 factorises all R candidate hyper-parameter vectors together on the device.  The optimiser itself is a small
 box-projected L-BFGS in NumPy (plumbing: R x (d+2) numbers per step).
 
-Parameters are theta = (log lengthscale[d], log outputscale, log noise).  Priors follow botorch's defaults
+Parameters are theta = (log lengthscale[d], log outputscale, log noise), plus log(linear variance) for the
+linear + Matern kernel (no prior on it, as in the reference's un-priored LinearKernel, Bayesian6.py:471-473).  Priors follow botorch's defaults
 (SURVEY.md App. A.2): ``"lognormal"`` = botorch >= 0.12 (lengthscale ~ LogNormal(sqrt2 + log(d)/2, sqrt3),
 noise ~ LogNormal(-4, 1)); ``"gamma"`` = botorch <= 0.11 (lengthscale ~ Gamma(3, 6), outputscale ~ Gamma(2, 0.15),
 noise ~ Gamma(1.1, 0.05)); ``None`` = plain maximum likelihood.
@@ -133,7 +134,7 @@ def lbfgs_lockstep(evaluate: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray
 def fit_map(engine, X, y, kernel: str, theta0: np.ndarray, lo: np.ndarray, hi: np.ndarray, prior: Optional[str] = None,
             maxiter: int = 50, mean: float = 0.0):
     """Lock-step multi-restart MAP fit.  Returns (best theta, best objective, all thetas, all objectives, n_evals)."""
-    d = np.asarray(theta0).shape[1] - 2
+    d = int(X.shape[1])            # theta = log lengthscale[d], log outputscale, log noise [, log linear variance]
 
     def evaluate(th):
         lml, grad, status = engine.lml_grad_batched(X, y, th, kernel, mean)

@@ -34,7 +34,8 @@ CSV_PARAM_COLS = ["n", "eta", "sigma_y", "width", "height"]
 @dataclass
 class GPConfig:
     """Knobs of the surrogate / acquisition path (passed as ``gp_config=``, the kwarg of Bayesian7.py:215)."""
-    kernel: str = "matern52"             # "matern52" (Bayesian6.py:471-473) | "rbf" (botorch >= 0.12 default)
+    kernel: str = "matern52"             # "matern52" | "rbf" (botorch >= 0.12 default) | "linear_matern52" (Bayesian6.py:471-473)
+    linear_variance: float = 1.0         # LinearKernel variance (initial value when hyper-parameters are fitted)
     acquisition: str = "logei"           # "logei" (Bayesian.py:101) | "ei" | "ucb" | "var" (Bayesian7.py:670-671)
     beta: float = 2.0                    # UCB exploration weight
     candidates_pool_size: int = 1_000_000  # Sobol pool scored per suggestion (reference: 1024 raw / 10^4 LHS)
@@ -126,7 +127,7 @@ class BayesianOptimizer:
         self.results_csv_path = self.results_file                                         # Bayesian7.py:255 name
         self._engine_factory = engine_factory or (lambda: GPEngine(self.device))
         self._engine = None
-        self._hyper = None            # (lengthscale[d], outputscale, noise) carried between refits (warm start)
+        self._hyper = None            # (lengthscale[d], outputscale, noise, linear variance) carried between refits (warm start)
         self._y_mean, self._y_std = 0.0, 1.0
         self._suggest_count = 0
         self._rng = np.random.default_rng(self.config.seed)
@@ -255,32 +256,40 @@ class BayesianOptimizer:
         prior = cfg.hyper_prior
         if prior == "auto":
             prior = "lognormal" if cfg.kernel == "rbf" else "gamma"
+        lin = cfg.kernel in ("linear_matern52", "linear+matern52")
         lo = np.concatenate([np.full(d, math.log(0.025)), [math.log(1e-2)], [math.log(cfg.min_noise)]])
         hi = np.concatenate([np.full(d, math.log(20.0)), [math.log(1e2)], [math.log(1.0)]])
         if self._hyper is not None:
-            ls0, s20, nz0 = self._hyper
+            ls0, s20, nz0, lv0 = self._hyper
         else:
             ls0 = np.full(d, 0.5) if cfg.lengthscale is None else np.broadcast_to(np.asarray(cfg.lengthscale, dtype=np.float64), (d,))
-            s20, nz0 = cfg.outputscale, cfg.noise
-        th0 = np.clip(np.concatenate([np.log(ls0), [math.log(s20)], [math.log(max(nz0, cfg.min_noise))]]), lo, hi)
+            s20, nz0, lv0 = cfg.outputscale, cfg.noise, cfg.linear_variance
+        th0 = np.concatenate([np.log(ls0), [math.log(s20)], [math.log(max(nz0, cfg.min_noise))]])
+        if lin:                                       # one more column: log LinearKernel variance
+            lo, hi = np.append(lo, math.log(1e-4)), np.append(hi, math.log(1e2))
+            th0 = np.append(th0, math.log(max(lv0, 1e-4)))
+        th0 = np.clip(th0, lo, hi)
         R = max(int(cfg.hyper_restarts), 1)
         thetas = np.tile(th0, (R, 1))
         if R > 1:
             thetas[1:, :d] = self._rng.uniform(math.log(0.1), math.log(3.0), size=(R - 1, d))
             thetas[1:, d] = self._rng.uniform(math.log(0.3), math.log(3.0), size=R - 1)
             thetas[1:, d + 1] = self._rng.uniform(math.log(cfg.min_noise), math.log(1e-1), size=R - 1)
+            if lin:
+                thetas[1:, d + 2] = self._rng.uniform(math.log(1e-2), math.log(1e1), size=R - 1)
         lml, _, status = eng.lml_grad_batched(X, y, thetas, cfg.kernel)
         score = np.asarray(lml, dtype=np.float64) + log_prior_and_grad(thetas, d, prior)[0]
         score = np.where(np.asarray(status) == 0, score, -np.inf)
+        unpack = lambda t: (np.exp(t[:d]), float(np.exp(t[d])), float(np.exp(t[d + 1])), float(np.exp(t[d + 2])) if lin else 0.0)
         if not np.isfinite(score).any():
-            return np.exp(th0[:d]), float(np.exp(th0[d])), float(np.exp(th0[d + 1]))
+            return unpack(th0)
         keep = np.argsort(-score)[:max(1, int(cfg.hyper_refine))]
         if 0 not in keep and np.isfinite(score[0]):
             keep = np.concatenate([keep[:-1], [0]]) if len(keep) > 1 else np.array([0])      # always refine the warm start
         th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas[keep], lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter))
         if not np.isfinite(F) or F < score[keep].max():
             th = thetas[keep[int(np.argmax(score[keep]))]]
-        return np.exp(th[:d]), float(np.exp(th[d])), float(np.exp(th[d + 1]))
+        return unpack(th)
 
     def fit_gp_model(self):
         """Fit the exact GP on the normalised data (Bayesian.py:89-94) and return the model handle."""
@@ -298,19 +307,19 @@ class BayesianOptimizer:
             keep = torch.as_tensor(np.unique(keep), device=X.device)
             X, y = X[keep], y[keep]
         if cfg.fit_hyperparameters and self.train_X.shape[0] >= 2 * d:
-            ls, s2, noise = self._fit_hyperparameters(eng, X, y)
+            ls, s2, noise, lv = self._fit_hyperparameters(eng, X, y)
         elif self._hyper is not None:
-            ls, s2, noise = self._hyper
+            ls, s2, noise, lv = self._hyper
         else:
             ls = np.full(d, 0.5) if cfg.lengthscale is None else np.broadcast_to(np.asarray(cfg.lengthscale, dtype=np.float64), (d,)).copy()
-            s2, noise = cfg.outputscale, cfg.noise
-        self._hyper = (np.asarray(ls, dtype=np.float64), float(s2), float(noise))
+            s2, noise, lv = cfg.outputscale, cfg.noise, cfg.linear_variance
+        self._hyper = (np.asarray(ls, dtype=np.float64), float(s2), float(noise), float(lv))
         try:
-            eng.fit(X, y, cfg.kernel, ls, s2, noise, mean=0.0, jitter=0.0)
+            eng.fit(X, y, cfg.kernel, ls, s2, noise, mean=0.0, jitter=0.0, linear_variance=lv)
         except NotPositiveDefiniteError as e:
             # retry-with-jitter convention of Bayesian6.py:482-488
             print(f"[fit_gp_model] Cholesky failed at pivot {e.pivot}; retrying with jitter {cfg.cholesky_jitter:g}")
-            eng.fit(X, y, cfg.kernel, ls, s2, noise, mean=0.0, jitter=cfg.cholesky_jitter)
+            eng.fit(X, y, cfg.kernel, ls, s2, noise, mean=0.0, jitter=cfg.cholesky_jitter, linear_variance=lv)
         return GPModel(eng, ls, s2, noise, mu, sd, sign)
 
     def _best_f(self):
@@ -352,7 +361,7 @@ class BayesianOptimizer:
             keep = idx >= 0
             starts = eng.sobol_points(sob, idx[keep])
             x, v = starts, vals[keep]
-            if cfg.refine_iters > 0:
+            if cfg.refine_iters > 0 and cfg.kernel not in ("linear_matern52", "linear+matern52"):   # pool-based for that kind
                 x, v = eng.refine(starts, cfg.acquisition, best_f, cfg.beta, iters=cfg.refine_iters)
             xb = x[int(torch.argmax(v).item())]
             out.append(xb.to(self.device))

@@ -41,6 +41,9 @@ extern "C" {
  * optimization/Bayesian.py:91), both under an (optional) ScaleKernel outputscale. */
 #define BO_KERNEL_MATERN52 0
 #define BO_KERNEL_RBF      1
+#define BO_KERNEL_LINEAR_MATERN52 2   /* ScaleKernel(LinearKernel + MaternKernel(2.5, ard)): outputscale * (v <x,x'> + matern),
+                                       * the explicit kernel of optimization/Bayesian6.py:471-473 and Bayesian7.py:162-166;
+                                       * supported by fit / posterior / sweep / append / lml (not by refine / acq_grad) */
 
 /* acquisition kinds (analytic closed forms; maximisation as in optimization/Bayesian.py:98) */
 #define BO_ACQ_EI    0   /* expected improvement                                  (Bayesian.py:100-101) */
@@ -95,6 +98,12 @@ int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_
                 int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
                 double mean, double jitter, void* stream);
 
+/* General form of bo_fit / bo_fit_host: adds the LinearKernel variance v of BO_KERNEL_LINEAR_MATERN52 (ignored for the
+ * stationary kinds) and takes host or device X / y (host_inputs != 0: host pointers, copied inside). */
+int bo_fit_ex(bo_handle* h, const double* X, const double* y, int32_t n, int32_t d, int32_t kernel_kind,
+              const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
+              double linear_variance, int32_t host_inputs, void* stream);
+
 /* introspection of the fitted state (device outputs; any may be NULL):
  *   alpha_dev[n], chol_dev[n,n] (lower triangle, upper zero), linv_dev[n,n] (lower, upper zero) */
 int bo_get_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, void* stream);
@@ -105,6 +114,13 @@ int bo_num_obs(const bo_handle* h);
  * (optimization/Bayesian2.py:168-171, optimization/Bayesian6.py:615-617, Bayesian7.py:666-671). */
 int bo_posterior(bo_handle* h, const double* Xs_dev, int64_t N, double min_variance,
                  double* mean_dev, double* var_dev, void* stream);
+
+/* m outputs that share the fitted kernel matrix (one Cholesky, m right-hand sides): posterior means mean_dev[N,m] at
+ * Xs_dev[N,d] for targets Y_dev[n,m] with constant means means_host[m] (NULL = zeros); the shared variance goes to
+ * var_dev[N] when non-NULL.  Exact-GP counterpart of the batched 8-task models and of model.posterior(X).mean with
+ * (N, m) outputs (optimization/Bayesian1.py:109-113, Bayesian2.py:168-171, Bayesian6.py:615-617, Bayesian7.py:129-195). */
+int bo_posterior_multi(bo_handle* h, const double* Y_dev, int32_t m, const double* means_host, const double* Xs_dev,
+                       int64_t N, double min_variance, double* mean_dev, double* var_dev, void* stream);
 
 /* Acquisition sweep over candidates [first_index, first_index + N) of a pool:
  *   cand_dev != NULL : explicit pool, cand_dev[N,d] holds exactly this shard's rows;
@@ -149,8 +165,9 @@ int bo_acq_grad(bo_handle* h, int32_t acq_kind, double best_f, double beta, doub
 int bo_append(bo_handle* h, const double* x_dev, double y, int32_t use_believer, void* stream);
 
 /* Batched exact log marginal likelihood and gradient over R hyper-parameter restarts on the
- * fitted X/y.  theta_host[R, d+2] = log lengthscale[d], log outputscale, log noise.
- * lml_host[R]; grad_host[R, d+2] (w.r.t. the log parameters); status_host[R] (0 or pivot).
+ * given X/y.  theta_host[R, p] = log lengthscale[d], log outputscale, log noise (p = d+2), plus log linear variance
+ * for BO_KERNEL_LINEAR_MATERN52 (p = d+3).  lml_host[R]; grad_host[R, p] (w.r.t. the log parameters);
+ * status_host[R] (0 or pivot).
  * Replaces the ExactMarginalLogLikelihood closure fit_gpytorch_mll evaluates
  * (optimization/Bayesian.py:92-93, optimization/Bayesian6.py:480-488). */
 int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d,

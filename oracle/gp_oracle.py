@@ -34,6 +34,7 @@ import scipy.special as ssp
 
 KERNEL_MATERN52 = 0
 KERNEL_RBF = 1
+KERNEL_LINEAR_MATERN52 = 2   # ScaleKernel(LinearKernel + MaternKernel(2.5, ard)): Bayesian6.py:471-473, Bayesian7.py:162-166
 
 ACQ_EI = 0
 ACQ_LOGEI = 1
@@ -93,8 +94,24 @@ def kernel_from_sqdist(sq, kind, outputscale):
     raise ValueError(f"unknown kernel kind {kind}")
 
 
-def kernel_matrix(A, B, kind, lengthscale, outputscale):
+def kernel_matrix(A, B, kind, lengthscale, outputscale, linear_variance=0.0):
+    """k(A, B).  Kind 2 is ScaleKernel(LinearKernel + Matern-5/2): s2 * (v <a, b> + matern(a, b)); gpytorch's LinearKernel
+    has ONE scalar variance v and acts on the raw inputs."""
+    if kind == KERNEL_LINEAR_MATERN52:
+        A = np.asarray(A, dtype=np.float64); B = np.asarray(B, dtype=np.float64)
+        lin = np.zeros((A.shape[0], B.shape[0]))
+        for k in range(A.shape[1]):
+            lin += A[:, k:k + 1] * B[:, k].reshape(1, -1)
+        return outputscale * linear_variance * lin + kernel_from_sqdist(scaled_sqdist(A, B, lengthscale), KERNEL_MATERN52, outputscale)
     return kernel_from_sqdist(scaled_sqdist(A, B, lengthscale), kind, outputscale)
+
+
+def prior_variance(X, kind, outputscale, linear_variance=0.0):
+    """k(x, x) per row: s2 for the stationary kinds, s2 (v |x|^2 + 1) for linear + Matern."""
+    X = np.asarray(X, dtype=np.float64)
+    if kind == KERNEL_LINEAR_MATERN52:
+        return outputscale * (linear_variance * np.sum(X * X, axis=1) + 1.0)
+    return np.full(X.shape[0], float(outputscale))
 
 
 class NotPositiveDefinite(np.linalg.LinAlgError):
@@ -117,6 +134,7 @@ class GPFit:
     mean: float
     L: np.ndarray          # lower Cholesky factor of K + (noise + jitter) I
     alpha: np.ndarray      # (K + noise I)^-1 (y - mean)
+    linear_variance: float = 0.0
 
     @property
     def n(self):
@@ -136,17 +154,18 @@ def _cholesky_lower(K):
     return L
 
 
-def fit(X, y, kind=KERNEL_MATERN52, lengthscale=None, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0):
+def fit(X, y, kind=KERNEL_MATERN52, lengthscale=None, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0,
+        linear_variance=0.0):
     """K = k(X,X) + (noise + jitter) I ; L = chol(K) ; alpha = K^-1 (y - mean).  """
     X = np.ascontiguousarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     n, d = X.shape
     ls = np.full(d, 1.0) if lengthscale is None else np.broadcast_to(np.asarray(lengthscale, dtype=np.float64), (d,)).copy()
-    K = kernel_matrix(X, X, kind, ls, outputscale)
-    K[np.diag_indices(n)] = outputscale + noise + jitter      # exact diagonal (gpytorch forces d(x,x)=0)
+    K = kernel_matrix(X, X, kind, ls, outputscale, linear_variance)
+    K[np.diag_indices(n)] = prior_variance(X, kind, outputscale, linear_variance) + noise + jitter   # exact diagonal (d(x,x)=0)
     L = _cholesky_lower(K)
     alpha = sla.cho_solve((L, True), y - mean)
-    return GPFit(X, y, kind, ls, float(outputscale), float(noise), float(mean), L, alpha)
+    return GPFit(X, y, kind, ls, float(outputscale), float(noise), float(mean), L, alpha, float(linear_variance))
 
 
 def posterior(gp: GPFit, Xs, min_variance=MIN_VARIANCE, chunk=2048):
@@ -156,10 +175,10 @@ def posterior(gp: GPFit, Xs, min_variance=MIN_VARIANCE, chunk=2048):
     mu = np.empty(N)
     var = np.empty(N)
     for s in range(0, N, chunk):
-        Ks = kernel_matrix(gp.X, Xs[s:s + chunk], gp.kind, gp.lengthscale, gp.outputscale)   # (n, c)
+        Ks = kernel_matrix(gp.X, Xs[s:s + chunk], gp.kind, gp.lengthscale, gp.outputscale, gp.linear_variance)   # (n, c)
         mu[s:s + chunk] = gp.mean + Ks.T @ gp.alpha
         V = sla.solve_triangular(gp.L, Ks, lower=True, check_finite=False)
-        var[s:s + chunk] = gp.outputscale - np.einsum("ij,ij->j", V, V)
+        var[s:s + chunk] = prior_variance(Xs[s:s + chunk], gp.kind, gp.outputscale, gp.linear_variance) - np.einsum("ij,ij->j", V, V)
     return mu, np.maximum(var, min_variance)
 
 
@@ -276,10 +295,11 @@ def sweep(gp: GPFit, Xs, acq_kind, best_f=0.0, beta=2.0, k=1, first_index=0, min
 # --------------------------------------------------------------------------------------
 # exact marginal log likelihood + gradient (Bayesian.py:92-93)
 # --------------------------------------------------------------------------------------
-def lml_and_grad(X, y, kind, lengthscale, outputscale, noise, mean=0.0):
+def lml_and_grad(X, y, kind, lengthscale, outputscale, noise, mean=0.0, linear_variance=0.0):
     """log N(y; m, K + noise I) and d/d(log l_k), d/d(log s2), d/d(log noise)  (un-normalised, no priors).
 
-    Returns (lml, grad[d + 2]).  Raises NotPositiveDefinite like ``fit``.
+    Returns (lml, grad[d + 2]); for the linear + Matern kind grad has a last entry d/d(log v).
+    Raises NotPositiveDefinite like ``fit``.
     """
     X = np.ascontiguousarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
@@ -287,17 +307,21 @@ def lml_and_grad(X, y, kind, lengthscale, outputscale, noise, mean=0.0):
     ls = np.broadcast_to(np.asarray(lengthscale, dtype=np.float64), (d,)).copy()
     sq = scaled_sqdist(X, X, ls)
     np.fill_diagonal(sq, 0.0)
-    Kf = kernel_from_sqdist(sq, kind, outputscale)
+    lin_kind = kind == KERNEL_LINEAR_MATERN52
+    Kf = kernel_from_sqdist(sq, KERNEL_MATERN52 if lin_kind else kind, outputscale)
+    if lin_kind:
+        Klin = outputscale * linear_variance * (X @ X.T)
+        Kf = Kf + Klin
     K = Kf.copy()
-    K[np.diag_indices(n)] = outputscale + noise
+    K[np.diag_indices(n)] = np.diag(Kf) + noise
     L = _cholesky_lower(K)
     r = y - mean
     alpha = sla.cho_solve((L, True), r)
     lml = -0.5 * float(r @ alpha) - float(np.log(np.diag(L)).sum()) - 0.5 * n * math.log(2.0 * math.pi)
     Kinv = sla.cho_solve((L, True), np.eye(n))
     W = np.outer(alpha, alpha) - Kinv            # dLML/dtheta = 0.5 tr(W dK/dtheta)
-    grad = np.empty(d + 2)
-    if kind == KERNEL_MATERN52:
+    grad = np.empty(d + 3 if lin_kind else d + 2)
+    if kind == KERNEL_MATERN52 or lin_kind:
         rr = np.sqrt(sq)
         G = outputscale * (5.0 / 3.0) * (1.0 + SQRT5 * rr) * np.exp(-SQRT5 * rr)   # dk/d(sq) * -2 ... see below
     else:
@@ -309,6 +333,8 @@ def lml_and_grad(X, y, kind, lengthscale, outputscale, noise, mean=0.0):
         grad[k] = 0.5 * float(np.sum(WG * diff * diff))
     grad[d] = 0.5 * float(np.sum(W * Kf))                       # d/d(log s2): dK/d(log s2) = Kf
     grad[d + 1] = 0.5 * noise * float(np.trace(W))              # d/d(log noise): dK/d(log noise) = noise I
+    if lin_kind:
+        grad[d + 2] = 0.5 * float(np.sum(W * Klin))             # d/d(log v): dK/d(log v) = s2 v X X^T
     return lml, grad
 
 
@@ -318,9 +344,9 @@ def lml_and_grad(X, y, kind, lengthscale, outputscale, noise, mean=0.0):
 def append_point(gp: GPFit, x, y=None):
     """Border L with the new row; y=None appends the believer value mu(x) (then alpha' = [alpha; 0])."""
     x = np.asarray(x, dtype=np.float64).reshape(1, -1)
-    k = kernel_matrix(gp.X, x, gp.kind, gp.lengthscale, gp.outputscale)[:, 0]
+    k = kernel_matrix(gp.X, x, gp.kind, gp.lengthscale, gp.outputscale, gp.linear_variance)[:, 0]
     l = sla.solve_triangular(gp.L, k, lower=True, check_finite=False)
-    lam2 = gp.outputscale + gp.noise - float(l @ l)
+    lam2 = float(prior_variance(x, gp.kind, gp.outputscale, gp.linear_variance)[0]) + gp.noise - float(l @ l)
     if not lam2 > 0.0:
         raise NotPositiveDefinite(gp.n + 1)
     lam = math.sqrt(lam2)
@@ -334,7 +360,7 @@ def append_point(gp: GPFit, x, y=None):
     X2 = np.vstack([gp.X, x])
     y2 = np.concatenate([gp.y, [y]])
     alpha2 = sla.cho_solve((L2, True), y2 - gp.mean)
-    return GPFit(X2, y2, gp.kind, gp.lengthscale, gp.outputscale, gp.noise, gp.mean, L2, alpha2)
+    return GPFit(X2, y2, gp.kind, gp.lengthscale, gp.outputscale, gp.noise, gp.mean, L2, alpha2, gp.linear_variance)
 
 
 # --------------------------------------------------------------------------------------
@@ -406,3 +432,51 @@ def fps(X, m, start=0):
         dist = np.minimum(dist, s)
         idx.append(int(np.argmax(dist)))
     return np.array(idx, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------------
+# several outputs sharing one kernel matrix (one Cholesky, m right-hand sides): SURVEY 8f N4
+# --------------------------------------------------------------------------------------
+def posterior_multi(gp: GPFit, Y, Xs, means=None, min_variance=MIN_VARIANCE):
+    """Posterior means (N, m) of m independent outputs Y (n, m) that share gp's kernel matrix, plus the shared
+    variance (N,).  The exact-GP analogue of the batched 8-task models (Bayesian1.py:109-113, Bayesian7.py:129-195)."""
+    Y = np.asarray(Y, dtype=np.float64).reshape(gp.n, -1)
+    m = Y.shape[1]
+    means = np.zeros(m) if means is None else np.asarray(means, dtype=np.float64)
+    A = sla.cho_solve((gp.L, True), Y - means[None, :])
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64).reshape(-1, gp.d)
+    Ks = kernel_matrix(gp.X, Xs, gp.kind, gp.lengthscale, gp.outputscale, gp.linear_variance)
+    mu = Ks.T @ A + means[None, :]
+    _, var = posterior(gp, Xs, min_variance)
+    return mu, var
+
+
+# --------------------------------------------------------------------------------------
+# log + standardise output transform and its lognormal back-transform (Bayesian6.py:427-443, 631-633, 703-707)
+# --------------------------------------------------------------------------------------
+@dataclass
+class LogStandardize:
+    shift: float
+    mean: np.ndarray      # (1, m) mean of log(Y + shift)
+    std: np.ndarray       # (1, m) unbiased std of log(Y + shift), floored at 1e-12
+
+    @staticmethod
+    def fit(Y):
+        Y = np.asarray(Y, dtype=np.float64).reshape(len(Y), -1)
+        eps = max(1e-12, float(np.abs(Y).max()) * 1e-6) if Y.size else 1e-6        # _compute_safe_epsilon, :421-425
+        ymin = float(Y.min())
+        shift = (-ymin + eps) if ymin <= 0.0 else eps                              # :431-435
+        lg = np.log(Y + shift)
+        std = lg.std(axis=0, ddof=1, keepdims=True)
+        std = np.where(std < 1e-12, 1e-12, std)                                    # :440-442
+        return LogStandardize(shift, lg.mean(axis=0, keepdims=True), std)
+
+    def forward(self, Y):
+        Y = np.asarray(Y, dtype=np.float64).reshape(len(Y), -1)
+        return np.nan_to_num((np.log(Y + self.shift) - self.mean) / self.std, nan=0.0)   # :464-468
+
+    def inverse_mean(self, mean_std, var_std):
+        """E[Y] of the lognormal: exp(mu_log + var_log / 2) - shift (:631-633)."""
+        log_mean = np.asarray(mean_std) * self.std + self.mean
+        log_var = np.asarray(var_std) * self.std ** 2
+        return np.exp(log_mean + 0.5 * log_var) - self.shift

@@ -6,7 +6,7 @@ import torch
 
 from oracle import gp_oracle as o
 
-_K = {"matern52": o.KERNEL_MATERN52, "rbf": o.KERNEL_RBF}
+_K = {"matern52": o.KERNEL_MATERN52, "rbf": o.KERNEL_RBF, "linear_matern52": o.KERNEL_LINEAR_MATERN52}
 _A = {"ei": o.ACQ_EI, "logei": o.ACQ_LOGEI, "ucb": o.ACQ_UCB, "var": o.ACQ_VAR, "mean": o.ACQ_MEAN}
 
 
@@ -25,12 +25,13 @@ class OracleEngine:
         self.n = self.d = 0
         self.fits = 0
 
-    def fit(self, X, y, kernel="matern52", lengthscale=1.0, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0):
+    def fit(self, X, y, kernel="matern52", lengthscale=1.0, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0,
+            linear_variance=0.0):
         from bayesianoptimizer_b200 import NotPositiveDefiniteError
         X = torch.as_tensor(X).cpu().numpy()
         y = torch.as_tensor(y).cpu().numpy().reshape(-1)
         try:
-            self.gp = o.fit(X, y, _K[kernel], lengthscale, outputscale, noise, mean, jitter)
+            self.gp = o.fit(X, y, _K[kernel], lengthscale, outputscale, noise, mean, jitter, linear_variance)
         except o.NotPositiveDefinite as e:
             raise NotPositiveDefiniteError(e.pivot)
         self.n, self.d = X.shape
@@ -40,6 +41,11 @@ class OracleEngine:
     def posterior(self, Xs, min_variance=1e-6):
         mu, var = o.posterior(self.gp, torch.as_tensor(Xs).cpu().numpy(), min_variance)
         return torch.from_numpy(mu), torch.from_numpy(var)
+
+    def posterior_multi(self, Y, Xs, means=None, min_variance=1e-6, with_variance=True):
+        mu, var = o.posterior_multi(self.gp, torch.as_tensor(Y).cpu().numpy(), torch.as_tensor(Xs).cpu().numpy(),
+                                    None if means is None else np.asarray(means, dtype=np.float64), min_variance)
+        return torch.from_numpy(mu), (torch.from_numpy(var) if with_variance else None)
 
     def sweep(self, acq="ei", best_f=0.0, beta=2.0, candidates=None, sobol=None, first_index=0, count=None, topk=1,
               min_variance=1e-6, return_all=False):
@@ -82,15 +88,18 @@ class OracleEngine:
 
     def lml_grad_batched(self, X, y, thetas, kernel="matern52", mean=0.0):
         X = torch.as_tensor(X).cpu().numpy(); y = torch.as_tensor(y).cpu().numpy().reshape(-1)
-        th = np.asarray(thetas, dtype=np.float64).reshape(-1, X.shape[1] + 2)
         d = X.shape[1]
+        lin = _K[kernel] == o.KERNEL_LINEAR_MATERN52
+        p = d + 3 if lin else d + 2
+        th = np.asarray(thetas, dtype=np.float64).reshape(-1, p)
         lml, grad, status = [], [], []
         for t in th:
             try:
-                l, g = o.lml_and_grad(X, y, _K[kernel], np.exp(t[:d]), np.exp(t[d]), np.exp(t[d + 1]), mean)
+                l, g = o.lml_and_grad(X, y, _K[kernel], np.exp(t[:d]), np.exp(t[d]), np.exp(t[d + 1]), mean,
+                                      np.exp(t[d + 2]) if lin else 0.0)
                 lml.append(l); grad.append(g); status.append(0)
             except o.NotPositiveDefinite as e:
-                lml.append(-np.inf); grad.append(np.zeros(d + 2)); status.append(e.pivot)
+                lml.append(-np.inf); grad.append(np.zeros(p)); status.append(e.pivot)
         return torch.tensor(lml), torch.from_numpy(np.array(grad)), torch.tensor(status, dtype=torch.int32)
 
     def fps(self, X, m, start=0):

@@ -1,0 +1,184 @@
+"""GPU tier, SURVEY 8f N4: ScaleKernel(Linear + Matern-5/2) (optimization/Bayesian6.py:471-473, Bayesian7.py:162-166)
+through fit / posterior / sweep / append / batched LML, and m outputs sharing one factorisation (bo_posterior_multi),
+each against the CPU oracle through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import assert_acq_close, assert_posterior_close, synth_problem
+from oracle import gp_oracle as o
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+LIN = o.KERNEL_LINEAR_MATERN52
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from bayesianoptimizer_b200 import GPEngine
+    eng = GPEngine(torch.device("cuda", 0))
+    yield eng
+    eng.close()
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _problem(n, d, seed):
+    X, y = synth_problem(n, d, seed, seed + 1)
+    y = y + 0.8 * (X @ np.linspace(1.0, -0.5, d))
+    return X, (y - y.mean()) / y.std(ddof=1)
+
+
+@pytest.mark.parametrize("n,d,N", [(300, 5, 2000), (129, 3, 100), (1000, 8, 4000), (640, 16, 300), (2500, 5, 10000)])
+def test_linear_matern_posterior_and_sweep(engine, n, d, N):
+    """Fused sweep (incl. the row-split path of small pools) with the per-candidate prior variance s2 (v |x|^2 + 1)."""
+    X, y = _problem(n, d, 31)
+    ls = np.linspace(0.4, 0.9, d)
+    kw = dict(lengthscale=ls, outputscale=1.3, noise=1e-3, mean=0.05, linear_variance=0.37)
+    gp = o.fit(X, y, LIN, **kw)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", ls, 1.3, 1e-3, mean=0.05, linear_variance=0.37)
+    alpha, L, _ = (t.cpu().numpy() for t in engine.state())
+    np.testing.assert_allclose(np.diag(L), np.diag(gp.L), rtol=1e-9)
+    assert np.abs(alpha - gp.alpha).max() <= 1e-7 * np.abs(gp.alpha).max()
+    xs = np.random.default_rng(7).random((N, d)) * 1.1 - 0.05
+    xs[0] = X[3]
+    bf = float(y.max())
+    for acq, ak in (("ei", o.ACQ_EI), ("logei", o.ACQ_LOGEI), ("ucb", o.ACQ_UCB)):
+        vals, idx, mu, var, av = engine.sweep(acq, bf, 2.0, candidates=_cuda(xs), topk=5, return_all=True)
+        tv, ti, omu, ovar, oav = o.sweep(gp, xs, ak, bf, 2.0, k=5)
+        assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+        assert_acq_close(acq, av.cpu().numpy(), oav)
+        assert idx.cpu().tolist() == ti.tolist()
+    mu, var = engine.posterior(_cuda(xs[:50]))
+    omu, ovar = o.posterior(gp, xs[:50])
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+
+
+def test_linear_matern_reference_kernel_agrees(engine, monkeypatch):
+    """Two-implementation cross-check on the device (plain-load kernel vs the TMA/DMMA kernel)."""
+    X, y = _problem(400, 6, 5)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.6, 1.1, 1e-3, linear_variance=0.5)
+    xs = _cuda(np.random.default_rng(1).random((500, 6)))
+    fast = engine.sweep("ei", 0.5, candidates=xs, topk=3, return_all=True)
+    monkeypatch.setenv("BO_B200_SWEEP_IMPL", "reference")
+    slow = engine.sweep("ei", 0.5, candidates=xs, topk=3, return_all=True)
+    assert fast[1].tolist() == slow[1].tolist()
+    assert_posterior_close(fast[2].cpu().numpy(), fast[3].cpu().numpy(), slow[2].cpu().numpy(), slow[3].cpu().numpy())
+
+
+def test_linear_matern_sobol_pool_and_append(engine):
+    from bayesianoptimizer_b200 import sobol_state
+    d = 4
+    X, y = _problem(250, d, 41)
+    kw = dict(lengthscale=0.5, outputscale=1.0, noise=1e-3, linear_variance=0.8)
+    gp = o.fit(X, y, LIN, **kw)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.5, 1.0, 1e-3, linear_variance=0.8)
+    st = sobol_state(d, 9)
+    se = torch.quasirandom.SobolEngine(d, scramble=True, seed=9)
+    pts = o.sobol_points(se.sobolstate.numpy(), se.shift.numpy(), 0, 3000)
+    bf = float(y.max())
+    for step in range(3):                                     # believer, believer, observed
+        v, i = engine.sweep("logei", bf, sobol=st, count=3000, topk=1)
+        tv, ti, _, _, _ = o.sweep(gp, pts, o.ACQ_LOGEI, bf, k=1)
+        assert i.item() == ti[0]
+        x = engine.sobol_points(st, i)[0]
+        yy = None if step < 2 else 0.3
+        engine.append(x, yy)
+        gp = o.append_point(gp, pts[ti[0]], yy)
+    xs = np.random.default_rng(2).random((100, d))
+    mu, var = engine.posterior(_cuda(xs))
+    omu, ovar = o.posterior(gp, xs)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+    ref = o.fit(gp.X, gp.y, LIN, **kw)
+    np.testing.assert_allclose(np.diag(engine.state()[1].cpu().numpy()), np.diag(ref.L), rtol=1e-8)
+
+
+def test_linear_matern_gradient_paths_refuse(engine):
+    from bayesianoptimizer_b200 import BoError
+    X, y = _problem(64, 3, 3)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.5, 1.0, 1e-3, linear_variance=0.5)
+    with pytest.raises(BoError):
+        engine.refine(_cuda(X[:4]), "ei", 0.0, iters=3)
+    with pytest.raises(BoError):
+        engine.acq_grad(_cuda(X[:4]), "ei", 0.0)
+    with pytest.raises(BoError):
+        engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.5, 1.0, 1e-3, linear_variance=-1.0)
+
+
+@pytest.mark.parametrize("n,d", [(300, 5), (700, 10), (130, 2)])
+def test_linear_matern_batched_lml_and_gradient(engine, n, d):
+    X, y = _problem(n, d, 8)
+    rng = np.random.default_rng(9)
+    R = 5
+    th = np.concatenate([rng.uniform(np.log(0.2), np.log(3.0), (R, d)), rng.uniform(np.log(0.5), np.log(2.0), (R, 1)),
+                         rng.uniform(np.log(1e-3), np.log(1e-1), (R, 1)), rng.uniform(np.log(0.05), np.log(2.0), (R, 1))], axis=1)
+    lml, grad, status = engine.lml_grad_batched(_cuda(X), _cuda(y), th, "linear_matern52")
+    assert status.tolist() == [0] * R and grad.shape == (R, d + 3)
+    for r in range(R):
+        l, g = o.lml_and_grad(X, y, LIN, np.exp(th[r, :d]), np.exp(th[r, d]), np.exp(th[r, d + 1]), linear_variance=np.exp(th[r, d + 2]))
+        assert abs(lml[r].item() - l) <= 1e-8 * abs(l), (r, lml[r].item(), l)
+        np.testing.assert_allclose(grad[r].numpy(), g, rtol=1e-6, atol=1e-7 * np.abs(g).max())
+
+
+def test_linear_matern_map_fit_finds_linear_variance(engine):
+    from bayesianoptimizer_b200.hyperfit import fit_map
+    n, d = 300, 3
+    X, y = _problem(n, d, 13)
+    lo = np.log(np.array([0.025] * d + [1e-2, 1e-4, 1e-4])); hi = np.log(np.array([20.0] * d + [1e2, 1.0, 1e2]))
+    th0 = np.log(np.array([[0.5] * d + [1.0, 1e-2, 0.1], [1.0] * d + [0.5, 1e-2, 1.0]]))
+    best, F, _, _, _ = fit_map(engine, _cuda(X), _cuda(y), "linear_matern52", th0, lo, hi, prior=None, maxiter=40)
+    f0, _ = o.lml_and_grad(X, y, LIN, np.exp(th0[0, :d]), np.exp(th0[0, d]), np.exp(th0[0, d + 1]), linear_variance=np.exp(th0[0, d + 2]))
+    fb, gb = o.lml_and_grad(X, y, LIN, np.exp(best[:d]), np.exp(best[d]), np.exp(best[d + 1]), linear_variance=np.exp(best[d + 2]))
+    assert abs(fb - F) <= 1e-7 * max(1.0, abs(F)) and F > f0
+    free = (best > lo + 1e-9) & (best < hi - 1e-9)
+    assert np.abs(gb[free]).max() <= 1e-2 * max(1.0, abs(F))         # stationary in the free coordinates
+
+
+@pytest.mark.parametrize("kname,kind,v", [("matern52", o.KERNEL_MATERN52, 0.0), ("linear_matern52", LIN, 0.4), ("rbf", o.KERNEL_RBF, 0.0)])
+@pytest.mark.parametrize("m", [1, 8, 11])
+def test_posterior_multi_shared_factorisation(engine, kname, kind, v, m):
+    """m outputs, one Cholesky: means equal m separate oracle fits; the variance is the shared one."""
+    n, d, N = 400, 5, 777
+    X, _ = _problem(n, d, 17)
+    rng = np.random.default_rng(m)
+    W = rng.standard_normal((d, m))
+    Y = np.sin(3 * X @ W) + 0.01 * rng.standard_normal((n, m))
+    means = rng.standard_normal(m) * 0.1
+    xs = rng.random((N, d))
+    engine.fit(_cuda(X), _cuda(Y[:, 0]), kname, 0.5, 1.2, 1e-3, mean=means[0], linear_variance=v)
+    mu, var = engine.posterior_multi(_cuda(Y), _cuda(xs), means)
+    gp = o.fit(X, Y[:, 0], kind, 0.5, 1.2, 1e-3, mean=means[0], linear_variance=v)
+    omu, ovar = o.posterior_multi(gp, Y, xs, means)
+    assert mu.shape == (N, m)
+    for t in range(m):
+        assert_posterior_close(mu[:, t].cpu().numpy(), var.cpu().numpy(), omu[:, t], ovar)
+    # the fitted single-output model is untouched
+    m0, v0 = engine.posterior(_cuda(xs[:20]))
+    assert_posterior_close(m0.cpu().numpy(), v0.cpu().numpy(), omu[:20, 0], ovar[:20])
+    mu2, none = engine.posterior_multi(_cuda(Y), _cuda(xs), means, with_variance=False)
+    assert none is None and torch.equal(mu2, mu)
+
+
+def test_log_transformed_eight_output_model_predicts_validation_rows(engine):
+    """The exact 8-output model of Bayesian6 (log + standardise -> GP -> lognormal back-transform), shared kernel."""
+    import os
+    from conftest import GOLDEN_DIR
+    from bayesianoptimizer_b200.simulators import DEFAULT_BOUNDS
+    from bayesianoptimizer_b200.transforms import LogStandardize
+    z = np.load(os.path.join(GOLDEN_DIR, "csv_cache_rows.npz"))
+    lo, hi = np.array(DEFAULT_BOUNDS).T
+    P, Yraw = z["params"], z["outputs"]
+    n = min(600, len(P) - 100)
+    U = (P - lo) / (hi - lo)
+    tr = LogStandardize.fit(_cuda(Yraw[:n]))
+    Z = tr.forward(_cuda(Yraw[:n]))
+    engine.fit(_cuda(U[:n]), Z[:, 0].contiguous(), "linear_matern52", [0.5, 0.4, 0.6, 0.8, 0.7], 1.0, 1e-2, linear_variance=0.3)
+    mu, var = engine.posterior_multi(Z, _cuda(U[n:n + 100]))
+    pred = tr.inverse_mean(mu, var).cpu().numpy()
+    otr = o.LogStandardize.fit(Yraw[:n])
+    gp = o.fit(U[:n], otr.forward(Yraw[:n])[:, 0], LIN, [0.5, 0.4, 0.6, 0.8, 0.7], 1.0, 1e-2, linear_variance=0.3)
+    omu, ovar = o.posterior_multi(gp, otr.forward(Yraw[:n]), U[n:n + 100])
+    np.testing.assert_allclose(pred, otr.inverse_mean(omu, ovar[:, None]), rtol=1e-7)
+    assert pred.shape == (100, 8) and np.all(np.isfinite(pred))

@@ -51,7 +51,7 @@ def test_full_loop_with_hyperparameter_fit(tmp_path):
     best_params, best_disp = opt.optimize()
     assert opt.train_X.shape == (44, 5) and sim.calls == 44
     assert len(open(opt.results_file).read().strip().split("\n")) == 45
-    ls, s2, noise = opt._hyper
+    ls, s2, noise, _ = opt._hyper
     assert ls.shape == (5,) and np.all(ls > 0) and s2 > 0 and noise >= cfg.min_noise
     # the fitted hyper-parameters are at least as likely as the defaults
     eng = opt._engine

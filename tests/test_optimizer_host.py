@@ -187,3 +187,26 @@ def test_prior_gradients_against_finite_differences():
             e = np.zeros(7); e[k] = 1e-6
             fd[:, k] = (log_prior_and_grad(th + e, 5, prior)[0] - log_prior_and_grad(th - e, 5, prior)[0]) / 2e-6
         np.testing.assert_allclose(g, fd, atol=1e-6)
+
+
+def test_linear_matern_kernel_loop_with_linear_variance_fit(tmp_path):
+    """N4: GPConfig(kernel="linear_matern52") carries a fourth hyper-parameter (the LinearKernel variance of
+    Bayesian6.py:471-473) through the lock-step fit, and suggestions stay pool-based for that kind."""
+    opt = _opt(tmp_path, gp_config=_cfg(kernel="linear_matern52", hyper_restarts=3, hyper_maxiter=4), n_batches=1)
+    opt.optimize()
+    ls, s2, noise, lv = opt._hyper
+    assert ls.shape == (5,) and lv > 0 and s2 > 0 and noise >= 1e-4
+    assert opt._engine.gp.kind == 2 and opt._engine.gp.linear_variance == pytest.approx(lv)
+    assert opt.train_X.shape == (14, 5)
+
+
+def test_log_standardize_matches_oracle_restatement():
+    from bayesianoptimizer_b200.transforms import LogStandardize
+    from oracle import gp_oracle as o
+    Y = np.random.default_rng(4).random((40, 8)) * 7 - 0.5
+    tr, ref = LogStandardize.fit(torch.from_numpy(Y)), o.LogStandardize.fit(Y)
+    assert tr.shift == pytest.approx(ref.shift, rel=1e-15)
+    np.testing.assert_allclose(tr.forward(torch.from_numpy(Y)).numpy(), ref.forward(Y), rtol=1e-12, atol=1e-13)
+    m, v = np.random.default_rng(5).standard_normal((30, 8)), np.random.default_rng(6).random(30)
+    np.testing.assert_allclose(tr.inverse_mean(torch.from_numpy(m), torch.from_numpy(v)).numpy(),
+                               ref.inverse_mean(m, v[:, None]), rtol=1e-12)

@@ -156,3 +156,93 @@ def test_transforms():
     ys, m, s = o.standardize(np.array([1.0, 2.0, 3.0, 4.0]))
     assert abs(m - 2.5) < 1e-15 and abs(s - np.std([1, 2, 3, 4], ddof=1)) < 1e-15
     assert abs(ys.mean()) < 1e-15
+
+
+# ---- N4: ScaleKernel(Linear + Matern-5/2), outputs sharing one kernel matrix -----------------------
+def _lin_problem(n=140, d=4):
+    X, y = synth_problem(n, d, 21, 22)
+    y = y + 0.8 * (X @ np.array([1.0, -0.5, 0.25, 0.7])[:d])          # a linear trend for the linear part to pick up
+    return X, (y - y.mean()) / y.std(ddof=1)
+
+
+def test_linear_matern_matches_sklearn_gpr():
+    """s2 (v <x,x'> + matern52) against sklearn's ConstantKernel * (ConstantKernel * DotProduct + Matern)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, DotProduct, Matern
+    X, y = _lin_problem()
+    ls, s2, v, noise = [0.5, 0.4, 0.6, 0.8], 1.3, 0.37, 1e-3
+    gp = o.fit(X, y, o.KERNEL_LINEAR_MATERN52, ls, s2, noise, linear_variance=v)
+    kern = ConstantKernel(s2) * (ConstantKernel(v) * DotProduct(sigma_0=1e-150) + Matern(ls, nu=2.5))
+    gpr = GaussianProcessRegressor(kernel=kern, alpha=noise, optimizer=None).fit(X, y)
+    xs = np.random.default_rng(3).random((300, 4)) * 1.2 - 0.1
+    m, s = gpr.predict(xs, return_std=True)
+    mu, var = o.posterior(gp, xs)
+    np.testing.assert_allclose(mu, m, rtol=1e-7, atol=1e-8)
+    far = var > 1e-2
+    np.testing.assert_allclose(var[far], (s ** 2)[far], rtol=1e-7)
+    lml, _ = o.lml_and_grad(X, y, o.KERNEL_LINEAR_MATERN52, ls, s2, noise, linear_variance=v)
+    assert abs(gpr.log_marginal_likelihood_value_ - lml) <= 1e-8 * abs(lml)
+
+
+def test_linear_matern_lml_gradient_against_finite_differences():
+    X, y = _lin_problem(110, 3)
+    theta = np.log(np.array([0.5, 0.4, 0.6, 1.3, 1e-2, 0.37]))
+
+    def f(t):
+        return o.lml_and_grad(X, y, o.KERNEL_LINEAR_MATERN52, np.exp(t[:3]), np.exp(t[3]), np.exp(t[4]), linear_variance=np.exp(t[5]))[0]
+
+    _, grad = o.lml_and_grad(X, y, o.KERNEL_LINEAR_MATERN52, np.exp(theta[:3]), np.exp(theta[3]), np.exp(theta[4]),
+                             linear_variance=np.exp(theta[5]))
+    assert grad.shape == (6,)
+    fd = np.array([(f(theta + 1e-6 * e) - f(theta - 1e-6 * e)) / 2e-6 for e in np.eye(6)])
+    np.testing.assert_allclose(grad, fd, rtol=2e-6, atol=1e-6)
+
+
+def test_linear_matern_append_equals_refit():
+    X, y = _lin_problem(90, 4)
+    kw = dict(kind=o.KERNEL_LINEAR_MATERN52, lengthscale=0.6, outputscale=1.1, noise=1e-3, linear_variance=0.5)
+    gp = o.fit(X, y, **kw)
+    xnew = np.array([0.9, 0.1, 0.5, 0.3])
+    gp2 = o.append_point(gp, xnew, 0.25)
+    ref = o.fit(np.vstack([X, xnew]), np.concatenate([y, [0.25]]), **kw)
+    np.testing.assert_allclose(gp2.L, ref.L, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gp2.alpha, ref.alpha, rtol=1e-8, atol=1e-10)
+    xs = np.random.default_rng(1).random((40, 4))
+    mu0, _ = o.posterior(gp, xs)
+    mu1, _ = o.posterior(o.append_point(gp, xnew), xs)                 # believer: mean unchanged
+    np.testing.assert_allclose(mu1, mu0, rtol=1e-8, atol=1e-9)
+
+
+def test_posterior_multi_equals_separate_fits():
+    X, _ = _lin_problem(100, 4)
+    rng = np.random.default_rng(5)
+    Y = np.stack([np.sin(3 * X).sum(1), np.cos(2 * X).sum(1), X @ rng.random(4)], axis=1) + 0.01 * rng.standard_normal((100, 3))
+    means = np.array([0.1, -0.2, 0.0])
+    xs = rng.random((60, 4))
+    for kind, v in ((o.KERNEL_MATERN52, 0.0), (o.KERNEL_LINEAR_MATERN52, 0.4)):
+        gp = o.fit(X, Y[:, 0], kind, 0.5, 1.0, 1e-3, mean=means[0], linear_variance=v)
+        mu, var = o.posterior_multi(gp, Y, xs, means)
+        for t in range(3):
+            gpt = o.fit(X, Y[:, t], kind, 0.5, 1.0, 1e-3, mean=means[t], linear_variance=v)
+            mt, vt = o.posterior(gpt, xs)
+            np.testing.assert_allclose(mu[:, t], mt, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(var, vt, rtol=1e-12)
+
+
+def test_log_standardize_round_trip_and_lognormal_mean():
+    """Output transform of optimization/Bayesian6.py:427-443 and its back-transform (:631-633, :703-707)."""
+    rng = np.random.default_rng(0)
+    Y = rng.random((50, 8)) * 10 + 0.05
+    tr = o.LogStandardize.fit(Y)
+    assert tr.shift == pytest.approx(max(1e-12, np.abs(Y).max() * 1e-6))
+    Z = tr.forward(Y)
+    np.testing.assert_allclose(Z.mean(axis=0), 0.0, atol=1e-12)
+    np.testing.assert_allclose(Z.std(axis=0, ddof=1), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(tr.inverse_mean(Z, np.zeros_like(Z)), Y, rtol=1e-12)       # zero variance: exact inverse
+    lm = tr.inverse_mean(Z, np.full_like(Z, 0.3))
+    np.testing.assert_allclose(lm, np.exp(np.log(Y + tr.shift) + 0.5 * 0.3 * tr.std ** 2) - tr.shift, rtol=1e-12)
+    # non-positive data: the shift lifts the minimum above zero
+    Yn = Y - 3.0
+    tn = o.LogStandardize.fit(Yn)
+    assert tn.shift == pytest.approx(-Yn.min() + max(1e-12, np.abs(Yn).max() * 1e-6))
+    assert np.all(np.isfinite(tn.forward(Yn)))
