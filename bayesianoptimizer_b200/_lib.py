@@ -45,6 +45,7 @@ SIGNATURES = {
     "bo_fit_host": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _vp]),
     "bo_fit_ex": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _f64, _i32, _vp]),
     "bo_posterior_multi": (C.c_int, [_vp, _vp, _i32, _pd, _vp, _i64, _f64, _vp, _vp, _vp]),
+    "bo_svgp_load": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp]),
     "bo_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "bo_num_obs": (C.c_int, [_vp]),
     "bo_posterior": (C.c_int, [_vp, _vp, _i64, _f64, _vp, _vp, _vp]),

@@ -68,6 +68,8 @@ int bo_release_workspace(bo_handle* h) {
     cudaDeviceSynchronize();
     if (h->panel) cudaFree(h->panel);
     h->panel = nullptr; h->panel_bytes = 0;
+    if (h->panel2) cudaFree(h->panel2);
+    h->panel2 = nullptr; h->panel2_bytes = 0;
     if (h->cand_stage) cudaFree(h->cand_stage);
     h->cand_stage = nullptr; h->cand_stage_bytes = 0;
     lml_release(h);
@@ -82,7 +84,7 @@ void bo_destroy(bo_handle* h) {
     lml_release(h);
     void* ptrs[] = {h->qbuf, h->split_ws, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
-                    h->out_stage_val, h->out_stage_idx};
+                    h->out_stage_val, h->out_stage_idx, h->Lp2};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->info_host) cudaFreeHost(h->info_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -127,6 +129,14 @@ int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_
                 int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
                 double mean, double jitter, void* stream) {
     return bo_fit_ex(h, X_host, y_host, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, 0.0, 1, stream);
+}
+
+int bo_svgp_load(bo_handle* h, const double* Z_dev, int32_t M, int32_t d, int32_t kernel_kind, const double* lengthscale_host,
+                 double outputscale, double linear_variance, double mean, double noise, double jitter,
+                 const double* var_mean_dev, const double* var_chol_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return svgp_load_impl(h, Z_dev, M, d, kernel_kind, lengthscale_host, outputscale, linear_variance, mean, noise, jitter,
+                          var_mean_dev, var_chol_dev, (cudaStream_t)stream);
 }
 
 int bo_get_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, void* stream) {

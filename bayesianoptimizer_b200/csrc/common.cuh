@@ -85,6 +85,14 @@ struct bo_handle {
     size_t plan_dev_cap = 0;
     int plan_np = -1;
 
+    // SVGP predictive mode (bo_svgp_load): the handle holds the inducing-point factorisation instead of an exact fit
+    bool svgp = false;
+    double sv_add = 0.0;         // K_uu jitter (gpytorch adds it to k** as well) + likelihood noise
+    double* Lp2 = nullptr;       // packed J Ls^T J (second triangular factor of the predictive variance)
+    size_t  Lp2_elems = 0;
+    double* panel2 = nullptr;    // [grid, np/SW_BK, SW_TILE] row-reversed interp-term panels
+    size_t  panel2_bytes = 0;
+
     // sweep workspaces
     double* panel = nullptr;     // [grid, np/SW_BK, SW_TILE] K(X*,X) panels, one per resident CTA
     size_t  panel_bytes = 0;
@@ -273,6 +281,9 @@ int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* i
                       double* out_dev, cudaStream_t st);
 int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);
 int refit_factor(bo_handle* h, cudaStream_t st);
+int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, const double* ls_host, double outputscale,
+                   double linear_variance, double mean, double noise, double jitter, const double* var_mean_dev,
+                   const double* var_chol_dev, cudaStream_t st);
 int create_handle(bo_handle** out, int device);
 void lml_release(bo_handle* h);
 int pack_row_block(bo_handle* h, int ib, cudaStream_t st);   // K build + Cholesky + inverse + alpha from h->Xs/h->yv

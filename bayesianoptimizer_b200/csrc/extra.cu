@@ -311,6 +311,7 @@ static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, doub
 
 static int check_query_args(bo_handle* h, int acq_kind, double beta, const void* a, const void* b, const void* c, int k) {
     if (!h->fitted) return fail(h, BO_E_NOTFIT, "acquisition gradient / refinement before a successful bo_fit");
+    if (h->svgp) return fail(h, BO_E_INVALID, "acquisition gradients / refinement are not defined on an SVGP predictive state");
     if (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52)
         return fail(h, BO_E_INVALID, "acquisition gradients / refinement are not implemented for the linear + Matern kernel "
                                      "(the reference uses it with pool-based acquisition only, Bayesian7.py:650-688)");
@@ -481,6 +482,7 @@ static int launch_kq1(bo_handle* h, const double* x, double* kv, cudaStream_t st
 
 int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st) {
     if (!h->fitted) return fail(h, BO_E_NOTFIT, "bo_append before a successful bo_fit");
+    if (h->svgp) return fail(h, BO_E_INVALID, "bo_append is not defined on an SVGP predictive state");
     if (!x_dev) return fail(h, BO_E_INVALID, "bo_append: null point");
     BO_CUDA(h, cudaSetDevice(h->device));
     int rc;
@@ -640,6 +642,7 @@ static int launch_multi_mean(bo_handle* h, const double* Xq, long long N, const 
 int posterior_multi_impl(bo_handle* h, const double* Y_dev, int m, const double* means_host, const double* Xs_dev, int64_t N,
                          double min_var, double* mean_dev, double* var_dev, cudaStream_t st) {
     if (!h->fitted) return fail(h, BO_E_NOTFIT, "bo_posterior_multi before a successful bo_fit");
+    if (h->svgp) return fail(h, BO_E_INVALID, "bo_posterior_multi is not defined on an SVGP predictive state");
     if (!Y_dev || m < 1 || m > 64 || N < 0 || (N > 0 && (!Xs_dev || !mean_dev))) return fail(h, BO_E_INVALID, "bo_posterior_multi: bad argument");
     BO_CUDA(h, cudaSetDevice(h->device));
     const int np = h->np;

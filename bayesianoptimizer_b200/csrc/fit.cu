@@ -532,7 +532,7 @@ static int solve_alpha(bo_handle* h, cudaStream_t st) {
     return solve_alpha_rhs(h, h->vec1, h->alpha, st);
 }
 
-int refit_factor(bo_handle* h, cudaStream_t st) {
+static int factor_and_pack(bo_handle* h, bool with_alpha, cudaStream_t st) {
     const int np = h->np, ld = h->cap_np, nb = np / NB;
     int rc;
     if (h->plan_np != np && (rc = build_plan(h, st))) return rc;
@@ -555,7 +555,7 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
         pack_linv_kernel<<<grid, 256, 0, st>>>(h->Li, ld, np, h->Lp, 0);
         BO_LAUNCH_CHECK(h);
     }
-    if ((rc = solve_alpha(h, st))) return rc;
+    if (with_alpha && (rc = solve_alpha(h, st))) return rc;
     BO_CUDA(h, cudaStreamSynchronize(st));
     const int info = *h->info_host;
     if (info != 0) {
@@ -568,6 +568,7 @@ int refit_factor(bo_handle* h, cudaStream_t st) {
     h->fitted = true;
     return 0;
 }
+int refit_factor(bo_handle* h, cudaStream_t st) { return factor_and_pack(h, true, st); }
 
 static int trmv_lower_m(bo_handle* h, const double* M, const double* v, double* z, cudaStream_t st) {
     trmv_lower_kernel<<<h->np / 8, 256, 0, st>>>(M, h->cap_np, h->np, v, z, 0);
@@ -603,7 +604,7 @@ int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv
     return 0;
 }
 
-int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
+static int fit_impl_prepare(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
              const double* ls_host, double outputscale, double noise, double mean, double jitter,
              double linear_variance, cudaStream_t st) {
     if (n < 1 || d < 1 || !X_dev || !y_dev || !ls_host) return fail(h, BO_E_INVALID, "bo_fit: bad argument");
@@ -615,6 +616,7 @@ int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     for (int k = 0; k < d; ++k) if (!(ls_host[k] > 0.0)) return fail(h, BO_E_INVALID, "bo_fit: lengthscale must be positive");
     BO_CUDA(h, cudaSetDevice(h->device));
     h->fitted = false;
+    h->svgp = false;
     const int np = round_up(n, PAD);
     int rc = ensure_capacity(h, np, st);
     if (rc) return rc;
@@ -628,7 +630,64 @@ int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     }
     stage_inputs_kernel<<<(np + 127) / 128, 128, 0, st>>>(X_dev, y_dev, n, d, np, hy, h->Xraw, h->Xs, h->yv);
     BO_LAUNCH_CHECK(h);
-    return refit_factor(h, st);
+    return 0;
+}
+int fit_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind,
+             const double* ls_host, double outputscale, double noise, double mean, double jitter,
+             double linear_variance, cudaStream_t st) {
+    const int rc = fit_impl_prepare(h, X_dev, y_dev, n, d, kind, ls_host, outputscale, noise, mean, jitter, linear_variance, st);
+    return rc ? rc : refit_factor(h, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// N2: SVGP predictive state (whitened VariationalStrategy + CholeskyVariationalDistribution, Bayesian7.py:129-195)
+// ------------------------------------------------------------------------------------------
+// second triangular factor of the predictive variance: A2 = J Ls^T J (lower triangular in the reversed index order),
+// packed exactly like L^-1 (pack_linv_kernel) so the sweep streams it with the same tile loop
+__global__ void __launch_bounds__(256) pack_rev_chol_kernel(const double* __restrict__ Ls, int M, int np, double* __restrict__ Lp2) {
+    constexpr int KCH = SW_BM / SW_BK;
+    const int ib = blockIdx.y;
+    const int kc = blockIdx.x;
+    if (kc >= (ib + 1) * KCH) return;
+    double* dst = Lp2 + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * SW_TILE;
+    const int row0 = ib * SW_BM, k0 = kc * SW_BK;
+    for (int e = threadIdx.x; e < SW_TILE; e += 256) {
+        const int k = e / SW_BM, r = e % SW_BM;          // consecutive threads walk a row of Ls backwards
+        const int ip = row0 + r, jp = k0 + k;            // A2[ip][jp] = Ls[np-1-jp][np-1-ip]
+        const int sr = np - 1 - jp, sc = np - 1 - ip;
+        const double v = (jp <= ip && sr < M) ? Ls[(size_t)sr * M + sc] : 0.0;
+        const int r8 = r >> 3, k8 = k >> 3;
+        const int lane = (r & 7) * 4 + (k & 3), khalf = (k & 7) >> 2;
+        dst[(r8 * (SW_BK / 8) + k8) * 64 + lane * 2 + khalf] = v;
+    }
+}
+
+int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, const double* ls_host, double outputscale,
+                   double linear_variance, double mean, double noise, double jitter, const double* var_mean_dev,
+                   const double* var_chol_dev, cudaStream_t st) {
+    if (M < 1 || d < 1 || !Z_dev || !ls_host || !var_mean_dev || !var_chol_dev) return fail(h, BO_E_INVALID, "bo_svgp_load: bad argument");
+    if (!(noise >= 0.0)) return fail(h, BO_E_INVALID, "bo_svgp_load: noise must be >= 0");
+    // inducing-point prior: K_uu + jitter I (no likelihood noise inside the factorisation); m rides in as the "targets"
+    int rc = fit_impl_prepare(h, Z_dev, var_mean_dev, M, d, kind, ls_host, outputscale, 0.0, mean, jitter, linear_variance, st);
+    if (rc) return rc;
+    if ((rc = factor_and_pack(h, false, st))) return rc;
+    h->fitted = false;                                   // until the second factor is in place
+    const int np = h->np;
+    if ((rc = trmv_lower_t_m(h, h->Li, h->yv, h->alpha, 0, st))) return rc;          // alpha = L^-T m  (mean = c + k*^T alpha)
+    const size_t packed = ((size_t)np / SW_BM) * (np / SW_BM + 1) / 2 * (SW_BM / SW_BK) * SW_TILE;
+    if (packed > h->Lp2_elems) {
+        if (h->Lp2) cudaFree(h->Lp2);
+        h->Lp2 = nullptr; h->Lp2_elems = 0;
+        BO_CUDA(h, cudaMalloc(&h->Lp2, packed * sizeof(double)));
+        h->Lp2_elems = packed;
+    }
+    pack_rev_chol_kernel<<<dim3(np / SW_BK, np / SW_BM), 256, 0, st>>>(var_chol_dev, M, np, h->Lp2);
+    BO_LAUNCH_CHECK(h);
+    BO_CUDA(h, cudaStreamSynchronize(st));               // var_chol_dev is borrowed for the call only
+    h->svgp = true;
+    h->sv_add = jitter + noise;
+    h->fitted = true;
+    return 0;
 }
 
 // GEMM throughput probe (development / roofline evidence for the fit's trailing updates): C = A * B^T, square tiles

@@ -35,6 +35,9 @@ struct SweepArgs {
     // chains the unsplit path keeps in registers, so the result is bit-identical for every split
     int G; int seg[SW_MAX_SEG + 1];
     double* part_cs; double* part_mu; double* part_kss; int* counters;
+    // SVGP predictive mode (SV kernels): second triangular factor J Ls^T J (packed like Lp), the panel that receives the
+    // row-reversed interp term u = L^-1 k*, and the constant added to the prior variance (K_uu jitter + likelihood noise)
+    const double* Lp2; double* panel2; double sv_add;
 };
 
 // ---- analytic acquisition (botorch.acquisition.analytic semantics) ------
@@ -103,7 +106,11 @@ struct SweepSmem {
     static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
 };
 
-template <int DP, int KIND>
+// SV = true: whitened-SVGP predictive variance k** + jitter - ||u||^2 + ||Ls^T u||^2 (+ noise), u = L^-1 k*
+// (gpytorch VariationalStrategy as driven by optimization/Bayesian7.py:664-671): phase B runs twice over the same ring --
+// pass 0 contracts L^-1 with the K panel and parks u, ROW-REVERSED, in a second panel (so that the upper-triangular
+// Ls^T becomes the lower-triangular J Ls^T J the tile loop already knows how to stream); pass 1 contracts that with u.
+template <int DP, int KIND, bool SV>
 __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem + SweepSmem::OFF_BAR);
@@ -124,6 +131,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
     const int nbm = a.np / SW_BM;
     constexpr int KCH = SW_BM / SW_BK;
     double* panel = a.panel + (size_t)blockIdx.x * (a.np / SW_BK) * SW_TILE;
+    double* panel2 = SV ? a.panel2 + (size_t)blockIdx.x * (a.np / SW_BK) * SW_TILE : nullptr;
 
     if (tid == 0) {
         for (int s = 0; s < SW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SW_CONSUMER_WARPS); }
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             // The scaled observations X~ and alpha are staged through the (idle) stage buffers in double-buffered
             // chunks with cp.async, so the panel build reads them from shared memory instead of stalling on L2.
             // PA_SL 8-row slices per iteration: 4 * PA_SL independent kernel evaluations per lane in flight.
-            constexpr int PA_SL = 4, PA_R = 2 * PA_SL;
+            constexpr int PA_SL = (KIND == BO_KERNEL_LINEAR_MATERN52 && DP >= 12) ? 2 : 4, PA_R = 2 * PA_SL;   // (xw doubles the candidate registers)
             constexpr int XCH = (DP <= 8) ? 1024 : 512;          // rows per chunk
             constexpr int XP = DP + 2;                           // padded row pitch (doubles): conflict-free LDS.128 over 4 rows
             constexpr int XBUF = XCH * XP + XCH;                 // doubles per buffer: rows + alpha
@@ -254,16 +262,28 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
 
         // ================= phase B: ||L^-1 k*||^2 on the DMMA path ============================
         {
+            const int wm = warp >> 2, wn = warp & 3;
+            double colsq[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) colsq[e] = 0.0;
+          for (int pass = 0; pass < (SV ? 2 : 1); ++pass) {
+            const double* Asrc = (SV && pass) ? a.Lp2 : a.Lp;
+            const double* Bsrc = (SV && pass) ? panel2 : panel;
+            if (SV && pass) {             // u is complete: generic-proxy panel2 writes -> visible to the TMA reads
+                __threadfence();
+                fence_proxy_async();
+                __syncthreads();
+            }
             const long long T = ((long long)ib1 * (ib1 + 1) / 2 - (long long)ib0 * (ib0 + 1) / 2) * KCH;   // pipeline stages of this item
             int pib = ib0, pkc = 0;                                          // producer position (thread 0)
             long long issued = 0;
             auto issue = [&]() {
                 mbar_wait(&empty[pstage], pphase ^ 1);
                 unsigned char* sb = smem + pstage * SweepSmem::STAGE_BYTES;
-                const double* At = a.Lp + ((size_t)pib * (pib + 1) / 2 * KCH + pkc) * SW_TILE;
+                const double* At = Asrc + ((size_t)pib * (pib + 1) / 2 * KCH + pkc) * SW_TILE;
                 mbar_expect_tx(&full[pstage], SweepSmem::STAGE_BYTES);
                 bulk_g2s(sb, At, SW_TILE * 8, &full[pstage]);
-                bulk_g2s(sb + SW_TILE * 8, panel + (size_t)pkc * SW_TILE, SW_TILE * 8, &full[pstage]);
+                bulk_g2s(sb + SW_TILE * 8, Bsrc + (size_t)pkc * SW_TILE, SW_TILE * 8, &full[pstage]);
                 if (++pstage == SW_STAGES) { pstage = 0; pphase ^= 1; }
                 if (++pkc == (pib + 1) * KCH) { pkc = 0; ++pib; }
                 ++issued;
@@ -271,11 +291,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             if (tid == 0)
                 while (issued < T && issued < SW_STAGES - 1) issue();
 
-            const int wm = warp >> 2, wn = warp & 3;
             bool ready = false;              // full[stage] already observed complete by the early probe
-            double colsq[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) colsq[e] = 0.0;
             for (int ib = ib0; ib < ib1; ++ib) {
                 double acc[8][4][2];
 #pragma unroll
@@ -342,6 +358,19 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     if (lane == 0) mbar_arrive(&empty[stage]);
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (SV && pass == 0) {
+                    // park u = (L^-1 k*) rows of this block in panel2, row-reversed (i -> np-1-i), in B-fragment order
+                    double* t2 = panel2 + ((size_t)(nbm - 1 - ib) * KCH + (1 - wm) * 2) * SW_TILE;
+#pragma unroll
+                    for (int mi = 0; mi < 8; ++mi) {
+                        double* tm = t2 + ((7 - mi) >> 2) * SW_TILE + ((7 - mi) & 3) * 64 + (3 - (g & 3)) * 2 + (1 - (g >> 2));
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                            for (int e2 = 0; e2 < 2; ++e2)
+                                tm[((wn * 4 + ni) * (SW_BK / 8)) * 64 + (2 * q + e2) * 8] = acc[mi][ni][e2];
+                    }
+                }
                 // canonical reduction (independent of the segment split): per row block, square-sum this thread's 8
                 // row groups, butterfly over the 8 row lanes, then add the row block's total to the running sum in
                 // ascending row-block order -- or park it in global memory for the finaliser to add in that order
@@ -357,10 +386,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                         if (g == 0)
                             a.part_cs[(((size_t)blk * nbm + ib) * 2 + wm) * SW_BN + wn * 32 + (e >> 1) * 8 + 2 * q + (e & 1)] = t;
                     } else {
-                        colsq[e] += t;
+                        colsq[e] += (SV && pass) ? -t : t;      // SV: ss = ||u||^2 - ||Ls^T u||^2
                     }
                 }
             }
+          }   // pass
             if (g == 0) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) colsum[wm * SW_BN + wn * 32 + (e >> 1) * 8 + 2 * q + (e & 1)] = colsq[e];
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                 ss = colsum[tid] + colsum[SW_BN + tid];
                 mu_c = mu_s[tid];
             }
-            const double var = fmax(prior - ss, a.min_var);
+            const double var = fmax((SV ? prior + a.sv_add : prior) - ss, a.min_var);
             const double mean = a.hyp.mean + mu_c;
             double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
             if (li < a.N) {
@@ -649,6 +679,12 @@ static int ensure_sweep_ws(bo_handle* h, int grid) {
         BO_CUDA(h, cudaMalloc(&h->panel, need));
         h->panel_bytes = need;
     }
+    if (h->svgp && need > h->panel2_bytes) {
+        if (h->panel2) cudaFree(h->panel2);
+        h->panel2 = nullptr; h->panel2_bytes = 0;
+        BO_CUDA(h, cudaMalloc(&h->panel2, need));
+        h->panel2_bytes = need;
+    }
     if (grid > h->part_grid) {
         if (h->part_val) cudaFree(h->part_val);
         if (h->part_idx) cudaFree(h->part_idx);
@@ -660,21 +696,26 @@ static int ensure_sweep_ws(bo_handle* h, int grid) {
     return 0;
 }
 
-template <int DP>
-static int launch_sweep(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t st) {
+template <int DP, int KIND, bool SV>
+static int launch_sweep_k(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t st) {
     // the opt-in is per device context: set it on every launch (a process may hold handles on several GPUs)
-    if (a.hyp.kind == BO_KERNEL_MATERN52) {
-        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
-        sweep_kernel<DP, BO_KERNEL_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
-    } else if (a.hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
-        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_LINEAR_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
-        sweep_kernel<DP, BO_KERNEL_LINEAR_MATERN52><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
-    } else {
-        BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, BO_KERNEL_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
-        sweep_kernel<DP, BO_KERNEL_RBF><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
-    }
+    BO_CUDA(h, cudaFuncSetAttribute(sweep_kernel<DP, KIND, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepSmem::BYTES));
+    sweep_kernel<DP, KIND, SV><<<grid, SW_THREADS, SweepSmem::BYTES, st>>>(a);
     BO_LAUNCH_CHECK(h);
     return 0;
+}
+template <int DP>
+static int launch_sweep(bo_handle* h, const SweepArgs& a, int grid, cudaStream_t st) {
+    const bool sv = a.Lp2 != nullptr;
+    switch (a.hyp.kind) {
+        case BO_KERNEL_MATERN52:
+            return sv ? launch_sweep_k<DP, BO_KERNEL_MATERN52, true>(h, a, grid, st) : launch_sweep_k<DP, BO_KERNEL_MATERN52, false>(h, a, grid, st);
+        case BO_KERNEL_LINEAR_MATERN52:
+            return sv ? launch_sweep_k<DP, BO_KERNEL_LINEAR_MATERN52, true>(h, a, grid, st)
+                      : launch_sweep_k<DP, BO_KERNEL_LINEAR_MATERN52, false>(h, a, grid, st);
+        default:
+            return sv ? launch_sweep_k<DP, BO_KERNEL_RBF, true>(h, a, grid, st) : launch_sweep_k<DP, BO_KERNEL_RBF, false>(h, a, grid, st);
+    }
 }
 template <int DP>
 static int launch_sweep_ref(bo_handle* h, const SweepArgs& a, cudaStream_t st) {
@@ -742,7 +783,7 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     }
 
     const char* impl = getenv("BO_B200_SWEEP_IMPL");
-    if (impl && strcmp(impl, "reference") == 0) {
+    if (impl && strcmp(impl, "reference") == 0 && !h->svgp) {
         // slow independent path: needs dense outputs; borrow temporaries if the caller passed none
         double *tm = nullptr, *tv = nullptr, *ta = nullptr;
         if (!a.mean_out) { BO_CUDA(h, cudaMalloc(&tm, N * 8)); a.mean_out = tm; }
@@ -765,7 +806,9 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     {
         const char* gs = getenv("BO_B200_SWEEP_SEGMENTS");      // test hook: force a segment count
         a.G = choose_segments(h->sm_count, a.nblocks, h->np / SW_BM, a.seg);
-        if (gs && atoi(gs) >= 1) {
+        if (h->svgp) {                 // the second pass needs the whole interp term of a block in one CTA: no row split
+            a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
+        } else if (gs && atoi(gs) >= 1) {
             const int nbm = h->np / SW_BM;
             int G = atoi(gs); if (G > nbm) G = nbm; if (G > SW_MAX_SEG) G = SW_MAX_SEG;
             // re-use the balancing by pretending a pool that makes G optimal: simple equal-stage split
@@ -793,6 +836,7 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
         BO_CUDA(h, cudaMemsetAsync(a.counters, 0, (size_t)a.nblocks * sizeof(int), st));
     }
     a.panel = h->panel; a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
+    if (h->svgp) { a.Lp2 = h->Lp2; a.panel2 = h->panel2; a.sv_add = h->sv_add; }
     BO_CUDA(h, cudaEventRecord(h->ev0, st));
     if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep, h, a, grid, st))) return rc;
     BO_CUDA(h, cudaEventRecord(h->ev1, st));

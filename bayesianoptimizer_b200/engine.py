@@ -146,6 +146,33 @@ class GPEngine:
                                            var.data_ptr(), _stream_ptr(self.device)))
         return mean, var
 
+    def load_svgp(self, Z, var_mean, var_chol, kernel="linear_matern52", lengthscale=1.0, outputscale=1.0,
+                  linear_variance=0.0, mean=0.0, noise=0.0, jitter=1e-6):
+        """Load one task of a sparse variational GP (whitened VariationalStrategy + CholeskyVariationalDistribution,
+        optimization/Bayesian7.py:129-195): afterwards ``posterior`` / ``sweep`` evaluate its predictive distribution
+        (mean = c + u^T m, var = k** + jitter - |u|^2 + |Ls^T u|^2 + noise with u = L^-1 k(Z, x*))."""
+        Z = self._dev64(Z)
+        M, d = Z.shape
+        m = self._dev64(var_mean, (-1,))
+        Ls = self._dev64(var_chol).reshape(M, M)
+        if m.numel() != M:
+            raise ValueError("var_mean must have M entries")
+        ls = torch.as_tensor(lengthscale, dtype=torch.float64).reshape(-1).cpu()
+        if ls.numel() == 1:
+            ls = ls.repeat(d)
+        if ls.numel() != d:
+            raise ValueError("lengthscale must be a scalar or have d entries")
+        ls_arr = (C.c_double * d)(*ls.tolist())
+        with torch.cuda.device(self.device):
+            rc = self._lib.bo_svgp_load(self._h, Z.data_ptr(), M, d, _KERNELS[kernel], ls_arr, float(outputscale),
+                                        float(linear_variance), float(mean), float(noise), float(jitter), m.data_ptr(),
+                                        Ls.data_ptr(), _stream_ptr(self.device))
+        self._check(rc)
+        if rc > 0:
+            raise NotPositiveDefiniteError(rc)
+        self.n, self.d = M, d
+        return self
+
     def posterior_multi(self, Y, Xs, means=None, min_variance: float = MIN_VARIANCE, with_variance: bool = True):
         """(mean[N,m], variance[N]) of m outputs Y (n,m) sharing the fitted kernel matrix (one Cholesky, m right-hand sides)."""
         Y = self._dev64(Y).reshape(self.n, -1)

@@ -104,6 +104,20 @@ int bo_fit_ex(bo_handle* h, const double* X, const double* y, int32_t n, int32_t
               const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
               double linear_variance, int32_t host_inputs, void* stream);
 
+/* SVGP predictive state: loads ONE task of the reference's batched sparse variational GP
+ * (optimization/Bayesian7.py:129-195: whitened VariationalStrategy, CholeskyVariationalDistribution, kernel
+ * ScaleKernel(Linear + Matern-5/2), ConstantMean, GaussianLikelihood) into the handle, after which bo_posterior / bo_sweep
+ * evaluate its predictive distribution exactly as the chunked pool scan of Bayesian7.py:664-671 does:
+ *   L = chol(k(Z,Z) + jitter I),  u = L^-1 k(Z,x*),  mean = mean_const + u^T m,
+ *   var = k(x*,x*) + jitter - ||u||^2 + ||Ls^T u||^2 + noise          (S = Ls Ls^T, clamped at min_variance)
+ * Z_dev[M,d] inducing points (in the model's own input space), var_mean_dev[M] = m, var_chol_dev[M,M] = Ls (lower,
+ * row-major; the upper triangle is ignored), jitter = gpytorch's variational_cholesky_jitter (1e-6 double / 1e-4 float),
+ * noise = the task's likelihood noise (0 for the latent variance).  Returns 0, a negative error or the failing pivot.
+ * bo_append / bo_refine / bo_acq_grad / bo_posterior_multi refuse a handle in this state; bo_fit returns it to the exact mode. */
+int bo_svgp_load(bo_handle* h, const double* Z_dev, int32_t M, int32_t d, int32_t kernel_kind, const double* lengthscale_host,
+                 double outputscale, double linear_variance, double mean, double noise, double jitter,
+                 const double* var_mean_dev, const double* var_chol_dev, void* stream);
+
 /* introspection of the fitted state (device outputs; any may be NULL):
  *   alpha_dev[n], chol_dev[n,n] (lower triangle, upper zero), linv_dev[n,n] (lower, upper zero) */
 int bo_get_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, void* stream);

@@ -480,3 +480,54 @@ class LogStandardize:
         log_mean = np.asarray(mean_std) * self.std + self.mean
         log_var = np.asarray(var_std) * self.std ** 2
         return np.exp(log_mean + 0.5 * log_var) - self.shift
+
+
+# --------------------------------------------------------------------------------------
+# SVGP predictive distribution: one task of the batched sparse variational GP of
+# optimization/Bayesian7.py:129-195 evaluated as the pool scan of :664-671 does.  gpytorch semantics [3P-recall]:
+# VariationalStrategy (whitened) -- L = chol(K_uu + jitter I), interp = L^-1 K_u*, mean = interp^T m + c,
+# covar = (K_** + jitter I) + interp^T (S - I) interp, S = Ls Ls^T from CholeskyVariationalDistribution (lower triangle of
+# chol_variational_covar); GaussianLikelihood adds the task's noise; MultivariateNormal.variance clamps at min_variance.
+# --------------------------------------------------------------------------------------
+@dataclass
+class SVGPTask:
+    Z: np.ndarray              # (M, d) inducing points, in the model's input space
+    kind: int
+    lengthscale: np.ndarray    # (d,)
+    outputscale: float
+    linear_variance: float
+    mean: float                # ConstantMean
+    noise: float               # likelihood noise (0: latent variance)
+    jitter: float              # variational_cholesky_jitter: 1e-6 double / 1e-4 float
+    m: np.ndarray              # (M,) whitened variational mean
+    Ls: np.ndarray             # (M, M) chol_variational_covar (lower triangle used)
+
+
+def svgp_predict(task: SVGPTask, Xs, min_variance=MIN_VARIANCE):
+    Z = np.ascontiguousarray(task.Z, dtype=np.float64)
+    M, d = Z.shape
+    ls = np.broadcast_to(np.asarray(task.lengthscale, dtype=np.float64), (d,))
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64).reshape(-1, d)
+    Kuu = kernel_matrix(Z, Z, task.kind, ls, task.outputscale, task.linear_variance)
+    Kuu[np.diag_indices(M)] = prior_variance(Z, task.kind, task.outputscale, task.linear_variance) + task.jitter
+    L = _cholesky_lower(Kuu)
+    Kus = kernel_matrix(Z, Xs, task.kind, ls, task.outputscale, task.linear_variance)          # (M, N)
+    interp = sla.solve_triangular(L, Kus, lower=True, check_finite=False)
+    Ls = np.tril(np.asarray(task.Ls, dtype=np.float64))
+    mean = task.mean + interp.T @ np.asarray(task.m, dtype=np.float64)
+    w = Ls.T @ interp
+    var = (prior_variance(Xs, task.kind, task.outputscale, task.linear_variance) + task.jitter
+           - np.einsum("ij,ij->j", interp, interp) + np.einsum("ij,ij->j", w, w) + task.noise)
+    return mean, np.maximum(var, min_variance)
+
+
+def svgp_transform_inputs(x_unit, bounds, x_log_mean, x_log_std):
+    """unit cube -> physical -> log -> standardised (BatchSVGP._transform_inputs, Bayesian7.py:178-188)."""
+    b = np.asarray(bounds, dtype=np.float64)
+    x_phys = np.asarray(x_unit, dtype=np.float64) * (b[1] - b[0]) + b[0]
+    return (np.log(np.maximum(x_phys, 1e-6)) - np.asarray(x_log_mean)) / np.asarray(x_log_std)
+
+
+def svgp_variance_score(tasks, Xs, min_variance=MIN_VARIANCE):
+    """pred.variance.sum(dim=0) over the tasks (Bayesian7.py:670-671)."""
+    return sum(svgp_predict(t, Xs, min_variance)[1] for t in tasks)

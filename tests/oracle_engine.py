@@ -22,6 +22,7 @@ class OracleEngine:
 
     def __init__(self):
         self.gp = None
+        self.svgp = None
         self.n = self.d = 0
         self.fits = 0
 
@@ -38,8 +39,19 @@ class OracleEngine:
         self.fits += 1
         return self
 
+    def load_svgp(self, Z, var_mean, var_chol, kernel="linear_matern52", lengthscale=1.0, outputscale=1.0,
+                  linear_variance=0.0, mean=0.0, noise=0.0, jitter=1e-6):
+        npy = lambda a: torch.as_tensor(a, dtype=torch.float64).cpu().numpy()
+        self.svgp = o.SVGPTask(npy(Z), _K[kernel], npy(lengthscale).reshape(-1), float(outputscale), float(linear_variance),
+                               float(mean), float(noise), float(jitter), npy(var_mean).reshape(-1), npy(var_chol))
+        self.n, self.d = self.svgp.Z.shape
+        return self
+
     def posterior(self, Xs, min_variance=1e-6):
-        mu, var = o.posterior(self.gp, torch.as_tensor(Xs).cpu().numpy(), min_variance)
+        if getattr(self, "svgp", None) is not None:
+            mu, var = o.svgp_predict(self.svgp, torch.as_tensor(Xs).cpu().numpy(), min_variance)
+        else:
+            mu, var = o.posterior(self.gp, torch.as_tensor(Xs).cpu().numpy(), min_variance)
         return torch.from_numpy(mu), torch.from_numpy(var)
 
     def posterior_multi(self, Y, Xs, means=None, min_variance=1e-6, with_variance=True):
@@ -53,6 +65,12 @@ class OracleEngine:
             pts = torch.as_tensor(candidates).cpu().numpy().reshape(-1, self.d)
         else:
             pts = o.sobol_points(*_sobol_arrays(sobol), first_index, count)
+        if getattr(self, "svgp", None) is not None:                       # SVGP state: variance / mean scores only
+            mu, var = o.svgp_predict(self.svgp, pts, min_variance)
+            av = var if acq == "var" else mu
+            tv, ti = o.topk(av, topk, first_index) if topk else (np.empty(0), np.empty(0, dtype=np.int64))
+            out = (torch.from_numpy(np.asarray(tv, dtype=np.float64)), torch.from_numpy(np.asarray(ti, dtype=np.int64)))
+            return out + ((torch.from_numpy(mu), torch.from_numpy(var), torch.from_numpy(av)) if return_all else ())
         tv, ti, mu, var, av = o.sweep(self.gp, pts, _A[acq], best_f, beta, k=topk, first_index=first_index,
                                       min_variance=min_variance)
         vals = np.full(topk, -np.inf); idx = np.full(topk, -1, dtype=np.int64)

@@ -210,3 +210,59 @@ def test_log_standardize_matches_oracle_restatement():
     m, v = np.random.default_rng(5).standard_normal((30, 8)), np.random.default_rng(6).random(30)
     np.testing.assert_allclose(tr.inverse_mean(torch.from_numpy(m), torch.from_numpy(v)).numpy(),
                                ref.inverse_mean(m, v[:, None]), rtol=1e-12)
+
+
+# ---- N2: batched SVGP predictor, host logic with the oracle-backed engine --------------------------------------
+def _svgp_states(T=3, M=40, d=5, seed=0):
+    from bayesianoptimizer_b200.svgp import SVGPTaskState
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(T):
+        Ls = np.tril(rng.standard_normal((M, M)) * 0.05) + np.diag(0.3 + 0.5 * rng.random(M))
+        out.append(SVGPTaskState(torch.from_numpy(rng.standard_normal((M, d))), torch.from_numpy(rng.standard_normal(M)),
+                                 torch.from_numpy(Ls), torch.from_numpy(rng.uniform(0.5, 1.5, d)), float(rng.uniform(0.5, 2)),
+                                 float(rng.uniform(0.05, 0.5)), float(rng.standard_normal()), float(rng.uniform(1e-4, 1e-2))))
+    return out
+
+
+def test_batch_svgp_predictor_host_logic():
+    from bayesianoptimizer_b200.svgp import BatchSVGPPredictor
+    from oracle import gp_oracle as o
+    tasks = _svgp_states()
+    bounds = torch.tensor(DEFAULT_BOUNDS, dtype=torch.float64).t()
+    xlm, xls = torch.full((1, 5), 0.3, dtype=torch.float64), torch.full((1, 5), 1.7, dtype=torch.float64)
+    pred = BatchSVGPPredictor(torch.device("cpu"), tasks, jitter=1e-6, bounds=bounds, x_log_mean=xlm, x_log_std=xls,
+                              engine_factory=OracleEngine)
+    U = np.random.default_rng(1).random((6000, 5))
+    mean, var = pred.predict(U[:50])
+    assert mean.shape == (3, 50) and var.shape == (3, 50)
+    xs = o.svgp_transform_inputs(U, bounds.numpy(), xlm.numpy(), xls.numpy())
+    ot = [o.SVGPTask(t.Z.numpy(), o.KERNEL_LINEAR_MATERN52, t.lengthscale.numpy(), t.outputscale, t.linear_variance, t.mean,
+                     t.noise, 1e-6, t.var_mean.numpy(), t.var_chol.numpy()) for t in tasks]
+    score = o.svgp_variance_score(ot, xs)
+    np.testing.assert_allclose(pred.variance_score(U).numpy(), score, rtol=1e-12)
+    pts, idx = pred.select_batch(U, 25, fps_start=0)
+    big = np.argsort(-score, kind="stable")[:5000]
+    assert set(idx.tolist()) <= set(big.tolist()) and pts.shape == (25, 5) and len(set(idx.tolist())) == 25
+    ref_sel = o.fps(U[torch.topk(torch.from_numpy(score), 5000).indices.numpy()], 25, 0)
+    assert idx.tolist() == torch.topk(torch.from_numpy(score), 5000).indices[ref_sel].tolist()
+
+
+def test_svgp_tasks_from_state_dict():
+    """Checkpoint layout written at Bayesian7.py:708-710 (gpytorch parameter names, softplus / GreaterThan constraints)."""
+    import torch.nn.functional as F
+    from bayesianoptimizer_b200.svgp import tasks_from_state_dict
+    T, M, d = 8, 16, 5
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    msd = {"variational_strategy.inducing_points": r(T, M, d), "variational_strategy.variational_params_initialized": torch.tensor(1),
+           "variational_strategy._variational_distribution.variational_mean": r(T, M),
+           "variational_strategy._variational_distribution.chol_variational_covar": r(T, M, M),
+           "mean_module.raw_constant": r(T), "covar_module.raw_outputscale": r(T),
+           "covar_module.base_kernel.kernels.0.raw_variance": r(T, 1, 1), "covar_module.base_kernel.kernels.1.raw_lengthscale": r(T, 1, d)}
+    lsd = {"noise_covar.raw_noise": r(T, 1)}
+    tasks = tasks_from_state_dict(msd, lsd)
+    assert len(tasks) == T and tasks[3].Z.shape == (M, d) and tasks[3].var_chol.shape == (M, M)
+    assert tasks[3].outputscale == pytest.approx(float(F.softplus(msd["covar_module.raw_outputscale"][3].double())))
+    assert tasks[5].noise == pytest.approx(float(F.softplus(lsd["noise_covar.raw_noise"][5, 0].double())) + 1e-4)
+    np.testing.assert_allclose(tasks[2].lengthscale.numpy(), F.softplus(msd["covar_module.base_kernel.kernels.1.raw_lengthscale"][2, 0].double()).numpy())

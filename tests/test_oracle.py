@@ -246,3 +246,61 @@ def test_log_standardize_round_trip_and_lognormal_mean():
     tn = o.LogStandardize.fit(Yn)
     assert tn.shift == pytest.approx(-Yn.min() + max(1e-12, np.abs(Yn).max() * 1e-6))
     assert np.all(np.isfinite(tn.forward(Yn)))
+
+
+# ---- N2: SVGP predictive (whitened variational strategy) ---------------------------------------------------------
+def _svgp_task(M=60, d=4, seed=0, kind=o.KERNEL_LINEAR_MATERN52):
+    rng = np.random.default_rng(seed)
+    Z = rng.standard_normal((M, d))
+    A = rng.standard_normal((M, M)) * 0.05
+    Ls = np.tril(A) + np.diag(0.3 + 0.5 * rng.random(M))
+    return o.SVGPTask(Z, kind, rng.uniform(0.5, 1.5, d), 1.3, 0.2 if kind == o.KERNEL_LINEAR_MATERN52 else 0.0,
+                      0.1, 2e-3, 1e-6, rng.standard_normal(M), Ls)
+
+
+def test_svgp_predictive_matches_unwhitened_formula():
+    """Independent route: q(u) = N(L m, L S L^T) -> mean = c + k^T K^-1 mu_u, var = k** - k^T K^-1 (K - Sigma_u) K^-1 k."""
+    for kind in (o.KERNEL_LINEAR_MATERN52, o.KERNEL_MATERN52, o.KERNEL_RBF):
+        t = _svgp_task(kind=kind)
+        xs = np.random.default_rng(1).standard_normal((200, 4))
+        mean, var = o.svgp_predict(t, xs, min_variance=0.0)
+        K = o.kernel_matrix(t.Z, t.Z, t.kind, t.lengthscale, t.outputscale, t.linear_variance) + t.jitter * np.eye(len(t.Z))
+        L = np.linalg.cholesky(K)
+        mu_u, Sig_u = L @ t.m, L @ np.tril(t.Ls) @ np.tril(t.Ls).T @ L.T
+        ks = o.kernel_matrix(t.Z, xs, t.kind, t.lengthscale, t.outputscale, t.linear_variance)
+        A = np.linalg.solve(K, ks)
+        np.testing.assert_allclose(mean, t.mean + A.T @ mu_u, rtol=1e-8, atol=1e-9)
+        ref = (o.prior_variance(xs, t.kind, t.outputscale, t.linear_variance) + t.jitter
+               - np.einsum("ij,ij->j", ks, A) + np.einsum("ij,ij->j", A, Sig_u @ A) + t.noise)
+        np.testing.assert_allclose(var, ref, rtol=1e-7, atol=1e-9)
+
+
+def test_svgp_with_optimal_variational_posterior_equals_exact_gp():
+    """Z = X and the optimal Gaussian q(u) (Titsias): the SVGP predictive is the exact GP posterior."""
+    X, y = synth_problem(80, 3, 5, 6)
+    ls, s2, noise = np.array([0.6, 0.5, 0.7]), 1.2, 5e-2
+    gp = o.fit(X, y, o.KERNEL_MATERN52, ls, s2, noise)
+    K = o.kernel_matrix(X, X, o.KERNEL_MATERN52, ls, s2)
+    L = np.linalg.cholesky(K)
+    Sig_u = np.linalg.inv(np.linalg.inv(K) + np.eye(80) / noise)
+    mu_u = Sig_u @ y / noise
+    S = np.linalg.solve(L, np.linalg.solve(L, Sig_u).T)
+    t = o.SVGPTask(X, o.KERNEL_MATERN52, ls, s2, 0.0, 0.0, 0.0, 0.0, np.linalg.solve(L, mu_u), np.linalg.cholesky((S + S.T) / 2))
+    xs = np.random.default_rng(2).random((100, 3))
+    mean, var = o.svgp_predict(t, xs)
+    omu, ovar = o.posterior(gp, xs)
+    np.testing.assert_allclose(mean, omu, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(var, ovar, rtol=1e-5, atol=1e-9)
+
+
+def test_svgp_prior_and_transform():
+    t = _svgp_task()
+    t.m[:] = 0.0
+    t.Ls = np.eye(len(t.Z))                                       # q(u) = prior -> predictive = prior
+    xs = np.random.default_rng(3).standard_normal((50, 4))
+    mean, var = o.svgp_predict(t, xs)
+    np.testing.assert_allclose(mean, t.mean, atol=1e-12)
+    np.testing.assert_allclose(var, o.prior_variance(xs, t.kind, t.outputscale, t.linear_variance) + t.jitter + t.noise, rtol=1e-9)
+    b = np.array([[0.3, 0.001], [1.0, 300.0]])
+    z = o.svgp_transform_inputs(np.array([[0.0, 0.0], [1.0, 1.0]]), b, np.array([[0.0, 1.0]]), np.array([[2.0, 0.5]]))
+    np.testing.assert_allclose(z, [[np.log(0.3) / 2, (np.log(0.001) - 1) / 0.5], [0.0, (np.log(300.0) - 1) / 0.5]], rtol=1e-12)
