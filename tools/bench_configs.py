@@ -83,12 +83,35 @@ Xd, yd = torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev)
 rng = np.random.default_rng(9)
 R = int(os.environ.get("C5_R", 64))
 th = np.concatenate([rng.uniform(np.log(0.05), np.log(5), (R, 10)), np.zeros((R, 1)), rng.uniform(np.log(1e-4), np.log(1e-1), (R, 1))], axis=1)
-eng.lml_grad_batched(Xd, yd, th[:2])
+eng.lml_grad_batched(Xd, yd, th)          # warm-up at the full R: the slot workspaces are sized by the first call
 torch.cuda.synchronize(); t = time.perf_counter()
 lml, grad, status = eng.lml_grad_batched(Xd, yd, th)
 torch.cuda.synchronize(); ms = (time.perf_counter() - t) * 1e3
 rep["C5"] = {"n": 2048, "d": 10, "R": R, "ms_total": ms, "ms_per_restart": ms / R, "failed": int((status != 0).sum()),
              "flops_per_restart": 2048 ** 3, "tflops": R * 2048 ** 3 / ms * 1e-9, "frac_of_fp64_peak": R * 2048 ** 3 / ms * 1e-9 / peak}
+# ---- N2: SVGP pool scan, T = 8 tasks x M = 2048 inducing points, d = 5 (Bayesian7 defaults: pool 10^4) ----
+from bayesianoptimizer_b200.svgp import BatchSVGPPredictor, SVGPTaskState
+T, M, d5 = 8, 2048, 5
+g = np.random.default_rng(21)
+states = []
+for _ in range(T):
+    Ls = np.tril(g.standard_normal((M, M)) * 0.01) + np.diag(0.3 + 0.5 * g.random(M))
+    states.append(SVGPTaskState(torch.from_numpy(g.standard_normal((M, d5))).to(dev), torch.from_numpy(g.standard_normal(M)).to(dev),
+                                torch.from_numpy(Ls).to(dev), torch.full((d5,), 1.5, dtype=torch.float64), 1.0, 0.2, 0.0, 1e-3))
+torch.cuda.synchronize(); t = time.perf_counter()
+pred = BatchSVGPPredictor(dev, states, jitter=1e-4)
+torch.cuda.synchronize(); load_ms = (time.perf_counter() - t) * 1e3
+sv = {"tasks": T, "M": M, "d": d5, "load_ms_all_tasks": load_ms, "flop_per_candidate_task": 2.0 * M * M + M * (3 * d5 + 14.0)}
+for pool in (10_000, 1_000_000):
+    U = torch.rand(pool, d5, dtype=torch.float64, device=dev)
+    ms = wall(lambda: pred.variance_score(U, 1e-3))
+    sel_ms = wall(lambda: pred.select_batch(U, 500, min_variance=1e-3)) if pool == 10_000 else None
+    sv[f"pool_{pool}"] = {"scan_ms": ms, "cand_per_s": pool / ms * 1e3,
+                          "tflops_alg": pool * T * sv["flop_per_candidate_task"] / ms * 1e-9,
+                          "frac_of_fp64_peak": pool * T * sv["flop_per_candidate_task"] / ms * 1e-9 / peak,
+                          "scan_topk_fps500_ms": sel_ms}
+rep["N2_svgp"] = sv
+pred.close()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rep, open("gpurun_out/configs_report.json", "w"), indent=1)
 print(json.dumps(rep, indent=1))
