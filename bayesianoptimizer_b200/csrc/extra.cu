@@ -151,35 +151,41 @@ __global__ void __launch_bounds__(256) trmm_lower_skinny_kernel(const double* __
     }
 }
 
-// W[q][j] = sum_{i>=j} Li[i][j] V[q][i] for QB right-hand sides (block per 32 columns, 8 row lanes)
+// Wp[s][q][j] = sum over the s-th row segment of { i >= j } of Li[i][j] V[q][i] for QB right-hand sides
+// (block per 32 columns x row segment x right-hand-side group; the finaliser adds the segments in order).
+// The rows below a column block are split into `gridDim.y` contiguous segments so that the long first columns do
+// not serialise on a single CTA (one CTA walking all np rows took 0.5 ms at n = 3000).
 template <int QB>
 __global__ void __launch_bounds__(256) trmm_lower_t_skinny_kernel(const double* __restrict__ Li, int ld, int np,
                                                                   const double* __restrict__ V, int k,
                                                                   double* __restrict__ out) {
     __shared__ double red[8][QB][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + tx, q0 = blockIdx.y * QB;
+    const int j0 = blockIdx.x * 32, j = j0 + tx, q0 = blockIdx.z * QB;
+    const int rows = np - j0;
+    const int chunk = ((rows + (int)gridDim.y - 1) / (int)gridDim.y + 7) & ~7;
+    const int r0 = j0 + blockIdx.y * chunk, r1 = min(np, r0 + chunk);
     double acc[QB];
 #pragma unroll
     for (int q = 0; q < QB; ++q) acc[q] = 0.0;
-    for (int i = blockIdx.x * 32 + ty; i < np; i += 8) {
-        if (i >= j) {
-            const double a = Li[(size_t)i * ld + j];
+#pragma unroll 4
+    for (int i = r0 + ty; i < r1; i += 8) {
+        const double a = (i >= j) ? Li[(size_t)i * ld + j] : 0.0;
 #pragma unroll
-            for (int q = 0; q < QB; ++q)
-                if (q0 + q < k) acc[q] = fma(a, V[(size_t)(q0 + q) * np + i], acc[q]);
-        }
+        for (int q = 0; q < QB; ++q)
+            if (q0 + q < k) acc[q] = fma(a, V[(size_t)(q0 + q) * np + i], acc[q]);
     }
 #pragma unroll
     for (int q = 0; q < QB; ++q) red[ty][q][tx] = acc[q];
     __syncthreads();
     if (ty == 0) {
+        double* o = out + (size_t)blockIdx.y * k * np;
 #pragma unroll
         for (int q = 0; q < QB; ++q) {
             double t = 0.0;
 #pragma unroll
             for (int r = 0; r < 8; ++r) t += red[r][q][tx];
-            if (q0 + q < k) out[(size_t)(q0 + q) * np + j] = t;
+            if (q0 + q < k) o[(size_t)(q0 + q) * np + j] = t;
         }
     }
 }
@@ -205,7 +211,7 @@ template <int DP>
 __global__ void __launch_bounds__(256) acq_grad_finalize_kernel(const double* __restrict__ Xs, const double* __restrict__ alpha,
                                                                 int n, int np, Hyper hyp, const double* __restrict__ Xq, int d,
                                                                 const double* __restrict__ kv, const double* __restrict__ gv,
-                                                                const double* __restrict__ V, const double* __restrict__ W,
+                                                                const double* __restrict__ V, const double* __restrict__ W, int wsplits, int k,
                                                                 int acq, double best_f, double sqrt_beta, double min_var,
                                                                 double* __restrict__ val, double* __restrict__ grad) {
     __shared__ double red[8];
@@ -220,7 +226,9 @@ __global__ void __launch_bounds__(256) acq_grad_finalize_kernel(const double* __
         const double v = V[(size_t)qi * np + j];
         ss = fma(v, v, ss);
         if (j < n) {
-            const double a = alpha[j], w = W[(size_t)qi * np + j], g = gv[(size_t)qi * np + j];
+            double w = 0.0;
+            for (int sp = 0; sp < wsplits; ++sp) w += W[((size_t)sp * k + qi) * np + j];      // row segments, in order
+            const double a = alpha[j], g = gv[(size_t)qi * np + j];
             mu = fma(kv[(size_t)qi * np + j], a, mu);
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
@@ -290,6 +298,13 @@ static int ensure_qbuf(bo_handle* h, size_t elems) {
 }
 
 constexpr int QB = 8;
+// row segments of the transposed skinny TRMM: enough CTAs for ~8 waves, at most 16 (workspace = (3 + splits) k np doubles)
+static int acq_wsplits(const bo_handle* h, int k) {
+    const int base = (h->np / 32) * ((k + QB - 1) / QB);
+    int s = (8 * h->sm_count + base - 1) / base;
+    return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+static size_t acq_ws_elems(const bo_handle* h, int k) { return (size_t)(3 + acq_wsplits(h, k)) * k * h->np; }
 
 template <int DP>
 static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, double min_var, const double* Xq, int k,
@@ -301,9 +316,10 @@ static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, doub
     const int qg = (k + QB - 1) / QB;
     trmm_lower_skinny_kernel<QB><<<dim3(np / 8, qg), 256, 0, st>>>(h->Li, ld, np, kv, k, V);
     BO_LAUNCH_CHECK(h);
-    trmm_lower_t_skinny_kernel<QB><<<dim3(np / 32, qg), 256, 0, st>>>(h->Li, ld, np, V, k, W);
+    const int ws_splits = acq_wsplits(h, k);
+    trmm_lower_t_skinny_kernel<QB><<<dim3(np / 32, ws_splits, qg), 256, 0, st>>>(h->Li, ld, np, V, k, W);
     BO_LAUNCH_CHECK(h);
-    acq_grad_finalize_kernel<DP><<<k, 256, 0, st>>>(h->Xs, h->alpha, h->n, np, h->hyp, Xq, h->d, kv, gv, V, W, acq, best_f,
+    acq_grad_finalize_kernel<DP><<<k, 256, 0, st>>>(h->Xs, h->alpha, h->n, np, h->hyp, Xq, h->d, kv, gv, V, W, ws_splits, k, acq, best_f,
                                                    sqrt(beta), min_var, val, grad);
     BO_LAUNCH_CHECK(h);
     return 0;
@@ -327,7 +343,7 @@ int acq_grad_impl(bo_handle* h, int acq_kind, double best_f, double beta, double
     int rc = check_query_args(h, acq_kind, beta, Xq_dev, val_dev, grad_dev, k);
     if (rc) return rc;
     BO_CUDA(h, cudaSetDevice(h->device));
-    if ((rc = ensure_qbuf(h, (size_t)4 * k * h->np + 64))) return rc;
+    if ((rc = ensure_qbuf(h, acq_ws_elems(h, k) + 64))) return rc;
     return BO_DISPATCH_DP(h->dp, eval_acq_grad, h, acq_kind, best_f, beta, min_var, Xq_dev, k, val_dev, grad_dev, h->qbuf, st);
 }
 
@@ -379,7 +395,7 @@ int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double m
     if (iters < 0) return fail(h, BO_E_INVALID, "bo_refine: iters must be >= 0");
     BO_CUDA(h, cudaSetDevice(h->device));
     const int d = h->d, np = h->np;
-    const size_t ws_elems = (size_t)4 * k * np;
+    const size_t ws_elems = acq_ws_elems(h, k);
     // layout: [acq-grad scratch | g | xn | fn | gn | step]
     if ((rc = ensure_qbuf(h, ws_elems + (size_t)k * (3 * d + 2) + 64))) return rc;
     double* ws = h->qbuf;
