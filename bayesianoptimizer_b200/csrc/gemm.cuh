@@ -33,14 +33,14 @@ struct GemmSmem {
 };
 
 template <int BM, int BN>
-__global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* __restrict__ probs, int nprob) {
+__global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* __restrict__ probs, int nprob, int tile0 = 0) {
     extern __shared__ __align__(16) double gsm[];
     using SM = GemmSmem<BM, BN>;
     constexpr int WM = BM / 2, WN = BN / 4;      // 8 warps as 2 (M) x 4 (N)
     constexpr int MT = WM / 8, NT = WN / 8;
 
     // locate the problem of this tile
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x + tile0;     // tile0: first flattened tile when `probs` is a sub-range of a launch list
     int pi = 0;
     while (pi + 1 < nprob && tile >= probs[pi].tile_end) ++pi;
     const GemmProblem P = probs[pi];

@@ -18,6 +18,11 @@ struct LmlBatch {
     Hyper* hyps = nullptr; int* info = nullptr;
     Hyper* hyps_host = nullptr; double* out_host = nullptr; int* info_host = nullptr;     // pinned
     std::vector<GemmProblem> probs; std::vector<GemmLaunch> launches; GemmProblem* plan_dev = nullptr;
+    // slot groups run their (panel -> SYRK -> panel ...) chains on separate streams, so one group's latency-bound panel
+    // kernels hide behind another group's trailing updates
+    static constexpr int MAX_GROUPS = 4;
+    cudaStream_t gstream[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static void lml_batch_free(LmlBatch* b) {
@@ -28,6 +33,11 @@ static void lml_batch_free(LmlBatch* b) {
     if (b->hyps_host) cudaFreeHost(b->hyps_host);
     if (b->out_host) cudaFreeHost(b->out_host);
     if (b->info_host) cudaFreeHost(b->info_host);
+    for (int g = 0; g < LmlBatch::MAX_GROUPS; ++g) {
+        if (b->gstream[g]) cudaStreamDestroy(b->gstream[g]);
+        if (b->join_ev[g]) cudaEventDestroy(b->join_ev[g]);
+    }
+    if (b->fork_ev) cudaEventDestroy(b->fork_ev);
     cudaGetLastError();
     delete b;
 }
@@ -149,18 +159,24 @@ __global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restric
     out[3 + d] = tot[DP + 4] + 0.5 * tot[DP + 5];                                  // d / d log linear variance (kind 2)
 }
 
+// slots [s0, s0 + S) of the batch
 template <int DP>
-static int lml_launch_gram(bo_handle* h, LmlBatch* b, int S, cudaStream_t st) {
-    gram_batched_kernel<DP><<<dim3(b->np / 32, b->np / 32, S), dim3(32, 8), 0, st>>>(b->Xs, b->n, b->np, b->np, b->hyps, b->Lm);
+static int lml_launch_gram(bo_handle* h, LmlBatch* b, int s0, int S, cudaStream_t st) {
+    const size_t c = b->np;
+    gram_batched_kernel<DP><<<dim3(b->np / 32, b->np / 32, S), dim3(32, 8), 0, st>>>(b->Xs + s0 * c * BO_MAX_DIM, b->n, b->np, b->np,
+                                                                                    b->hyps + s0, b->Lm + s0 * c * c);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
 template <int DP>
-static int lml_launch_grad(bo_handle* h, LmlBatch* b, int S, cudaStream_t st) {
+static int lml_launch_grad(bo_handle* h, LmlBatch* b, int s0, int S, cudaStream_t st) {
     const int nt = b->np / 32;
-    lml_grad_tile_kernel<DP><<<dim3(nt, nt, S), 256, 0, st>>>(b->Xs, b->alpha, b->Kw, b->Lm, b->yv, b->np, b->n, b->np, b->hyps, b->gpart);
+    const size_t c = b->np;
+    double* gpart = b->gpart + (size_t)s0 * nt * nt * (DP + 6);
+    lml_grad_tile_kernel<DP><<<dim3(nt, nt, S), 256, 0, st>>>(b->Xs + s0 * c * BO_MAX_DIM, b->alpha + s0 * c, b->Kw + s0 * c * c,
+                                                              b->Lm + s0 * c * c, b->yv, b->np, b->n, b->np, b->hyps + s0, gpart);
     BO_LAUNCH_CHECK(h);
-    lml_reduce_kernel<DP><<<S, 256, 0, st>>>(b->gpart, nt * nt, b->n, b->d, b->hyps, b->out);
+    lml_reduce_kernel<DP><<<S, 256, 0, st>>>(gpart, nt * nt, b->n, b->d, b->hyps + s0, b->out + (size_t)s0 * (BO_MAX_DIM + 4));
     BO_LAUNCH_CHECK(h);
     return 0;
 }
@@ -191,6 +207,11 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaMallocHost(&b->hyps_host, S * sizeof(Hyper));
     if (e == cudaSuccess) e = cudaMallocHost(&b->out_host, (size_t)S * (BO_MAX_DIM + 4) * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost(&b->info_host, S * sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming);
+    for (int g = 0; g < LmlBatch::MAX_GROUPS && e == cudaSuccess; ++g) {
+        e = cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->join_ev[g], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         lml_batch_free(b);
         cudaGetLastError();
@@ -264,16 +285,58 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
     return 0;
 }
 
-static int lml_gemm(bo_handle* h, LmlBatch* b, int li, int S_active, cudaStream_t st) {
-    // a launch lists the problems slot-major with identical tile counts per slot -> a prefix covers S_active slots
+static int lml_gemm(bo_handle* h, LmlBatch* b, int li, int s0, int S_active, cudaStream_t st) {
+    // a launch lists the problems slot-major with identical tile counts per slot -> slots [s0, s0 + S_active) are a
+    // contiguous sub-range of the list; the problems' tile_begin stay launch-absolute, hence the tile offset
     const GemmLaunch& L = b->launches[li];
     if (L.tiles == 0) return 0;
     const int per_slot = L.count / b->S, tiles_per_slot = L.tiles / b->S;
     const int count = per_slot * S_active, tiles = tiles_per_slot * S_active;
-    if (L.cfg == 1) dgemm_grouped_kernel<128, 128><<<tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(b->plan_dev + L.first, count);
-    else dgemm_grouped_kernel<64, 64><<<tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(b->plan_dev + L.first, count);
+    const GemmProblem* pr = b->plan_dev + L.first + (size_t)per_slot * s0;
+    if (L.cfg == 1) dgemm_grouped_kernel<128, 128><<<tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(pr, count, tiles_per_slot * s0);
+    else dgemm_grouped_kernel<64, 64><<<tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(pr, count, tiles_per_slot * s0);
     BO_LAUNCH_CHECK(h);
     return 0;
+}
+
+// the whole evaluation of slots [s0, s0 + Sa): Gram -> Cholesky -> inverse -> K^-1 -> alpha -> gradient partials
+static int lml_run_slots(bo_handle* h, LmlBatch* b, int s0, int Sa, int n, int d, double mean, cudaStream_t st) {
+    const int np = b->np, ld = np, nb = np / NB;
+    const size_t c = np, mat = c * c;
+    int rc;
+    double* Lm = b->Lm + s0 * mat; double* Li = b->Li + s0 * mat;
+    rescale_batched_kernel<<<dim3((np + 127) / 128, 1, Sa), 128, 0, st>>>(np, d, b->hyps + s0, b->Xraw, b->Xs + s0 * c * BO_MAX_DIM);
+    BO_LAUNCH_CHECK(h);
+    if ((rc = BO_DISPATCH_DP(b->dp, lml_launch_gram, h, b, s0, Sa, st))) return rc;
+    BO_CUDA(h, cudaMemsetAsync(Li, 0, (size_t)Sa * mat * sizeof(double), st));
+    for (int kb = 0; kb < nb; ++kb) {
+        const size_t off = (size_t)kb * NB * ld + kb * NB;
+        chol_panel_kernel<<<Sa * (nb - kb), 256, 0, st>>>(Lm + off, ld, Li + off, b->info + s0, kb * NB, mat, nb - kb);
+        BO_LAUNCH_CHECK(h);
+        if (kb + 1 < nb && (rc = lml_gemm(h, b, kb, s0, Sa, st))) return rc;
+    }
+    leaf_inverse_kernel<<<Sa * nb, 256, 0, st>>>(Lm, ld, Li, mat, nb);
+    BO_LAUNCH_CHECK(h);
+    for (int li = nb - 1; li < (int)b->launches.size(); ++li)             // inverse levels, then K^-1 = L^-T L^-1
+        if ((rc = lml_gemm(h, b, li, s0, Sa, st))) return rc;
+    // alpha = L^-T (L^-1 r) + one refinement step against the factor (as in the single fit)
+    const dim3 gv((np + 255) / 256, 1, Sa), gr(np / 8, 1, Sa), gt(np / 32, TRMVT_SPLITS, Sa);
+    double* v1 = b->v1 + s0 * c; double* v2 = b->v2 + s0 * c; double* v3 = b->v3 + s0 * c; double* alpha = b->alpha + s0 * c;
+    double* tpart = b->tpart + (size_t)s0 * TRMVT_SPLITS * c;
+    resid_init_kernel<<<gv, 256, 0, st>>>(b->yv, n, np, mean, v1);
+    trmv_lower_kernel<<<gr, 256, 0, st>>>(Li, ld, np, v1, v2, mat);
+    trmv_lower_t_kernel<<<gt, 256, 0, st>>>(Li, ld, np, v2, tpart, mat);
+    trmv_reduce_kernel<<<gv, 256, 0, st>>>(tpart, np, alpha, 0);
+    trmv_lower_t_kernel<<<gt, 256, 0, st>>>(Lm, ld, np, alpha, tpart, mat);
+    trmv_reduce_kernel<<<gv, 256, 0, st>>>(tpart, np, v2, 0);
+    trmv_lower_kernel<<<gr, 256, 0, st>>>(Lm, ld, np, v2, v3, mat);
+    sub_vec_kernel<<<gv, 256, 0, st>>>(v1, v3, np, v2);
+    trmv_lower_kernel<<<gr, 256, 0, st>>>(Li, ld, np, v2, v3, mat);
+    trmv_lower_t_kernel<<<gt, 256, 0, st>>>(Li, ld, np, v3, tpart, mat);
+    trmv_reduce_kernel<<<gv, 256, 0, st>>>(tpart, np, alpha, 1);
+    h->launches += 11;
+    BO_CUDA(h, cudaGetLastError());
+    return BO_DISPATCH_DP(b->dp, lml_launch_grad, h, b, s0, Sa, st);
 }
 
 int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int d, int kind, double mean,
@@ -316,36 +379,20 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
         }
         BO_CUDA(h, cudaMemcpyAsync(b->hyps, b->hyps_host, Sa * sizeof(Hyper), cudaMemcpyHostToDevice, st));
         BO_CUDA(h, cudaMemsetAsync(b->info, 0, Sa * sizeof(int), st));
-        rescale_batched_kernel<<<dim3((np + 127) / 128, 1, Sa), 128, 0, st>>>(np, d, b->hyps, b->Xraw, b->Xs);
-        BO_LAUNCH_CHECK(h);
-        if ((rc = BO_DISPATCH_DP(b->dp, lml_launch_gram, h, b, Sa, st))) return rc;
-        BO_CUDA(h, cudaMemsetAsync(b->Li, 0, (size_t)Sa * mat * sizeof(double), st));
-        for (int kb = 0; kb < nb; ++kb) {
-            const size_t off = (size_t)kb * NB * ld + kb * NB;
-            chol_panel_kernel<<<Sa * (nb - kb), 256, 0, st>>>(b->Lm + off, ld, b->Li + off, b->info, kb * NB, mat, nb - kb);
-            BO_LAUNCH_CHECK(h);
-            if (kb + 1 < nb && (rc = lml_gemm(h, b, kb, Sa, st))) return rc;
+        // slot groups on their own streams (fork after the parameter upload, join before the read-back)
+        // measured (tools/lml_groups_probe.py): 4 groups win 8-10 % from 8 slots up, 2 groups 4 % at 4-7 slots of a large
+        // problem; below that the split only shrinks the launches
+        int G = Sa >= 8 ? 4 : (Sa >= 4 && np >= 2048) ? 2 : 1;
+        { const char* ge = getenv("BO_B200_LML_GROUPS"); if (ge && atoi(ge) >= 1 && atoi(ge) <= LmlBatch::MAX_GROUPS && atoi(ge) <= Sa) G = atoi(ge); }
+        BO_CUDA(h, cudaEventRecord(b->fork_ev, st));
+        for (int g = 0, s0 = 0; g < G; ++g) {
+            const int Sg = Sa / G + (g < Sa % G ? 1 : 0);
+            BO_CUDA(h, cudaStreamWaitEvent(b->gstream[g], b->fork_ev, 0));
+            if ((rc = lml_run_slots(h, b, s0, Sg, n, d, mean, b->gstream[g]))) return rc;
+            BO_CUDA(h, cudaEventRecord(b->join_ev[g], b->gstream[g]));
+            BO_CUDA(h, cudaStreamWaitEvent(st, b->join_ev[g], 0));
+            s0 += Sg;
         }
-        leaf_inverse_kernel<<<Sa * nb, 256, 0, st>>>(b->Lm, ld, b->Li, mat, nb);
-        BO_LAUNCH_CHECK(h);
-        for (int li = nb - 1; li < (int)b->launches.size(); ++li)             // inverse levels, then K^-1 = L^-T L^-1
-            if ((rc = lml_gemm(h, b, li, Sa, st))) return rc;
-        // alpha = L^-T (L^-1 r) + one refinement step against the factor (as in the single fit)
-        const dim3 gv((np + 255) / 256, 1, Sa), gr(np / 8, 1, Sa), gt(np / 32, TRMVT_SPLITS, Sa);
-        resid_init_kernel<<<gv, 256, 0, st>>>(b->yv, n, np, mean, b->v1);
-        trmv_lower_kernel<<<gr, 256, 0, st>>>(b->Li, ld, np, b->v1, b->v2, mat);
-        trmv_lower_t_kernel<<<gt, 256, 0, st>>>(b->Li, ld, np, b->v2, b->tpart, mat);
-        trmv_reduce_kernel<<<gv, 256, 0, st>>>(b->tpart, np, b->alpha, 0);
-        trmv_lower_t_kernel<<<gt, 256, 0, st>>>(b->Lm, ld, np, b->alpha, b->tpart, mat);
-        trmv_reduce_kernel<<<gv, 256, 0, st>>>(b->tpart, np, b->v2, 0);
-        trmv_lower_kernel<<<gr, 256, 0, st>>>(b->Lm, ld, np, b->v2, b->v3, mat);
-        sub_vec_kernel<<<gv, 256, 0, st>>>(b->v1, b->v3, np, b->v2);
-        trmv_lower_kernel<<<gr, 256, 0, st>>>(b->Li, ld, np, b->v2, b->v3, mat);
-        trmv_lower_t_kernel<<<gt, 256, 0, st>>>(b->Li, ld, np, b->v3, b->tpart, mat);
-        trmv_reduce_kernel<<<gv, 256, 0, st>>>(b->tpart, np, b->alpha, 1);
-        h->launches += 11;
-        BO_CUDA(h, cudaGetLastError());
-        if ((rc = BO_DISPATCH_DP(b->dp, lml_launch_grad, h, b, Sa, st))) return rc;
         BO_CUDA(h, cudaMemcpyAsync(b->out_host, b->out, (size_t)Sa * (BO_MAX_DIM + 4) * sizeof(double), cudaMemcpyDeviceToHost, st));
         BO_CUDA(h, cudaMemcpyAsync(b->info_host, b->info, Sa * sizeof(int), cudaMemcpyDeviceToHost, st));
         BO_CUDA(h, cudaStreamSynchronize(st));
