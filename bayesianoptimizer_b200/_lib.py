@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbo_b200.so")
 
 BO_MAX_DIM = 16
 BO_MAX_TOPK = 64
+BO_MAX_SELECT = 8192
 BO_SOBOL_BITS = 30
 
 KERNEL_MATERN52, KERNEL_RBF, KERNEL_LINEAR_MATERN52 = 0, 1, 2
@@ -45,6 +46,7 @@ SIGNATURES = {
     "bo_fit_host": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _vp]),
     "bo_fit_ex": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _f64, _i32, _vp]),
     "bo_posterior_multi": (C.c_int, [_vp, _vp, _i32, _pd, _vp, _i64, _f64, _vp, _vp, _vp]),
+    "bo_topk_scores": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "bo_svgp_load": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _pd, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp]),
     "bo_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "bo_num_obs": (C.c_int, [_vp]),

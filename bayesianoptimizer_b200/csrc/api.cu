@@ -12,6 +12,8 @@ int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double m
 int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, cudaStream_t st);
 int posterior_multi_impl(bo_handle* h, const double* Y_dev, int m, const double* means_host, const double* Xs_dev, int64_t N,
                          double min_var, double* mean_dev, double* var_dev, cudaStream_t st);
+int topk_scores_impl(bo_handle* h, const double* scores_dev, int64_t N, int64_t first_index, int K, double* vals_dev,
+                     int64_t* idx_dev, cudaStream_t st);
 int fps_impl(bo_handle* h, const double* X_dev, int64_t N, int d, int m, int64_t start, int64_t* idx_dev, cudaStream_t st);
 int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops);
 int export_state(bo_handle* h, double* alpha_dev, double* chol_dev, double* linv_dev, cudaStream_t st);
@@ -84,7 +86,7 @@ void bo_destroy(bo_handle* h) {
     lml_release(h);
     void* ptrs[] = {h->qbuf, h->split_ws, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
-                    h->out_stage_val, h->out_stage_idx, h->Lp2};
+                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->info_host) cudaFreeHost(h->info_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -129,6 +131,12 @@ int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_
                 int32_t kernel_kind, const double* lengthscale_host, double outputscale, double noise,
                 double mean, double jitter, void* stream) {
     return bo_fit_ex(h, X_host, y_host, n, d, kernel_kind, lengthscale_host, outputscale, noise, mean, jitter, 0.0, 1, stream);
+}
+
+int bo_topk_scores(bo_handle* h, const double* scores_dev, int64_t N, int64_t first_index, int32_t K, double* vals_dev,
+                   int64_t* idx_dev, void* stream) {
+    if (!h) return BO_E_INVALID;
+    return topk_scores_impl(h, scores_dev, N, first_index, K, vals_dev, idx_dev, (cudaStream_t)stream);
 }
 
 int bo_svgp_load(bo_handle* h, const double* Z_dev, int32_t M, int32_t d, int32_t kernel_kind, const double* lengthscale_host,

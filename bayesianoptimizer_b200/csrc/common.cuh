@@ -106,6 +106,8 @@ struct bo_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool sweep_timed = false;
 
+    void* select_ws = nullptr; size_t select_bytes = 0;  // large top-K (select.cu)
+
     // K5-K7 workspaces
     double* qbuf = nullptr; size_t qbuf_elems = 0;      // refinement / acq-grad scratch
     void* lml_batch = nullptr;                          // bo::LmlBatch: slot workspaces of the batched LML restarts (lml.cuh)

@@ -298,6 +298,16 @@ class GPEngine:
                                                   status.data_ptr(), _stream_ptr(self.device)))
         return lml, grad, status
 
+    def topk_scores(self, scores, k: int, first_index: int = 0):
+        """(values[k], indices[k]) of the k <= 8192 best scores on the device, value desc / index asc / NaN last
+        (the CPU ``torch.topk(unc, K_big)`` of Bayesian7.py:681)."""
+        scores = self._dev64(scores, (-1,))
+        vals = torch.empty(int(k), dtype=torch.float64, device=self.device)
+        idx = torch.empty(int(k), dtype=torch.int64, device=self.device)
+        self._check(self._lib.bo_topk_scores(self._h, scores.data_ptr(), scores.numel(), int(first_index), int(k),
+                                             vals.data_ptr(), idx.data_ptr(), _stream_ptr(self.device)))
+        return vals, idx
+
     def fps(self, X, m: int, start: int = 0) -> torch.Tensor:
         """Indices of m farthest-point samples of X (N,d), greedy from ``start`` (Bayesian7.py:82-107)."""
         X = self._dev64(X)

@@ -46,6 +46,7 @@ class GPConfig:
     fit_hyperparameters: bool = True     # maximise the exact LML (fit_gpytorch_mll, Bayesian.py:93)
     hyper_restarts: int = 16             # batched random restarts screened by bo_lml_grad_batched
     hyper_refine: int = 4                # best screened restarts refined in lock step (one batched LML call per step)
+    hyper_refine_warm: int = 2           # ... once a previous fit warm-starts the search (the reference refits from one start)
     hyper_maxiter: int = 50              # lock-step L-BFGS iterations
     hyper_prior: Optional[str] = "auto"  # "auto": botorch defaults (rbf -> lognormal, matern52 -> gamma); None = max. likelihood
     lengthscale: Optional[Sequence[float]] = None   # fixed / initial ARD lengthscales (unit cube)
@@ -283,7 +284,8 @@ class BayesianOptimizer:
         unpack = lambda t: (np.exp(t[:d]), float(np.exp(t[d])), float(np.exp(t[d + 1])), float(np.exp(t[d + 2])) if lin else 0.0)
         if not np.isfinite(score).any():
             return unpack(th0)
-        keep = np.argsort(-score)[:max(1, int(cfg.hyper_refine))]
+        n_refine = cfg.hyper_refine if self._hyper is None else min(cfg.hyper_refine, cfg.hyper_refine_warm)
+        keep = np.argsort(-score)[:max(1, int(n_refine))]
         if 0 not in keep and np.isfinite(score[0]):
             keep = np.concatenate([keep[:-1], [0]]) if len(keep) > 1 else np.array([0])      # always refine the warm start
         th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas[keep], lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter))
@@ -382,7 +384,7 @@ class BayesianOptimizer:
         _, _, _, _, acq = eng.sweep(cfg.acquisition, best_f, cfg.beta, sobol=sob, count=N, topk=1, return_all=True)
         K_big = int(min(max(5000, 20 * q), cfg.K_BIG_CAP, N))
         K_big = max(K_big, min(q, N))
-        idx = torch.topk(acq, K_big).indices
+        _, idx = eng.topk_scores(acq, K_big)
         pts = eng.sobol_points(sob, idx)
         sel = eng.fps(pts, min(q, K_big), 0)          # device FPS from the best-scoring candidate (Bayesian7.py:685)
         return pts[sel].to(self.device, dtype=torch.float64)

@@ -8,7 +8,7 @@ inducing points, variational mean / Cholesky factor, kernel and likelihood param
 distribution with the same fused CUDA sweep as the exact path: one ``bo_svgp_load`` per task, then ``bo_posterior`` /
 ``bo_sweep`` (two triangular DMMA contractions per candidate block), the variance-sum score, top-K and FPS on the device.
 
-PyTorch here is plumbing (tensors, elementwise input transform, the T-way sum of scores, ``topk`` of the summed score).
+PyTorch here is plumbing (tensors, the elementwise input transform, the T-way sum of the per-task scores).
 """
 from __future__ import annotations
 
@@ -110,7 +110,7 @@ class BatchSVGPPredictor:
         N = cand_unit.shape[0]
         score = self.variance_score(cand_unit, min_variance)
         K_big = int(min(max(5000, 20 * batch_k), K_big_cap, N))
-        idx_big = torch.topk(score, K_big).indices
+        _, idx_big = self.engines[0].topk_scores(score, K_big)                  # device radix select (bo_topk_scores)
         big = cand_unit[idx_big].contiguous()
         if batch_k >= K_big:
             return big, idx_big

@@ -60,6 +60,7 @@ extern "C" {
 #define BO_E_CAPACITY (-5)  /* n or d or topk beyond the compiled limits     */
 
 #define BO_MAX_DIM   16     /* input dimension limit (reference: d = 5)      */
+#define BO_MAX_SELECT 8192   /* largest K of bo_topk_scores (K_BIG_CAP = 8000, optimization/Bayesian7.py:66) */
 #define BO_MAX_TOPK  64     /* in-kernel top-k limit                         */
 #define BO_SOBOL_BITS 30    /* torch.quasirandom.SobolEngine.MAXBIT          */
 
@@ -187,6 +188,13 @@ int bo_append(bo_handle* h, const double* x_dev, double y, int32_t use_believer,
 int bo_lml_grad_batched(bo_handle* h, const double* X_dev, const double* y_dev, int32_t n, int32_t d,
                         int32_t kernel_kind, double mean, const double* theta_host, int32_t R,
                         double* lml_host, double* grad_host, int32_t* status_host, void* stream);
+
+/* Large top-K of a dense score array: the K <= BO_MAX_SELECT best entries of scores_dev[N] in the order of the fused
+ * sweep's top-k (value descending, global index = first_index + position ascending, NaN last) to vals_dev[K] /
+ * idx_dev[K]; entries past N are (-inf, -1).  Radix select + ordered tie compaction + one-CTA bitonic sort.
+ * Replaces `torch.topk(unc, K_big)` on the CPU copy of all scores (optimization/Bayesian7.py:671-682). */
+int bo_topk_scores(bo_handle* h, const double* scores_dev, int64_t N, int64_t first_index, int32_t K, double* vals_dev,
+                   int64_t* idx_dev, void* stream);
 
 /* Greedy farthest-point sampling of m of the N points X_dev[N,d], starting from index `start`; picks go to
  * idx_dev[m] in selection order (arg-max of the running min squared distance, first index on ties).

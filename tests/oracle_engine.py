@@ -120,6 +120,12 @@ class OracleEngine:
                 lml.append(-np.inf); grad.append(np.zeros(p)); status.append(e.pivot)
         return torch.tensor(lml), torch.from_numpy(np.array(grad)), torch.tensor(status, dtype=torch.int32)
 
+    def topk_scores(self, scores, k, first_index=0):
+        tv, ti = o.topk(torch.as_tensor(scores).cpu().numpy().reshape(-1), int(k), first_index)
+        vals = np.full(int(k), -np.inf); idx = np.full(int(k), -1, dtype=np.int64)
+        vals[:len(tv)] = tv; idx[:len(ti)] = ti
+        return torch.from_numpy(vals), torch.from_numpy(idx)
+
     def fps(self, X, m, start=0):
         return torch.from_numpy(o.fps(torch.as_tensor(X).cpu().numpy(), m, start))
 

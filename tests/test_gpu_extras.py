@@ -217,3 +217,29 @@ def test_device_fps_matches_reference_algorithm(engine, N, d, m):
     assert np.array_equal(got, ref)
     if m > 1:
         assert len(set(got.tolist())) == min(m, N - 1) or m == N     # distinct picks until only duplicates remain
+
+
+@pytest.mark.parametrize("N,K,kind", [(10_000, 8000, "random"), (10_000, 5000, "ties"), (300, 8192, "random"), (1, 1, "random"),
+                                      (1_000_000, 8192, "random"), (50_000, 4096, "allequal"), (70_000, 100, "nan"),
+                                      (4097, 4096, "ties"), (20_000, 7, "signed_zero")])
+def test_device_topk_scores_matches_oracle_order(engine, N, K, kind):
+    """bo_topk_scores vs the oracle's (value desc, index asc, NaN last) order, incl. massive ties at the threshold."""
+    rng = np.random.default_rng(N + K)
+    s = rng.standard_normal(N)
+    if kind == "ties":
+        s = np.round(s * 4) / 4                                   # ~30 distinct values: the threshold bucket holds thousands of ties
+    elif kind == "allequal":
+        s[:] = 1e-3                                               # e.g. every variance clamped at min_variance
+    elif kind == "nan":
+        s[rng.integers(0, N, N // 2)] = np.nan
+        s[:50] = -np.inf
+    elif kind == "signed_zero":
+        s = np.where(rng.random(N) < 0.5, 0.0, -0.0) * 1.0
+        s[100] = 1.0
+    vals, idx = engine.topk_scores(_cuda(s), K, first_index=123)
+    tv, ti = o.topk(s, K, first_index=123)
+    vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
+    m = len(ti)
+    assert np.array_equal(idx[:m], ti)
+    assert np.array_equal(vals[:m], tv)
+    assert np.all(idx[m:] == -1) and np.all(np.isneginf(vals[m:]))
