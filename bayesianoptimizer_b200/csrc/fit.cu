@@ -32,38 +32,63 @@ __global__ void stage_inputs_kernel(const double* __restrict__ X, const double* 
 // ------------------------------------------------------------------------------------------
 // K1: Gram builder, lower triangle of K = k(X,X) + (noise + jitter) I, identity on the padding
 // ------------------------------------------------------------------------------------------
-template <int DP>
-__device__ __forceinline__ void gram_body(const double* __restrict__ Xs, int n, int np, int ld,
-                                          const Hyper& hyp, double* __restrict__ K) {
-    // block = 32 (cols) x 8 (rows) threads, tile 32 x 32
-    const int j = blockIdx.x * 32 + threadIdx.x;
-    const int i0 = blockIdx.y * 32;
-    if (blockIdx.x > blockIdx.y) return;
-    double xj[DP];
+// CTA tile: GRAM_ROWS rows x 32 columns (lane = column, warp = 16 consecutive rows, processed 4 at a time with
+// straight-line code so that the sqrt/exp chains of independent pairs interleave); the kernel kind is resolved once
+// outside the loops.  Only tiles that touch the lower triangle do work.
+constexpr int GRAM_ROWS = 128;
+
+template <int DP, int KIND>
+__device__ __forceinline__ void gram_rows(const double (*xs_i)[DP], const double* xj, int i0, int j, int n, int ld,
+                                          const Hyper& hyp, double* __restrict__ K, int warp) {
+    double xw[KIND == BO_KERNEL_LINEAR_MATERN52 ? DP : 1];
+    if (KIND == BO_KERNEL_LINEAR_MATERN52) {
 #pragma unroll
-    for (int k = 0; k < DP; ++k) xj[k] = Xs[(size_t)j * BO_MAX_DIM + k];
-    const bool lin_kind = hyp.kind == BO_KERNEL_LINEAR_MATERN52;
+        for (int k = 0; k < DP; ++k) xw[k] = hyp.lin_w[k] * xj[k];
+    }
+    for (int rb = 0; rb < 16; rb += 4) {
+        double v[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = i0 + threadIdx.y + r * 8;
-        double v;
-        if (i >= n || j >= n) {
-            v = (i == j) ? 1.0 : 0.0;
-        } else {
+        for (int u = 0; u < 4; ++u) {
+            const int r = warp * 16 + rb + u;
             double sq = 0.0, lin = 0.0;
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                const double xi = Xs[(size_t)i * BO_MAX_DIM + k];
+                const double xi = xs_i[r][k];
                 const double df = xi - xj[k];
                 sq = fma(df, df, sq);
-                lin = fma(hyp.lin_w[k] * xi, xj[k], lin);
+                if (KIND == BO_KERNEL_LINEAR_MATERN52) lin = fma(xw[k], xi, lin);
             }
-            if (i == j) v = hyp.outputscale * (lin_kind ? lin + 1.0 : 1.0) + hyp.noise + hyp.jitter;   // exact diagonal
-            else v = lin_kind ? fma(hyp.outputscale, lin, kernel_value(hyp.kind, sq, hyp.outputscale))
-                              : kernel_value(hyp.kind, sq, hyp.outputscale);
+            const int i = i0 + r;
+            const double off = kernel_pair_t<KIND>(sq, lin, hyp.outputscale);
+            const double dg = hyp.outputscale * (KIND == BO_KERNEL_LINEAR_MATERN52 ? lin + 1.0 : 1.0) + hyp.noise + hyp.jitter;   // exact diagonal
+            const double inside = (i == j) ? dg : off;
+            v[u] = (i >= n || j >= n) ? ((i == j) ? 1.0 : 0.0) : inside;
         }
-        if (j <= i) K[(size_t)i * ld + j] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + warp * 16 + rb + u;
+            if (j <= i) K[(size_t)i * ld + j] = v[u];
+        }
     }
+}
+
+template <int DP>
+__device__ __forceinline__ void gram_body(const double* __restrict__ Xs, int n, int np, int ld,
+                                          const Hyper& hyp, double* __restrict__ K) {
+    // block = 32 (cols) x 8 (warps) threads, tile GRAM_ROWS x 32
+    __shared__ double xs_i[GRAM_ROWS][DP];
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    if (bj * 32 > bi * GRAM_ROWS + GRAM_ROWS - 1) return;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int i0 = bi * GRAM_ROWS, j = bj * 32 + threadIdx.x;
+    for (int e = tid; e < GRAM_ROWS * DP; e += 256) xs_i[e / DP][e % DP] = Xs[(size_t)(i0 + e / DP) * BO_MAX_DIM + e % DP];
+    double xj[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xj[k] = Xs[(size_t)j * BO_MAX_DIM + k];
+    __syncthreads();
+    if (hyp.kind == BO_KERNEL_MATERN52) gram_rows<DP, BO_KERNEL_MATERN52>(xs_i, xj, i0, j, n, ld, hyp, K, threadIdx.y);
+    else if (hyp.kind == BO_KERNEL_RBF) gram_rows<DP, BO_KERNEL_RBF>(xs_i, xj, i0, j, n, ld, hyp, K, threadIdx.y);
+    else gram_rows<DP, BO_KERNEL_LINEAR_MATERN52>(xs_i, xj, i0, j, n, ld, hyp, K, threadIdx.y);
 }
 
 template <int DP>
@@ -493,7 +518,7 @@ int ensure_capacity(bo_handle* h, int np, cudaStream_t st) {
 
 template <int DP>
 static int launch_gram(bo_handle* h, cudaStream_t st) {
-    dim3 grid(h->np / 32, h->np / 32), block(32, 8);
+    dim3 grid(h->np / 32, h->np / GRAM_ROWS), block(32, 8);
     gram_kernel<DP><<<grid, block, 0, st>>>(h->Xs, h->n, h->np, h->cap_np, h->hyp, h->Lm);
     BO_LAUNCH_CHECK(h);
     return 0;

@@ -43,60 +43,42 @@ static void lml_batch_free(LmlBatch* b) {
 }
 void lml_release(bo_handle* h) { lml_batch_free(static_cast<LmlBatch*>(h->lml_batch)); h->lml_batch = nullptr; }
 
-// per 32x32 tile of the lower triangle: partial sums of W_ij dK_ij/dlog l_k (k < DP), W_ij K_ij, and on the
-// diagonal W_ii, log L_ii, r_i alpha_i.  blockIdx.z = slot.
-template <int DP>
-__global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __restrict__ Xs_all, const double* __restrict__ alpha_all,
-                                                            const double* __restrict__ Kinv_all, const double* __restrict__ Lm_all,
-                                                            const double* __restrict__ yv, int ld, int n, int np,
-                                                            const Hyper* __restrict__ hyps, double* __restrict__ part_all) {
-    __shared__ double red[8];
-    const size_t s = blockIdx.z;
-    const Hyper& hyp = hyps[s];
-    const double* Xs = Xs_all + s * np * BO_MAX_DIM;
-    const double* alpha = alpha_all + s * np;
-    const double* Kinv = Kinv_all + s * np * ld;
-    const double* Lm = Lm_all + s * np * ld;
-    const int bj = blockIdx.x, bi = blockIdx.y;
-    const int tile = bi * gridDim.x + bj;
-    double* part = part_all + (s * gridDim.x * gridDim.y + tile) * (DP + 6);
-    double acc[DP + 6];
+// per GRAM_ROWS x 32 tile of the lower triangle: partial sums of W_ij dK_ij/dlog l_k (k < DP), W_ij K_ij, and on the
+// diagonal W_ii, log L_ii, r_i alpha_i.  blockIdx.z = slot.  Lane = column j, warp = 16 consecutive rows processed four
+// at a time with branch-free code (masked pairs carry w = 0), kernel kind resolved outside the loops, the tile's rows of
+// X~ / alpha staged in shared memory, one barrier for the whole reduction.
+template <int DP, int KIND>
+__device__ __forceinline__ void lml_pair_rows(const double (*xs_i)[DP], const double* al_i, const double* xj, double aj, int i0,
+                                              int j, int n, int ld, const Hyper& hyp, const double* __restrict__ Kinv, int warp,
+                                              double* acc) {
+    double xw[KIND == BO_KERNEL_LINEAR_MATERN52 ? DP : 1];
+    if (KIND == BO_KERNEL_LINEAR_MATERN52) {
 #pragma unroll
-    for (int k = 0; k < DP + 6; ++k) acc[k] = 0.0;
-    if (bj <= bi) {
-        const int j = bj * 32 + (threadIdx.x & 31);
-        double xj[DP];
+        for (int k = 0; k < DP; ++k) xw[k] = hyp.lin_w[k] * xj[k];
+    }
+    const double s5 = 2.23606797749978969640917366873128;
+    for (int rb = 0; rb < 16; rb += 4) {
 #pragma unroll
-        for (int k = 0; k < DP; ++k) xj[k] = (j < n) ? Xs[(size_t)j * BO_MAX_DIM + k] : 0.0;
-        const double aj = (j < n) ? alpha[j] : 0.0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int i = bi * 32 + (threadIdx.x >> 5) + r * 8;
-            if (i >= n || j >= n || j > i) continue;
-            const double w = alpha[i] * aj - Kinv[(size_t)i * ld + j];
+        for (int u = 0; u < 4; ++u) {
+            const int r = warp * 16 + rb + u, i = i0 + r;
+            const bool valid = i < n && j < i;                        // strict lower triangle inside the data (j < i < n)
+            const double kin = Kinv[(size_t)i * ld + j];
+            const double w = valid ? fma(al_i[r], aj, -kin) : 0.0;
             double sq = 0.0, lin = 0.0, df2[DP];
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                const double xi = Xs[(size_t)i * BO_MAX_DIM + k];
+                const double xi = xs_i[r][k];
                 const double df = xi - xj[k];
                 df2[k] = df * df;
                 sq += df2[k];
-                lin = fma(hyp.lin_w[k] * xi, xj[k], lin);
-            }
-            const double klin = hyp.outputscale * lin;              // s2 v <x_i, x_j>  (0 for the stationary kinds)
-            if (i == j) {
-                acc[DP + 1] += w;                                   // trace(W)
-                acc[DP + 2] += log(Lm[(size_t)i * ld + i]);         // log det / 2
-                acc[DP + 3] += (yv[i] - hyp.mean) * alpha[i];       // quadratic form
-                acc[DP + 5] = fma(w, klin, acc[DP + 5]);            // sum_i W_ii s2 v |x_i|^2
-                continue;
+                if (KIND == BO_KERNEL_LINEAR_MATERN52) lin = fma(xw[k], xi, lin);
             }
             double kval, G;
-            if (hyp.kind != BO_KERNEL_RBF) {
-                const double s5 = 2.23606797749978969640917366873128;
+            if (KIND != BO_KERNEL_RBF) {
                 const double rr = sqrt_pos(sq), e = exp_neg(s5 * rr);
-                kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, rr, 1.0)) * e;
-                G = hyp.outputscale * (5.0 / 3.0) * fma(s5, rr, 1.0) * e;
+                const double t = fma(s5, rr, 1.0);
+                kval = hyp.outputscale * fma(sq, 5.0 / 3.0, t) * e;
+                G = hyp.outputscale * (5.0 / 3.0) * t * e;
             } else {
                 kval = hyp.outputscale * exp_neg(0.5 * sq);
                 G = kval;
@@ -104,8 +86,61 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __rest
             const double wg = w * G;
 #pragma unroll
             for (int k = 0; k < DP; ++k) acc[k] = fma(wg, df2[k], acc[k]);
-            acc[DP] = fma(w, kval + klin, acc[DP]);
-            acc[DP + 4] = fma(w, klin, acc[DP + 4]);                // sum_{i>j} W_ij s2 v <x_i, x_j>
+            if (KIND == BO_KERNEL_LINEAR_MATERN52) {
+                const double klin = hyp.outputscale * lin;            // s2 v <x_i, x_j>
+                acc[DP] = fma(w, kval + klin, acc[DP]);
+                acc[DP + 4] = fma(w, klin, acc[DP + 4]);              // sum_{i>j} W_ij s2 v <x_i, x_j>
+            } else {
+                acc[DP] = fma(w, kval, acc[DP]);
+            }
+        }
+    }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __restrict__ Xs_all, const double* __restrict__ alpha_all,
+                                                            const double* __restrict__ Kinv_all, const double* __restrict__ Lm_all,
+                                                            const double* __restrict__ yv, int ld, int n, int np,
+                                                            const Hyper* __restrict__ hyps, double* __restrict__ part_all) {
+    __shared__ double xs_i[GRAM_ROWS][DP];
+    __shared__ double al_i[GRAM_ROWS];
+    __shared__ double red[8][DP + 6];
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    if (bj * 32 > bi * GRAM_ROWS + GRAM_ROWS - 1) return;             // tile entirely above the diagonal
+    const size_t s = blockIdx.z;
+    const Hyper& hyp = hyps[s];
+    const double* Xs = Xs_all + s * np * BO_MAX_DIM;
+    const double* alpha = alpha_all + s * np;
+    const double* Kinv = Kinv_all + s * np * ld;
+    const double* Lm = Lm_all + s * np * ld;
+    const int tile = bi * gridDim.x + bj;
+    double* part = part_all + (s * gridDim.x * gridDim.y + tile) * (DP + 6);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = bi * GRAM_ROWS, j = bj * 32 + lane;
+    for (int e = tid; e < GRAM_ROWS * DP; e += 256) xs_i[e / DP][e % DP] = Xs[(size_t)(i0 + e / DP) * BO_MAX_DIM + e % DP];
+    if (tid < GRAM_ROWS) al_i[tid] = alpha[i0 + tid];
+    double xj[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xj[k] = Xs[(size_t)j * BO_MAX_DIM + k];           // padded rows of X~ are zero
+    const double aj = alpha[j];
+    __syncthreads();
+    double acc[DP + 6];
+#pragma unroll
+    for (int k = 0; k < DP + 6; ++k) acc[k] = 0.0;
+    if (hyp.kind == BO_KERNEL_MATERN52) lml_pair_rows<DP, BO_KERNEL_MATERN52>(xs_i, al_i, xj, aj, i0, j, n, ld, hyp, Kinv, warp, acc);
+    else if (hyp.kind == BO_KERNEL_RBF) lml_pair_rows<DP, BO_KERNEL_RBF>(xs_i, al_i, xj, aj, i0, j, n, ld, hyp, Kinv, warp, acc);
+    else lml_pair_rows<DP, BO_KERNEL_LINEAR_MATERN52>(xs_i, al_i, xj, aj, i0, j, n, ld, hyp, Kinv, warp, acc);
+    // diagonal entries of this tile (columns that are also rows of the tile): one warp, lane = its own (j, j)
+    if (warp == 0 && j >= i0 && j < i0 + GRAM_ROWS && j < n) {
+        const double w = fma(aj, aj, -Kinv[(size_t)j * ld + j]);
+        acc[DP + 1] += w;                                   // trace(W)
+        acc[DP + 2] += log(Lm[(size_t)j * ld + j]);         // log det / 2
+        acc[DP + 3] += (yv[j] - hyp.mean) * aj;             // quadratic form
+        if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+            double nn = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) nn = fma(hyp.lin_w[k] * xj[k], xj[k], nn);
+            acc[DP + 5] = fma(w, hyp.outputscale * nn, acc[DP + 5]);            // sum_i W_ii s2 v |x_i|^2
         }
     }
 #pragma unroll
@@ -113,21 +148,20 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __rest
         double v = acc[k];
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < DP + 6) {
+        double t = 0.0;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) t += red[w8];
-            part[k] = t;
-        }
+        for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
+        part[tid] = t;
     }
 }
 
 // deterministic final reduction: one block per slot sums the tile partials column by column
 template <int DP>
-__global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restrict__ part_all, int tiles, int n, int d,
+__global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restrict__ part_all, int tiles, int ntx, int n, int d,
                                                          const Hyper* __restrict__ hyps, double* __restrict__ out_all) {
     __shared__ double red[8];
     __shared__ double tot[DP + 6];
@@ -137,7 +171,8 @@ __global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restric
     double* out = out_all + s * (BO_MAX_DIM + 4);
     for (int k = 0; k < DP + 6; ++k) {
         double v = 0.0;
-        for (int t = threadIdx.x; t < tiles; t += 256) v += part[(size_t)t * (DP + 6) + k];
+        for (int t = threadIdx.x; t < tiles; t += 256)
+            if ((t % ntx) * 32 <= (t / ntx) * GRAM_ROWS + GRAM_ROWS - 1) v += part[(size_t)t * (DP + 6) + k];     // tiles that ran
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         __syncthreads();
@@ -163,20 +198,20 @@ __global__ void __launch_bounds__(256) lml_reduce_kernel(const double* __restric
 template <int DP>
 static int lml_launch_gram(bo_handle* h, LmlBatch* b, int s0, int S, cudaStream_t st) {
     const size_t c = b->np;
-    gram_batched_kernel<DP><<<dim3(b->np / 32, b->np / 32, S), dim3(32, 8), 0, st>>>(b->Xs + s0 * c * BO_MAX_DIM, b->n, b->np, b->np,
+    gram_batched_kernel<DP><<<dim3(b->np / 32, b->np / GRAM_ROWS, S), dim3(32, 8), 0, st>>>(b->Xs + s0 * c * BO_MAX_DIM, b->n, b->np, b->np,
                                                                                     b->hyps + s0, b->Lm + s0 * c * c);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
 template <int DP>
 static int lml_launch_grad(bo_handle* h, LmlBatch* b, int s0, int S, cudaStream_t st) {
-    const int nt = b->np / 32;
+    const int nt = b->np / 32, nty = b->np / GRAM_ROWS;
     const size_t c = b->np;
-    double* gpart = b->gpart + (size_t)s0 * nt * nt * (DP + 6);
-    lml_grad_tile_kernel<DP><<<dim3(nt, nt, S), 256, 0, st>>>(b->Xs + s0 * c * BO_MAX_DIM, b->alpha + s0 * c, b->Kw + s0 * c * c,
+    double* gpart = b->gpart + (size_t)s0 * nt * nty * (DP + 6);
+    lml_grad_tile_kernel<DP><<<dim3(nt, nty, S), 256, 0, st>>>(b->Xs + s0 * c * BO_MAX_DIM, b->alpha + s0 * c, b->Kw + s0 * c * c,
                                                               b->Lm + s0 * c * c, b->yv, b->np, b->n, b->np, b->hyps + s0, gpart);
     BO_LAUNCH_CHECK(h);
-    lml_reduce_kernel<DP><<<S, 256, 0, st>>>(gpart, nt * nt, b->n, b->d, b->hyps + s0, b->out + (size_t)s0 * (BO_MAX_DIM + 4));
+    lml_reduce_kernel<DP><<<S, 256, 0, st>>>(gpart, nt * nty, nt, b->n, b->d, b->hyps + s0, b->out + (size_t)s0 * (BO_MAX_DIM + 4));
     BO_LAUNCH_CHECK(h);
     return 0;
 }
