@@ -400,6 +400,28 @@ static int pick_tile(int sm, std::initializer_list<int> dims, long tiles128) {
     return 64;
 }
 
+// Trailing update after the panel of block column kb in the TWO-LEVEL right-looking scheme: block columns are grouped
+// into outer blocks of OB; inside an outer block a panel only updates the remaining columns of that block (K = NB,
+// narrow), and the last panel of the block applies all OB panels to the rest of the matrix at once (K = OB * NB).
+// The K = 64 updates stream C through L2 once per 64 columns (4 flop/B, 20 TFLOP/s); K = 256 quarters that traffic.
+static int chol_outer_blocks() {
+    static int ob = [] { const char* e = getenv("BO_B200_CHOL_OB"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();
+    return ob;
+}
+static void add_trailing_update(GemmBatch& g, double* Lm, int ld, int np, int kb, int nb) {
+    const int OB = chol_outer_blocks();
+    const int ob0 = (kb / OB) * OB, oend = std::min(ob0 + OB, nb);
+    const int r0 = (kb + 1) * NB;
+    double* C = Lm + (size_t)r0 * ld + r0;
+    if (kb + 1 < oend) {
+        double* P = Lm + (size_t)r0 * ld + kb * NB;                  // panel kb below its diagonal block
+        g.add(P, ld, P, ld, C, ld, np - r0, oend * NB - r0, NB, -1.0, 1.0, /*transB=*/1, GEMM_LOWER_C);
+    } else if (r0 < np) {
+        double* P = Lm + (size_t)r0 * ld + ob0 * NB;                 // panels ob0 .. kb side by side
+        g.add(P, ld, P, ld, C, ld, np - r0, np - r0, (kb + 1 - ob0) * NB, -1.0, 1.0, /*transB=*/1, GEMM_LOWER_C);
+    }
+}
+
 // Build the launch plan of the factorisation (one SYRK launch per block column; the panel kernel does the
 // diagonal block + triangular solve) followed by the recursive inverse (2 launches per level).
 //   plan_launches[kb] = SYRK trailing update of block column kb      (kb = 0 .. nb-2)
@@ -409,12 +431,10 @@ static int build_plan(bo_handle* h, cudaStream_t st) {
     h->plan_probs.clear();
     h->plan_launches.clear();
     for (int kb = 0; kb + 1 < nb; ++kb) {
-        const int r0 = (kb + 1) * NB, m = np - r0;
-        double* P = h->Lm + (size_t)r0 * ld + kb * NB;                 // panel below the diagonal block
-        double* C = h->Lm + (size_t)r0 * ld + r0;
+        const int m = np - (kb + 1) * NB;
         long t128 = (long)(m / 128) * (m / 128 + 1) / 2;
         GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
-        syrk.add(P, ld, P, ld, C, ld, m, m, NB, -1.0, 1.0, /*transB=*/1, GEMM_LOWER_C);
+        add_trailing_update(syrk, h->Lm, ld, np, kb, nb);
         plan_push(h, syrk);
     }
     // recursive inverse: collect merge nodes by depth

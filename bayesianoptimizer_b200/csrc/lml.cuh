@@ -264,11 +264,7 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
         const int r0 = (kb + 1) * NB, m = np - r0;
         long t128 = (long)(m / 128) * (m / 128 + 1) / 2 * S;
         GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
-        for (int s = 0; s < S; ++s) {
-            double* Lm = b->Lm + (size_t)s * mat;
-            double* P = Lm + (size_t)r0 * ld + kb * NB;
-            syrk.add(P, ld, P, ld, Lm + (size_t)r0 * ld + r0, ld, m, m, NB, -1.0, 1.0, 1, GEMM_LOWER_C);
-        }
+        for (int s = 0; s < S; ++s) add_trailing_update(syrk, b->Lm + (size_t)s * mat, ld, np, kb, nb);
         plan_push(syrk);
     }
     struct Node { int lo, mid, hi, depth; };
