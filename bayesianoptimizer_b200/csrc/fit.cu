@@ -369,6 +369,9 @@ __global__ void export_lower_kernel(const double* __restrict__ src, int ld, int 
 int gemm_init(bo_handle* h) {
     BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)GemmSmem<64, 64>::BYTES));
+    // production shape: 64x64 tiles, 2-stage ring, 4 CTAs/SM (64 registers) -- best at every K in tools/gemm_probe.py
+    BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64, 16, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)GemmSmem<64, 64, 16, 2>::BYTES));
     BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)GemmSmem<128, 128>::BYTES));
     BO_CUDA(h, cudaFuncSetAttribute(dgemm_grouped_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -381,7 +384,7 @@ int gemm_launch(bo_handle* h, const GemmLaunch& L, cudaStream_t st) {
     if (L.cfg == 1)
         dgemm_grouped_kernel<128, 128><<<L.tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(h->plan_dev + L.first, L.count);
     else
-        dgemm_grouped_kernel<64, 64><<<L.tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(h->plan_dev + L.first, L.count);
+        dgemm_grouped_kernel<64, 64, 16, 2, 4><<<L.tiles, 256, GemmSmem<64, 64, 16, 2>::BYTES, st>>>(h->plan_dev + L.first, L.count);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
@@ -394,8 +397,8 @@ static void plan_push(bo_handle* h, const GemmBatch& b) {
 
 // pick the tile: 128 when every dimension allows it and the launch still fills the GPU
 static int pick_tile(int sm, std::initializer_list<int> dims, long tiles128) {
-    // measured with bo_gemm_probe on B200 (tools/gemm_probe.py): 64x64 tiles (3 CTAs/SM hide the prologue and
-    // the C read-modify-write) beat 128x128 and 128x64 at every K from 64 to 4096 -> always 64
+    // measured with bo_gemm_probe on B200 (tools/gemm_probe.py): 64x64 tiles (4 CTAs/SM with the 2-stage ring hide the
+    // prologue and the C read-modify-write) beat 128x128 and 128x64 at every K from 64 to 4096 -> always 64
     (void)sm; (void)dims; (void)tiles128;
     return 64;
 }
@@ -738,8 +741,14 @@ int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, co
 // GEMM throughput probe (development / roofline evidence for the fit's trailing updates): C = A * B^T, square tiles
 int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops) {
     BO_CUDA(h, cudaSetDevice(h->device));
-    const int bm = cfg == 0 ? 64 : 128, bn = cfg == 1 ? 128 : 64;
-    if (m % bm || n % bn || k % 16 || m < bm || n < bn || k < 16) return fail(h, BO_E_INVALID, "bo_gemm_probe: sizes must be tile multiples");
+    const int bm = (cfg == 1 || cfg == 2 || cfg == 6) ? 128 : 64, bn = (cfg == 1 || cfg == 6) ? 128 : 64;
+    {   // probe-only variants opt in here
+        cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64, 16, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64, 64, 16, 2>::BYTES);
+        cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64, 32, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64, 64, 32, 2>::BYTES);
+        cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64, 32, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64, 64, 32, 3>::BYTES);
+        cudaFuncSetAttribute(dgemm_grouped_kernel<128, 128, 32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<128, 128, 32, 2>::BYTES);
+    }
+    if (m % bm || n % bn || k % 32 || m < bm || n < bn || k < 16) return fail(h, BO_E_INVALID, "bo_gemm_probe: sizes must be tile multiples");
     double *A, *B, *C; GemmProblem* pd;
     BO_CUDA(h, cudaMalloc(&A, (size_t)m * k * 8)); BO_CUDA(h, cudaMalloc(&B, (size_t)n * k * 8)); BO_CUDA(h, cudaMalloc(&C, (size_t)m * n * 8));
     BO_CUDA(h, cudaMalloc(&pd, sizeof(GemmProblem)));
@@ -750,6 +759,10 @@ int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double
     auto launch = [&]() {
         if (cfg == 1) dgemm_grouped_kernel<128, 128><<<p.tile_end, 256, GemmSmem<128, 128>::BYTES>>>(pd, 1);
         else if (cfg == 2) dgemm_grouped_kernel<128, 64><<<p.tile_end, 256, GemmSmem<128, 64>::BYTES>>>(pd, 1);
+        else if (cfg == 3) dgemm_grouped_kernel<64, 64, 16, 2, 4><<<p.tile_end, 256, GemmSmem<64, 64, 16, 2>::BYTES>>>(pd, 1);
+        else if (cfg == 4) dgemm_grouped_kernel<64, 64, 32, 2, 3><<<p.tile_end, 256, GemmSmem<64, 64, 32, 2>::BYTES>>>(pd, 1);
+        else if (cfg == 5) dgemm_grouped_kernel<64, 64, 32, 3, 2><<<p.tile_end, 256, GemmSmem<64, 64, 32, 3>::BYTES>>>(pd, 1);
+        else if (cfg == 6) dgemm_grouped_kernel<128, 128, 32, 2, 1><<<p.tile_end, 256, GemmSmem<128, 128, 32, 2>::BYTES>>>(pd, 1);
         else dgemm_grouped_kernel<64, 64><<<p.tile_end, 256, GemmSmem<64, 64>::BYTES>>>(pd, 1);
         h->launches++;
     };

@@ -16,26 +16,25 @@ enum : int {
     GEMM_K_FROM_MAX = 32,  // both operands vanish for k < max(tile_m * BM, tile_n * BN) (L^-T L^-1 products)
 };
 
-constexpr int GEMM_BK = 16;
-constexpr int GEMM_STAGES = 3;
-constexpr int GEMM_LDK = GEMM_BK + 4;     // [row][k] layout stride (conflict-free DMMA fragment reads)
-
-template <int BM, int BN>
+// Tile shape BM x BN, contraction chunk BK per stage, STAGES-deep cp.async ring, MINB resident CTAs per SM requested.
+template <int BM, int BN, int BK = 16, int STAGES = 3>
 struct GemmSmem {
-    static constexpr int A_N = BM * GEMM_LDK;
-    static constexpr int A_T = GEMM_BK * (BM + 4);
+    static constexpr int LDK = BK + 4;        // [row][k] layout stride (conflict-free DMMA fragment reads)
+    static constexpr int A_N = BM * LDK;
+    static constexpr int A_T = BK * (BM + 4);
     static constexpr int A_ELEMS = A_N > A_T ? A_N : A_T;
-    static constexpr int B_NT = BN * GEMM_LDK;
-    static constexpr int B_NN = GEMM_BK * (BN + 4);
+    static constexpr int B_NT = BN * LDK;
+    static constexpr int B_NN = BK * (BN + 4);
     static constexpr int B_ELEMS = B_NT > B_NN ? B_NT : B_NN;
     static constexpr int STAGE = A_ELEMS + B_ELEMS;
-    static constexpr size_t BYTES = (size_t)GEMM_STAGES * STAGE * sizeof(double);
+    static constexpr size_t BYTES = (size_t)STAGES * STAGE * sizeof(double);
 };
 
-template <int BM, int BN>
-__global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* __restrict__ probs, int nprob, int tile0 = 0) {
+template <int BM, int BN, int BK = 16, int STAGES = 3, int MINB = (BM * BN <= 4096 ? 3 : 1)>
+__global__ void __launch_bounds__(256, MINB) dgemm_grouped_kernel(const GemmProblem* __restrict__ probs, int nprob, int tile0 = 0) {
     extern __shared__ __align__(16) double gsm[];
-    using SM = GemmSmem<BM, BN>;
+    using SM = GemmSmem<BM, BN, BK, STAGES>;
+    constexpr int LDK = SM::LDK;
     constexpr int WM = BM / 2, WN = BN / 4;      // 8 warps as 2 (M) x 4 (N)
     constexpr int MT = WM / 8, NT = WN / 8;
 
@@ -54,44 +53,61 @@ __global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* _
     if (P.mode & GEMM_B_LOWER_NT) k_end = min(k_end, (tn + 1) * BN);
     if (P.mode & GEMM_K_FROM_MAX) k_begin = max(k_begin, max(tm * BM, tn * BN));
     const bool transA = (P.mode & GEMM_TRANS_A) != 0;
-    const int nk = (k_end - k_begin) / GEMM_BK;
+    const int nk = (k_end - k_begin) / BK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, q = lane & 3;
 
-    const double* Ag = transA ? P.A + tm * BM : P.A + (size_t)(tm * BM) * P.lda;
-    const double* Bg = P.transB ? P.B + (size_t)(tn * BN) * P.ldb : P.B + tn * BN;
+    // per-thread copy assignment, fixed over the k loop: [row][k] operands move BK/2 16-byte chunks per row,
+    // [k][col] operands BM/2 (BN/2) chunks per k row; only the k offset advances
+    constexpr int CK = BK / 2;                       // chunks per row, [row][k] form
+    constexpr int RS = 256 / CK;                     // rows covered per pass
+    const double* a_src; int a_dst; size_t a_step;   // source, smem offset, source step per pass
+    const double* b_src; int b_dst; size_t b_step;
+    if (transA) {
+        const int mq = tid % (BM / 2), kr = tid / (BM / 2);
+        a_src = P.A + tm * BM + (size_t)(k_begin + kr) * P.lda + mq * 2;
+        a_dst = kr * (BM + 4) + mq * 2;
+        a_step = (size_t)(256 / (BM / 2)) * P.lda;
+    } else {
+        const int row = tid / CK, kq = tid % CK;
+        a_src = P.A + (size_t)(tm * BM + row) * P.lda + k_begin + kq * 2;
+        a_dst = row * LDK + kq * 2;
+        a_step = (size_t)RS * P.lda;
+    }
+    if (P.transB) {
+        const int row = tid / CK, kq = tid % CK;
+        b_src = P.B + (size_t)(tn * BN + row) * P.ldb + k_begin + kq * 2;
+        b_dst = row * LDK + kq * 2;
+        b_step = (size_t)RS * P.ldb;
+    } else {
+        const int nq = tid % (BN / 2), kr = tid / (BN / 2);
+        b_src = P.B + tn * BN + (size_t)(k_begin + kr) * P.ldb + nq * 2;
+        b_dst = kr * (BN + 4) + nq * 2;
+        b_step = (size_t)(256 / (BN / 2)) * P.ldb;
+    }
+    const size_t a_kadv = transA ? (size_t)BK * P.lda : (size_t)BK;       // source advance per k tile
+    const size_t b_kadv = P.transB ? (size_t)BK : (size_t)BK * P.ldb;
 
     auto load_stage = [&](int s, int kt) {
         double* As = gsm + s * SM::STAGE;
         double* Bs = As + SM::A_ELEMS;
-        const int k0 = k_begin + kt * GEMM_BK;
+        const double* ap = a_src + (size_t)kt * a_kadv;
+        const double* bp = b_src + (size_t)kt * b_kadv;
         if (transA) {
 #pragma unroll
-            for (int c = tid; c < GEMM_BK * (BM / 2); c += 256) {
-                int kr = c / (BM / 2), mq = c % (BM / 2);
-                cp_async16(As + kr * (BM + 4) + mq * 2, Ag + (size_t)(k0 + kr) * P.lda + mq * 2);
-            }
+            for (int it = 0; it < BK * (BM / 2) / 256; ++it) cp_async16(As + a_dst + it * (256 / (BM / 2)) * (BM + 4), ap + it * a_step);
         } else {
 #pragma unroll
-            for (int c = tid; c < BM * (GEMM_BK / 2); c += 256) {
-                int row = c >> 3, kq = c & 7;
-                cp_async16(As + row * GEMM_LDK + kq * 2, Ag + (size_t)row * P.lda + k0 + kq * 2);
-            }
+            for (int it = 0; it < BM * CK / 256; ++it) cp_async16(As + a_dst + it * RS * LDK, ap + it * a_step);
         }
         if (P.transB) {
 #pragma unroll
-            for (int c = tid; c < BN * (GEMM_BK / 2); c += 256) {
-                int row = c >> 3, kq = c & 7;
-                cp_async16(Bs + row * GEMM_LDK + kq * 2, Bg + (size_t)row * P.ldb + k0 + kq * 2);
-            }
+            for (int it = 0; it < BN * CK / 256; ++it) cp_async16(Bs + b_dst + it * RS * LDK, bp + it * b_step);
         } else {
 #pragma unroll
-            for (int c = tid; c < GEMM_BK * (BN / 2); c += 256) {
-                int kr = c / (BN / 2), nq = c % (BN / 2);
-                cp_async16(Bs + kr * (BN + 4) + nq * 2, Bg + (size_t)(k0 + kr) * P.ldb + nq * 2);
-            }
+            for (int it = 0; it < BK * (BN / 2) / 256; ++it) cp_async16(Bs + b_dst + it * (256 / (BN / 2)) * (BN + 4), bp + it * b_step);
         }
     };
 
@@ -102,37 +118,32 @@ __global__ void __launch_bounds__(256) dgemm_grouped_kernel(const GemmProblem* _
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) load_stage(s, s);
         cp_async_commit();
     }
+    // fragment read offsets (fixed over the k loop)
+    const int a_frag = transA ? q * (BM + 4) + wm * WM + g : (wm * WM + g) * LDK + q;
+    const int b_frag = P.transB ? (wn * WN + g) * LDK + q : q * (BN + 4) + wn * WN + g;
+    const int a_i = transA ? 8 : 8 * LDK, a_k = transA ? 4 * (BM + 4) : 4;      // steps per 8-row group / per k4 step
+    const int b_j = P.transB ? 8 * LDK : 8, b_k = P.transB ? 4 : 4 * (BN + 4);
     for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<GEMM_STAGES - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
         {   // prefetch tile kt + STAGES - 1 into the slot consumed at iteration kt - 1
-            int nx = kt + GEMM_STAGES - 1;
-            if (nx < nk) load_stage(nx % GEMM_STAGES, nx);
+            int nx = kt + STAGES - 1;
+            if (nx < nk) load_stage(nx % STAGES, nx);
             cp_async_commit();
         }
-        const double* As = gsm + (kt % GEMM_STAGES) * SM::STAGE;
-        const double* Bs = As + SM::A_ELEMS;
+        const double* As = gsm + (kt % STAGES) * SM::STAGE + a_frag;
+        const double* Bs = gsm + (kt % STAGES) * SM::STAGE + SM::A_ELEMS + b_frag;
 #pragma unroll
-        for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
+        for (int kk = 0; kk < BK / 4; ++kk) {
             double a[MT], b[NT];
-            if (transA) {
 #pragma unroll
-                for (int i = 0; i < MT; ++i) a[i] = As[(kk * 4 + q) * (BM + 4) + wm * WM + i * 8 + g];
-            } else {
+            for (int i = 0; i < MT; ++i) a[i] = As[i * a_i + kk * a_k];
 #pragma unroll
-                for (int i = 0; i < MT; ++i) a[i] = As[(wm * WM + i * 8 + g) * GEMM_LDK + kk * 4 + q];
-            }
-            if (P.transB) {
-#pragma unroll
-                for (int j = 0; j < NT; ++j) b[j] = Bs[(wn * WN + j * 8 + g) * GEMM_LDK + kk * 4 + q];
-            } else {
-#pragma unroll
-                for (int j = 0; j < NT; ++j) b[j] = Bs[(kk * 4 + q) * (BN + 4) + wn * WN + j * 8 + g];
-            }
+            for (int j = 0; j < NT; ++j) b[j] = Bs[j * b_j + kk * b_k];
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll

@@ -325,7 +325,7 @@ static int lml_gemm(bo_handle* h, LmlBatch* b, int li, int s0, int S_active, cud
     const int count = per_slot * S_active, tiles = tiles_per_slot * S_active;
     const GemmProblem* pr = b->plan_dev + L.first + (size_t)per_slot * s0;
     if (L.cfg == 1) dgemm_grouped_kernel<128, 128><<<tiles, 256, GemmSmem<128, 128>::BYTES, st>>>(pr, count, tiles_per_slot * s0);
-    else dgemm_grouped_kernel<64, 64><<<tiles, 256, GemmSmem<64, 64>::BYTES, st>>>(pr, count, tiles_per_slot * s0);
+    else dgemm_grouped_kernel<64, 64, 16, 2, 4><<<tiles, 256, GemmSmem<64, 64, 16, 2>::BYTES, st>>>(pr, count, tiles_per_slot * s0);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
