@@ -98,7 +98,7 @@ __device__ __forceinline__ void lml_pair_rows(const double (*xs_i)[DP], const do
 }
 
 template <int DP>
-__global__ void __launch_bounds__(256) lml_grad_tile_kernel(const double* __restrict__ Xs_all, const double* __restrict__ alpha_all,
+__global__ void __launch_bounds__(256, 2) lml_grad_tile_kernel(const double* __restrict__ Xs_all, const double* __restrict__ alpha_all,
                                                             const double* __restrict__ Kinv_all, const double* __restrict__ Lm_all,
                                                             const double* __restrict__ yv, int ld, int n, int np,
                                                             const Hyper* __restrict__ hyps, double* __restrict__ part_all) {
