@@ -92,13 +92,13 @@ __device__ __forceinline__ void gram_body(const double* __restrict__ Xs, int n, 
 }
 
 template <int DP>
-__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xs, int n, int np, int ld,
+__global__ void __launch_bounds__(256, 3) gram_kernel(const double* __restrict__ Xs, int n, int np, int ld,
                                                    Hyper hyp, double* __restrict__ K) {
     gram_body<DP>(Xs, n, np, ld, hyp, K);
 }
 // per-slot variant for the batched LML restarts: blockIdx.z = slot, hyper-parameters from a device array
 template <int DP>
-__global__ void __launch_bounds__(256) gram_batched_kernel(const double* __restrict__ Xs, int n, int np, int ld,
+__global__ void __launch_bounds__(256, 3) gram_batched_kernel(const double* __restrict__ Xs, int n, int np, int ld,
                                                            const Hyper* __restrict__ hyps, double* __restrict__ K) {
     const size_t s = blockIdx.z;
     gram_body<DP>(Xs + s * np * BO_MAX_DIM, n, np, ld, hyps[s], K + s * np * ld);
