@@ -73,6 +73,9 @@ class BatchSVGPPredictor:
             self.engines.append(eng)
         f64 = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float64, device=self.device)
         self.bounds, self.x_log_mean, self.x_log_std = f64(bounds), f64(x_log_mean), f64(x_log_std)
+        # one stream per task: a 10^4-candidate pool is only 79 blocks of 128 -- less than one wave of the 148 SMs -- so the
+        # T task sweeps run concurrently and the block scheduler packs their CTAs onto the free SMs
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in self.engines] if self.device.type == "cuda" else None
 
     @property
     def num_tasks(self):
@@ -90,16 +93,34 @@ class BatchSVGPPredictor:
     def predict(self, x_unit, min_variance: float = MIN_VARIANCE):
         """``likelihood(model(x))``: (mean[T, N], variance[T, N]) as read at Bayesian7.py:558-560 / :668-670."""
         xs = self.transform_inputs(x_unit).contiguous()
-        out = [eng.posterior(xs, min_variance) for eng in self.engines]
+        out = self._per_task(lambda eng: eng.posterior(xs, min_variance))
         return torch.stack([o[0] for o in out]), torch.stack([o[1] for o in out])
+
+    def _per_task(self, fn):
+        """Run ``fn(engine)`` for every task, each on its own stream (forked from / joined to the current stream)."""
+        if not self._streams:
+            return [fn(eng) for eng in self.engines]
+        cur = torch.cuda.current_stream(self.device)
+        out = []
+        for eng, st in zip(self.engines, self._streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                out.append(fn(eng))
+        for st in self._streams:
+            cur.wait_stream(st)
+        for o in out:                                   # allocated on the side streams, consumed on the current one
+            for t in (o if isinstance(o, (tuple, list)) else (o,)):
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(cur)
+        return out
 
     def variance_score(self, x_unit, min_variance: float = MIN_VARIANCE):
         """Uncertainty score of the pool scan: ``pred.variance.sum(dim=0)`` (Bayesian7.py:670-671), on the device."""
         xs = self.transform_inputs(x_unit).contiguous()
-        score = None
-        for eng in self.engines:
-            _, _, _, var, _ = eng.sweep("var", candidates=xs, topk=0, min_variance=min_variance, return_all=True)
-            score = var if score is None else score.add_(var)
+        vars_ = self._per_task(lambda eng: eng.sweep("var", candidates=xs, topk=0, min_variance=min_variance, return_all=True)[3])
+        score = vars_[0].clone()
+        for v in vars_[1:]:
+            score.add_(v)
         return score
 
     def select_batch(self, cand_unit, batch_k: int, K_big_cap: int = 8000, fps_start: int = 0,
