@@ -46,7 +46,8 @@ class GPConfig:
     fit_hyperparameters: bool = True     # maximise the exact LML (fit_gpytorch_mll, Bayesian.py:93)
     hyper_restarts: int = 16             # batched random restarts screened by bo_lml_grad_batched
     hyper_refine: int = 4                # best screened restarts refined in lock step (one batched LML call per step)
-    hyper_refine_warm: int = 2           # ... once a previous fit warm-starts the search (the reference refits from one start)
+    hyper_refine_warm: int = 1           # ... once a previous fit warm-starts the search (the reference refits from one start)
+    hyper_full_every: int = 8            # every k-th refit repeats the full screened multi-start (guards against a stale local optimum)
     hyper_maxiter: int = 50              # lock-step L-BFGS iterations
     hyper_prior: Optional[str] = "auto"  # "auto": botorch defaults (rbf -> lognormal, matern52 -> gamma); None = max. likelihood
     lengthscale: Optional[Sequence[float]] = None   # fixed / initial ARD lengthscales (unit cube)
@@ -270,7 +271,10 @@ class BayesianOptimizer:
             lo, hi = np.append(lo, math.log(1e-4)), np.append(hi, math.log(1e2))
             th0 = np.append(th0, math.log(max(lv0, 1e-4)))
         th0 = np.clip(th0, lo, hi)
-        R = max(int(cfg.hyper_restarts), 1)
+        self._hyper_fits = getattr(self, "_hyper_fits", 0) + 1
+        warm_only = (self._hyper is not None and int(cfg.hyper_refine_warm) <= 1 and
+                     (int(cfg.hyper_full_every) <= 0 or (self._hyper_fits - 1) % int(cfg.hyper_full_every) != 0))
+        R = 1 if warm_only else max(int(cfg.hyper_restarts), 1)      # warm refits skip the screening of random restarts
         thetas = np.tile(th0, (R, 1))
         if R > 1:
             thetas[1:, :d] = self._rng.uniform(math.log(0.1), math.log(3.0), size=(R - 1, d))
@@ -278,13 +282,16 @@ class BayesianOptimizer:
             thetas[1:, d + 1] = self._rng.uniform(math.log(cfg.min_noise), math.log(1e-1), size=R - 1)
             if lin:
                 thetas[1:, d + 2] = self._rng.uniform(math.log(1e-2), math.log(1e1), size=R - 1)
+        unpack = lambda t: (np.exp(t[:d]), float(np.exp(t[d])), float(np.exp(t[d + 1])), float(np.exp(t[d + 2])) if lin else 0.0)
+        if R == 1:                                    # nothing to screen: refine the (warm) start directly
+            th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas, lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter))
+            return unpack(th if np.isfinite(F) else th0)
         lml, _, status = eng.lml_grad_batched(X, y, thetas, cfg.kernel)
         score = np.asarray(lml, dtype=np.float64) + log_prior_and_grad(thetas, d, prior)[0]
         score = np.where(np.asarray(status) == 0, score, -np.inf)
-        unpack = lambda t: (np.exp(t[:d]), float(np.exp(t[d])), float(np.exp(t[d + 1])), float(np.exp(t[d + 2])) if lin else 0.0)
         if not np.isfinite(score).any():
             return unpack(th0)
-        n_refine = cfg.hyper_refine if self._hyper is None else min(cfg.hyper_refine, cfg.hyper_refine_warm)
+        n_refine = cfg.hyper_refine if (self._hyper is None or int(cfg.hyper_refine_warm) <= 1) else min(cfg.hyper_refine, cfg.hyper_refine_warm)
         keep = np.argsort(-score)[:max(1, int(n_refine))]
         if 0 not in keep and np.isfinite(score[0]):
             keep = np.concatenate([keep[:-1], [0]]) if len(keep) > 1 else np.array([0])      # always refine the warm start

@@ -266,3 +266,26 @@ def test_svgp_tasks_from_state_dict():
     assert tasks[3].outputscale == pytest.approx(float(F.softplus(msd["covar_module.raw_outputscale"][3].double())))
     assert tasks[5].noise == pytest.approx(float(F.softplus(lsd["noise_covar.raw_noise"][5, 0].double())) + 1e-4)
     np.testing.assert_allclose(tasks[2].lengthscale.numpy(), F.softplus(msd["covar_module.base_kernel.kernels.1.raw_lengthscale"][2, 0].double()).numpy())
+
+
+def test_warm_refits_use_one_start_and_periodic_full_multistart(tmp_path):
+    """Hyper-parameter refit policy: first fit = screened multi-start; warm refits refine the previous optimum only
+    (the reference refits from a single start, Bayesian.py:92-93); every hyper_full_every-th fit is a full one again."""
+    calls = []
+
+    class CountingEngine(OracleEngine):
+        def lml_grad_batched(self, X, y, thetas, kernel="matern52", mean=0.0):
+            calls.append(np.asarray(thetas).reshape(-1, X.shape[1] + 2).shape[0])
+            return super().lml_grad_batched(X, y, thetas, kernel, mean)
+
+    opt = _opt(tmp_path, engine_factory=CountingEngine, gp_config=_cfg(hyper_restarts=5, hyper_refine=2, hyper_maxiter=2, hyper_full_every=3))
+    for x in opt.collect_initial_points():
+        opt.register(x)
+    widths = []
+    for _ in range(4):
+        calls.clear()
+        opt.fit_gp_model()
+        widths.append(max(calls))
+    assert widths[0] == 5            # cold: 5 restarts screened
+    assert widths[1] == 1 and widths[2] == 1     # warm: the previous optimum only, no screening
+    assert widths[3] == 5            # 4th fit = (fits - 1) % 3 == 0 -> full multi-start again
