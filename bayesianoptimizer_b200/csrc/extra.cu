@@ -297,10 +297,13 @@ static int ensure_qbuf(bo_handle* h, size_t elems) {
     return 0;
 }
 
-constexpr int QB = 8;
+// right-hand sides per pass over L^-1: 8.  (16 would cover the default 10 restarts in one pass, but the kernels are bound by
+// the per-element FMA/load chains, not by the L^-1 stream: measured 75 vs 31 us for the transposed product at n = 3000.)
+static int acq_qb(int k) { (void)k; return 8; }
 // row segments of the transposed skinny TRMM: enough CTAs for ~8 waves, at most 16 (workspace = (3 + splits) k np doubles)
 static int acq_wsplits(const bo_handle* h, int k) {
-    const int base = (h->np / 32) * ((k + QB - 1) / QB);
+    const int qb = acq_qb(k);
+    const int base = (h->np / 32) * ((k + qb - 1) / qb);
     int s = (8 * h->sm_count + base - 1) / base;
     return s < 1 ? 1 : (s > 16 ? 16 : s);
 }
@@ -313,11 +316,17 @@ static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, doub
     double* kv = ws; double* gv = kv + (size_t)k * np; double* V = gv + (size_t)k * np; double* W = V + (size_t)k * np;
     kq_build_kernel<DP><<<dim3(np / 256 + (np % 256 != 0), k), 256, 0, st>>>(h->Xs, h->n, np, h->hyp, Xq, h->d, kv, gv);
     BO_LAUNCH_CHECK(h);
-    const int qg = (k + QB - 1) / QB;
-    trmm_lower_skinny_kernel<QB><<<dim3(np / 8, qg), 256, 0, st>>>(h->Li, ld, np, kv, k, V);
-    BO_LAUNCH_CHECK(h);
+    const int qb = acq_qb(k), qg = (k + qb - 1) / qb;
     const int ws_splits = acq_wsplits(h, k);
-    trmm_lower_t_skinny_kernel<QB><<<dim3(np / 32, ws_splits, qg), 256, 0, st>>>(h->Li, ld, np, V, k, W);
+    if (qb == 16) {
+        trmm_lower_skinny_kernel<16><<<dim3(np / 8, qg), 256, 0, st>>>(h->Li, ld, np, kv, k, V);
+        BO_LAUNCH_CHECK(h);
+        trmm_lower_t_skinny_kernel<16><<<dim3(np / 32, ws_splits, qg), 256, 0, st>>>(h->Li, ld, np, V, k, W);
+    } else {
+        trmm_lower_skinny_kernel<8><<<dim3(np / 8, qg), 256, 0, st>>>(h->Li, ld, np, kv, k, V);
+        BO_LAUNCH_CHECK(h);
+        trmm_lower_t_skinny_kernel<8><<<dim3(np / 32, ws_splits, qg), 256, 0, st>>>(h->Li, ld, np, V, k, W);
+    }
     BO_LAUNCH_CHECK(h);
     acq_grad_finalize_kernel<DP><<<k, 256, 0, st>>>(h->Xs, h->alpha, h->n, np, h->hyp, Xq, h->d, kv, gv, V, W, ws_splits, k, acq, best_f,
                                                    sqrt(beta), min_var, val, grad);
