@@ -119,6 +119,10 @@ __global__ void rescale_batched_kernel(int np, int d, const Hyper* __restrict__ 
 // Right-looking Cholesky with the block held in REGISTERS: thread (ti, tk) of a 16 x 16 grid owns the
 // 4 x 4 elements (ti + 16x, tk + 16y); per column one shared-memory broadcast of the pivot column and one
 // barrier (double-buffered), the rank-1 update is 16 register FMAs.  Leaves L (lower, upper zero) in S.
+// The update is UNMASKED: a finished column is copied to S the moment it is final, after which the registers of
+// rows <= j / columns <= j may hold anything -- a valid entry (i, k > j) is only ever updated with L[i][j] L[k][j],
+// both taken from the still-valid part of the pivot column, so stale values never reach a live entry.  This halves
+// the instructions of a step (the chain of 64 steps is issue-bound: 124 -> ~65 SASS instructions per warp and step).
 __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int lda, double (*S)[NB + 1],
                                               double (*colS)[NB], int* info, int pivot_base, bool report) {
     const int tid = threadIdx.x;
@@ -154,32 +158,25 @@ __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int 
             rs = rs * fma(-hj, rs * rs, 1.5);
             double li[4], lk[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) { const int i = ti + 16 * x; li[x] = (i > j) ? col[i] * rs : 0.0; }
+            for (int x = 0; x < 4; ++x) li[x] = col[ti + 16 * x] * rs;
 #pragma unroll
-            for (int y = 0; y < 4; ++y) { const int k = tk + 16 * y; lk[y] = (k > j) ? col[k] * rs : 0.0; }
+            for (int y = 0; y < 4; ++y) lk[y] = col[tk + 16 * y] * rs;
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
                     if (y >= jb) a[x][y] = fma(-li[x], lk[y], a[x][y]);      // column groups left of j are final
-            if (tk == jt) {
+            if (tk == jt) {                          // column j is final: park it in S (zero above the diagonal)
                 double sj = dj * rs;
                 sj = fma(0.5 * rs, fma(-sj, sj, dj), sj);          // sqrt(dj), Heron-corrected
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     const int i = ti + 16 * x;
-                    if (i >= j) a[x][jb] = (i > j) ? li[x] : sj;
+                    S[i][j] = (i > j) ? li[x] : (i == j ? sj : 0.0);
                 }
             }
         }
     }
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = ti + 16 * x, k = tk + 16 * y;
-            S[i][k] = (k <= i) ? a[x][y] : 0.0;
-        }
     __syncthreads();
 }
 
