@@ -243,3 +243,40 @@ def test_device_topk_scores_matches_oracle_order(engine, N, K, kind):
     assert np.array_equal(idx[:m], ti)
     assert np.array_equal(vals[:m], tv)
     assert np.all(idx[m:] == -1) and np.all(np.isneginf(vals[m:]))
+
+
+def test_c5_full_size_256_restarts(engine):
+    """BASELINE config 5 at full size: 256 batched restarts, n_obs = 2048, d = 10 (SURVEY 8d inputs); three restarts
+    against the oracle, and a restart evaluated alone equals its value inside the batch (slot / group independence)."""
+    n, d, R = 2048, 10, 256
+    X, y = synth_problem(n, d, 8, 5)
+    rng = np.random.default_rng(9)
+    th = np.concatenate([rng.uniform(np.log(0.05), np.log(5), (R, d)), np.zeros((R, 1)),
+                         rng.uniform(np.log(1e-4), np.log(1e-1), (R, 1))], axis=1)
+    lml, grad, st = engine.lml_grad_batched(_cuda(X), _cuda(y), th)
+    assert st.tolist() == [0] * R and torch.isfinite(lml).all() and torch.isfinite(grad).all()
+    for r in (0, 100, 255):
+        l, g = o.lml_and_grad(X, y, o.KERNEL_MATERN52, np.exp(th[r, :d]), np.exp(th[r, d]), np.exp(th[r, d + 1]))
+        assert abs(lml[r].item() - l) <= 1e-8 * abs(l), (r, lml[r].item(), l)
+        np.testing.assert_allclose(grad[r].numpy(), g, rtol=1e-6, atol=1e-7 * np.abs(g).max())
+    l1, g1, _ = engine.lml_grad_batched(_cuda(X), _cuda(y), th[100:101])
+    assert l1[0].item() == lml[100].item() and torch.equal(g1[0], grad[100])
+
+
+def test_c4_appends_across_the_4096_boundary(engine):
+    """BASELINE config 4 shape: Kriging-believer / observed appends growing n past a capacity and padding boundary
+    (4090 -> 4100 rows); the appended model equals an oracle refit on the extended data."""
+    n0, d = 4090, 8
+    X, y = synth_problem(n0 + 10, d, 7, 5)
+    engine.fit(_cuda(X[:n0]), _cuda(y[:n0]), "matern52", 0.7, 1.0, 1e-3)
+    for i in range(n0, n0 + 10):
+        engine.append(_cuda(X[i]), float(y[i]))
+    assert engine.n == n0 + 10
+    ref = o.fit(X, y, o.KERNEL_MATERN52, 0.7, 1.0, 1e-3)
+    xs = np.random.default_rng(3).random((300, d))
+    mu, var = engine.posterior(_cuda(xs))
+    omu, ovar = o.posterior(ref, xs)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+    vals, idx = engine.sweep("ei", float(y.max()), candidates=_cuda(xs), topk=4)
+    tv, ti, _, _, _ = o.sweep(ref, xs, o.ACQ_EI, float(y.max()), k=4)
+    assert idx.cpu().tolist() == ti.tolist()
