@@ -397,6 +397,23 @@ __global__ void refine_update_kernel(int k, int d, double* __restrict__ x, doubl
     }
 }
 
+// number of starts that are NOT yet converged: projected gradient (components pushing out of the box dropped) below
+// gtol * max(1, |f|), or a step so small that the point can no longer move (pgtol-style test of L-BFGS-B)
+__global__ void refine_active_kernel(int k, int d, const double* __restrict__ x, const double* __restrict__ f,
+                                     const double* __restrict__ g, const double* __restrict__ step, double gtol,
+                                     int* __restrict__ active) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    double pg = 0.0;
+    for (int c = 0; c < d; ++c) {
+        const double xv = x[(size_t)s * d + c], gv = g[(size_t)s * d + c];
+        const bool blocked = (xv <= 0.0 && gv < 0.0) || (xv >= 1.0 && gv > 0.0);
+        if (!blocked && isfinite(gv)) pg = fmax(pg, fabs(gv));
+    }
+    const double fs = isfinite(f[s]) ? fabs(f[s]) : 0.0;
+    if (pg > gtol * fmax(1.0, fs) && step[s] * pg > 1e-13) atomicAdd(active, 1);
+}
+
 int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var, const double* starts_dev, int k,
                 int iters, double* x_dev, double* val_dev, cudaStream_t st) {
     int rc = check_query_args(h, acq_kind, beta, starts_dev, x_dev, val_dev, k);
@@ -414,7 +431,16 @@ int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double m
     if ((rc = BO_DISPATCH_DP(h->dp, eval_acq_grad, h, acq_kind, best_f, beta, min_var, x_dev, k, val_dev, g, ws, st))) return rc;
     refine_init_kernel<<<(k + 127) / 128, 128, 0, st>>>(k, d, g, step);
     BO_LAUNCH_CHECK(h);
+    constexpr int CHECK_EVERY = 16;          // convergence poll: one 4-byte read-back per 16 iterations
     for (int it = 0; it < iters; ++it) {
+        if (it > 0 && it % CHECK_EVERY == 0 && it + CHECK_EVERY <= iters) {
+            BO_CUDA(h, cudaMemsetAsync(h->info_dev, 0, sizeof(int), st));
+            refine_active_kernel<<<(k + 127) / 128, 128, 0, st>>>(k, d, x_dev, val_dev, g, step, 1e-6, h->info_dev);
+            BO_LAUNCH_CHECK(h);
+            BO_CUDA(h, cudaMemcpyAsync(h->info_host, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BO_CUDA(h, cudaStreamSynchronize(st));
+            if (*h->info_host == 0) break;     // every start has converged (maxiter is an upper bound, Bayesian.py:111)
+        }
         refine_propose_kernel<<<(k * d + 127) / 128, 128, 0, st>>>(k, d, x_dev, g, step, xn);
         BO_LAUNCH_CHECK(h);
         if ((rc = BO_DISPATCH_DP(h->dp, eval_acq_grad, h, acq_kind, best_f, beta, min_var, xn, k, fn, gn, ws, st))) return rc;
