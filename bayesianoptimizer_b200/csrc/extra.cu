@@ -420,7 +420,7 @@ int refine_impl(bo_handle* h, int acq_kind, double best_f, double beta, double m
     if (rc) return rc;
     if (iters < 0) return fail(h, BO_E_INVALID, "bo_refine: iters must be >= 0");
     BO_CUDA(h, cudaSetDevice(h->device));
-    const int d = h->d, np = h->np;
+    const int d = h->d;
     const size_t ws_elems = acq_ws_elems(h, k);
     // layout: [acq-grad scratch | g | xn | fn | gn | step]
     if ((rc = ensure_qbuf(h, ws_elems + (size_t)k * (3 * d + 2) + 64))) return rc;

@@ -261,7 +261,7 @@ static int lml_prepare(bo_handle* h, int n, int d, int S, cudaStream_t st) {
         b->launches.push_back(L);
     };
     for (int kb = 0; kb + 1 < nb; ++kb) {
-        const int r0 = (kb + 1) * NB, m = np - r0;
+        const int m = np - (kb + 1) * NB;
         long t128 = (long)(m / 128) * (m / 128 + 1) / 2 * S;
         GemmBatch syrk(pick_tile(h->sm_count, {m}, t128));
         for (int s = 0; s < S; ++s) add_trailing_update(syrk, b->Lm + (size_t)s * mat, ld, np, kb, nb);
@@ -388,8 +388,6 @@ int lml_impl(bo_handle* h, const double* X_dev, const double* y_dev, int n, int 
     if (rc) return rc;
     LmlBatch* b = static_cast<LmlBatch*>(h->lml_batch);
     S = b->S;                         // slots actually allocated (>= the request)
-    const int ld = np, nb = np / NB;
-    const size_t mat = (size_t)np * np;
     Hyper zero{};   // inv_ls = 1, mean: staging of the unscaled inputs uses an identity scale
     for (int k = 0; k < BO_MAX_DIM; ++k) zero.inv_ls[k] = 1.0;
     stage_inputs_kernel<<<(np + 127) / 128, 128, 0, st>>>(X_dev, y_dev, n, d, np, zero, b->Xraw, b->Xs, b->yv);

@@ -479,7 +479,6 @@ __global__ void __launch_bounds__(1024) topk_merge_kernel(double* __restrict__ p
     __shared__ double sv[32];
     __shared__ long long si[32];
     __shared__ int sp[32];
-    __shared__ int win;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int r = 0; r < topk; ++r) {
         double bv = -INFINITY; long long bi = IDX_EMPTY; int bp = -1;
@@ -510,12 +509,10 @@ __global__ void __launch_bounds__(1024) topk_merge_kernel(double* __restrict__ p
             if (lane == 0) {
                 vals[r] = (bp >= 0) ? bv : -INFINITY;
                 idx[r] = (bp >= 0) ? bi : -1;
-                win = bp;
                 if (bp >= 0) pi[bp] = IDX_EMPTY;
             }
         }
         __syncthreads();
-        (void)win;
     }
 }
 
