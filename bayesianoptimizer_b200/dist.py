@@ -1,4 +1,6 @@
-"""Candidate sharding over the GPUs of one box and the single (value, index) exchange.
+"""Sharding over the GPUs of one box: candidates of a sweep, and -- the same idea one level up --
+the independent hyper-parameter restarts of a batched LML evaluation (BASELINE config 5) and the independent tasks of
+a batched SVGP scan.  Each has exactly one collective.
 
 Every rank holds a replica of the fitted GP and scores a contiguous shard of the global candidate index
 range; the only bytes that cross NVLink are one all-gather of ``topk`` packed (value, index) pairs per rank,
@@ -66,3 +68,44 @@ def sharded_sweep(engine, acq, best_f, beta, sobol, total: int, topk: int, rank:
     if world == 1:
         return v, i
     return allgather_topk(v, i, topk, group)
+
+
+def sharded_lml_grad(engine, X, y, thetas, kernel="matern52", mean: float = 0.0, rank: int = 0, world: int = 1, group=None):
+    """Batched LML + gradient with the R restarts split contiguously over the ranks (they are independent
+    factorisations: nothing but the results crosses NVLink).  One all-gather of [ceil(R/world), p + 2] doubles per rank;
+    every rank returns the full (lml[R], grad[R,p], status[R]) on the host, like ``GPEngine.lml_grad_batched``."""
+    th = torch.as_tensor(thetas, dtype=torch.float64, device="cpu")
+    th = th.reshape(-1, th.shape[-1]) if th.ndim > 1 else th.reshape(1, -1)
+    R, p = th.shape
+    if world == 1:
+        return engine.lml_grad_batched(X, y, th, kernel, mean)
+    import torch.distributed as dist
+    per = -(-R // world)
+    first, count = shard_range(R, rank, world)
+    buf = torch.zeros(per, p + 2, dtype=torch.float64)
+    buf[:, 0] = float("-inf")
+    if count > 0:
+        lml, grad, status = engine.lml_grad_batched(X, y, th[first:first + count], kernel, mean)
+        buf[:count, 0] = torch.as_tensor(lml, dtype=torch.float64).cpu()
+        buf[:count, 1] = torch.as_tensor(status, dtype=torch.float64).cpu()
+        buf[:count, 2:] = torch.as_tensor(grad, dtype=torch.float64).cpu()
+    dev = engine.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    out = torch.empty(world * per, p + 2, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, buf.to(dev).contiguous(), group=group)
+    out = out.cpu()[:R] if per * world >= R else out.cpu()
+    # rank r's rows sit at [r * per, r * per + count_r): with contiguous shards of ceil(R / world) that is already restart order
+    return out[:, 0].contiguous(), out[:, 2:].contiguous(), out[:, 1].to(torch.int32)
+
+
+def task_shard(num_tasks: int, rank: int, world: int):
+    """Tasks of a batched SVGP handled by this rank (contiguous split)."""
+    first, count = shard_range(num_tasks, rank, world)
+    return list(range(first, first + count))
+
+
+def allreduce_score(score: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the per-rank partial variance scores of a task-sharded SVGP scan (one all-reduce of N doubles)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(score, op=dist.ReduceOp.SUM, group=group)
+    return score

@@ -286,7 +286,12 @@ class BayesianOptimizer:
         if R == 1:                                    # nothing to screen: refine the (warm) start directly
             th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas, lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter))
             return unpack(th if np.isfinite(F) else th0)
-        lml, _, status = eng.lml_grad_batched(X, y, thetas, cfg.kernel)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .dist import sharded_lml_grad                    # restarts are independent: shard the screening over the ranks
+            lml, _, status = sharded_lml_grad(eng, X, y, thetas, cfg.kernel, 0.0, dist.get_rank(), dist.get_world_size())
+        else:
+            lml, _, status = eng.lml_grad_batched(X, y, thetas, cfg.kernel)
         score = np.asarray(lml, dtype=np.float64) + log_prior_and_grad(thetas, d, prior)[0]
         score = np.where(np.asarray(status) == 0, score, -np.inf)
         if not np.isfinite(score).any():

@@ -54,6 +54,32 @@ sob = sobol_state(3, 7)
 v, i = sharded_sweep(eng, "ucb", 0.0, 2.0, sob, 4001, 5, rank, world)
 v1, i1 = eng.sweep("ucb", 0.0, 2.0, sobol=sob, count=4001, topk=5)
 assert i.tolist() == i1.tolist() and v.tolist() == v1.tolist(), (rank, i.tolist(), i1.tolist())
+# restart sharding of the batched LML (BASELINE config 5): 5 restarts over 2 ranks == one unsharded call
+from bayesianoptimizer_b200.dist import sharded_lml_grad
+th = np.random.default_rng(3).uniform(-1.0, 0.5, (5, 5)); th[:, 4] = np.log(1e-2)
+l, g, st = sharded_lml_grad(eng, X, y, th, "matern52", 0.0, rank, world)
+l1, g1, st1 = eng.lml_grad_batched(X, y, th, "matern52", 0.0)
+assert l.shape == (5,) and g.shape == (5, 5) and st.tolist() == st1.tolist()
+assert torch.equal(l, l1.to(torch.float64)) and torch.equal(g, g1.to(torch.float64)), (rank, l, l1)
+# task sharding of a batched SVGP scan: partial variance sums meet in one all-reduce
+from bayesianoptimizer_b200.dist import task_shard, allreduce_score
+from oracle import gp_oracle as o
+rng = np.random.default_rng(5)
+tasks = []
+for t in range(3):
+    M = 20
+    Ls = np.tril(rng.standard_normal((M, M)) * 0.05) + np.diag(0.3 + 0.5 * rng.random(M))
+    tasks.append(o.SVGPTask(rng.standard_normal((M, 3)), o.KERNEL_LINEAR_MATERN52, rng.uniform(0.5, 1.5, 3), 1.2, 0.2, 0.0, 1e-3, 1e-6,
+                            rng.standard_normal(M), Ls))
+xs = rng.standard_normal((200, 3))
+mine = task_shard(3, rank, world)
+part = torch.zeros(200, dtype=torch.float64)
+for t in mine:
+    e = OracleEngine().load_svgp(tasks[t].Z, tasks[t].m, tasks[t].Ls, "linear_matern52", tasks[t].lengthscale, 1.2, 0.2, 0.0, 1e-3, 1e-6)
+    part += e.sweep("var", candidates=xs, topk=0, return_all=True)[3]
+total = allreduce_score(part)
+np.testing.assert_allclose(total.numpy(), o.svgp_variance_score(tasks, xs), rtol=1e-12)
+assert sorted(sum((task_shard(3, r, world) for r in range(world)), [])) == [0, 1, 2]
 print("rank", rank, "ok", i.tolist())
 dist.destroy_process_group()
 '''
