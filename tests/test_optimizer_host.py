@@ -289,3 +289,49 @@ def test_warm_refits_use_one_start_and_periodic_full_multistart(tmp_path):
     assert widths[0] == 5            # cold: 5 restarts screened
     assert widths[1] == 1 and widths[2] == 1     # warm: the previous optimum only, no screening
     assert widths[3] == 5            # 4th fit = (fits - 1) % 3 == 0 -> full multi-start again
+
+
+_REF_DRIVER = "/root/reference/scripts/run_optimization.py"
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_DRIVER), reason="the reference checkout is only mounted in the build container")
+def test_reference_driver_runs_with_only_its_import_switched(tmp_path, monkeypatch):
+    """INTEGRATION.md section 1, executed: the reference's OWN scripts/run_optimization.py (read from the mounted checkout, never
+    copied) with line 4 switched to this package -- fresh run, then an automatic resume to a larger target.  The Taichi
+    simulator module is stubbed by the cached-CSV double, the CUDA engine by the oracle-backed double (CPU tier)."""
+    import sys
+    import types
+    import bayesianoptimizer_b200.optimizer as optmod
+    src = open(_REF_DRIVER).read()
+    line4 = "from optimization.Bayesian7 import BayesianOptimizer"
+    assert src.splitlines()[3] == line4
+    src = src.replace(line4, "from bayesianoptimizer_b200.optimizer import BayesianOptimizer")      # the one-line switch
+    sims = []
+
+    def make_sim(xml_path):
+        assert xml_path == "config/setting.xml"
+        sims.append(_sim())
+        return sims[-1]
+
+    fake = types.ModuleType("simulation.taichi")
+    fake.MPMSimulator = make_sim
+    monkeypatch.setitem(sys.modules, "simulation", types.ModuleType("simulation"))
+    monkeypatch.setitem(sys.modules, "simulation.taichi", fake)
+    monkeypatch.syspath_prepend("/root/reference")                      # config.config: the reference's own bounds
+    monkeypatch.delitem(sys.modules, "config", raising=False)
+    monkeypatch.delitem(sys.modules, "config.config", raising=False)
+    monkeypatch.setattr(optmod, "GPEngine", lambda device: OracleEngine())
+    monkeypatch.setattr(optmod, "GPConfig", lambda: _cfg(candidates_pool_size=256))
+    ns = {"__name__": "run_optimization_under_test"}
+    exec(compile(src, _REF_DRIVER, "exec"), ns)
+    out = str(tmp_path / "results")
+    best_params, best_value = ns["run_optimization"](total_evaluations=18, n_initial_points=12, batch_size=3, seed=0, output_dir=out)
+    csv = os.path.join(out, "optimization_results.csv")
+    assert ns["_count_existing_evals"](csv) == 18 and sims[0].cleaned and sims[0].calls == 18
+    assert len(best_params) == 5 and np.isfinite(best_value)
+    lo, hi = np.array(DEFAULT_BOUNDS).T
+    assert np.all(best_params >= lo - 1e-9) and np.all(best_params <= hi + 1e-9)
+    # second call: the driver detects the CSV, passes resume=True / target_total, and only the missing rows are added
+    ns["run_optimization"](total_evaluations=22, n_initial_points=12, batch_size=3, seed=0, output_dir=out)
+    assert ns["_count_existing_evals"](csv) == 22 and sims[1].calls == 4
+    assert ns["run_optimization"](total_evaluations=22, n_initial_points=12, batch_size=3, seed=0, output_dir=out) == (None, None)
