@@ -63,6 +63,36 @@ for c in range(cases):
             srt = np.sort(oav)[::-1]
             gap = np.min(np.abs(np.diff(srt[:m + 1]))) if len(srt) > 1 else 1.0
             assert gap <= 1e-6 * max(1.0, abs(srt[0])), f"top-k differs: {idx[:m].tolist()} vs {ti.tolist()} (gap {gap:g})"
+        # acquisition gradient at a few points (stationary kinds only)
+        if kind != 2 and n >= 2 and rng.random() < 0.3:
+            Xq = rng.random((int(rng.integers(1, 12)), d))
+            val, grad = eng.acq_grad(cu(Xq), acq, bf, beta)
+            val, grad = val.cpu().numpy(), grad.cpu().numpy()
+            for i in range(Xq.shape[0]):
+                vv, gg = o.acquisition_with_grad(gp, Xq[i], AC[acq], bf, beta)
+                mq, vq = o.posterior(gp, Xq[i:i + 1])
+                uq = abs((mq[0] - bf) / np.sqrt(vq[0]))
+                scale = {"logei": 1.0, "ucb": abs(mq[0]) + np.sqrt(beta * vq[0]), "mean": abs(mq[0]) + 1e-3}.get(acq, abs(vv))
+                cond = 1.0 + uq + uq * uq if acq in ("ei", "logei") else 1.0
+                assert abs(val[i] - vv) <= 1e-6 * scale * cond + 1e-300, ("acq value", acq, val[i], vv)
+                gn = np.abs(gg).max()
+                if vq[0] > 1.1e-6:                      # away from the variance clamp (the clamp zeroes the variance gradient)
+                    assert np.abs(grad[i] - gg).max() <= 1e-5 * gn * cond + 1e-10, ("acq grad", acq, grad[i], gg)
+        # m outputs sharing the factorisation
+        if n >= 4 and rng.random() < 0.2:
+            m = int(rng.integers(1, 12))
+            Y = np.sin(X @ rng.standard_normal((d, m))) + 0.05 * rng.standard_normal((n, m))
+            means = rng.standard_normal(m) * 0.1
+            q = rng.random((257, d))
+            mm, vv2 = eng.posterior_multi(cu(Y), cu(q), means)
+            om, ov = o.posterior_multi(gp, Y, q, means)
+            for t_ in range(m):
+                assert_posterior_close(mm[:, t_].cpu().numpy(), vv2.cpu().numpy(), om[:, t_], ov)
+        # device farthest-point sampling on the pool
+        if N >= 128 and rng.random() < 0.2:
+            mfp = int(rng.integers(1, min(N, 300)))
+            stt_ = int(rng.integers(0, N))
+            assert np.array_equal(eng.fps(cu(xs), mfp, stt_).cpu().numpy(), o.fps(xs, mfp, stt_))
         # an append now and then (stationary and linear kinds)
         if n >= 2 and rng.random() < 0.3:
             xn = rng.random(d); yn = None if rng.random() < 0.5 else float(rng.normal())
