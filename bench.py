@@ -162,10 +162,33 @@ def run_reference(args):
                                        f"slice per core in a thread pool, chunk 2048 like Bayesian7.py:63); the reference's "
                                        f"botorch/gpytorch stack is not installable offline"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    communicator when NCCL_DEBUG is set), so everything else is pointed at stderr and the line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -320,7 +343,7 @@ def main():
             line["cpu_baseline"] = {"value": r["cand_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                     "sample": f"{sample}-candidate prefix of the same Sobol pool, NumPy/SciPy FP64 oracle, one slice "
                                               f"per core (fit {r['fit_s']:.2f} s, sweep {r['sweep_s']:.2f} s)"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
