@@ -738,6 +738,8 @@ int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, co
 // GEMM throughput probe (development / roofline evidence for the fit's trailing updates): C = A * B^T, square tiles
 int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double* tflops) {
     BO_CUDA(h, cudaSetDevice(h->device));
+    const int form = cfg / 10;          // 0: A [M][K], B [N][K] (SYRK / TRSM shape) | 1: B [K][N] (inverse levels) | 2: A [K][M], B [K][N] (L^-T L^-1)
+    cfg %= 10;
     const int bm = (cfg == 1 || cfg == 2 || cfg == 6) ? 128 : 64, bn = (cfg == 1 || cfg == 6) ? 128 : 64;
     {   // probe-only variants opt in here
         cudaFuncSetAttribute(dgemm_grouped_kernel<64, 64, 16, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmem<64, 64, 16, 2>::BYTES);
@@ -752,6 +754,8 @@ int gemm_probe_impl(bo_handle* h, int m, int n, int k, int cfg, int reps, double
     BO_CUDA(h, cudaMemset(A, 0, (size_t)m * k * 8)); BO_CUDA(h, cudaMemset(B, 0, (size_t)n * k * 8)); BO_CUDA(h, cudaMemset(C, 0, (size_t)m * n * 8));
     GemmProblem p{}; p.A = A; p.B = B; p.C = C; p.M = m; p.N = n; p.K = k; p.lda = k; p.ldb = k; p.ldc = n; p.alpha = 1.0; p.beta = 1.0;
     p.transB = 1; p.mode = 0; p.tiles_n = n / bn; p.tile_begin = 0; p.tile_end = (m / bm) * (n / bn);
+    if (form >= 1) { p.transB = 0; p.ldb = n; }
+    if (form == 2) { p.mode = GEMM_TRANS_A; p.lda = m; }
     BO_CUDA(h, cudaMemcpy(pd, &p, sizeof p, cudaMemcpyHostToDevice));
     auto launch = [&]() {
         if (cfg == 1) dgemm_grouped_kernel<128, 128><<<p.tile_end, 256, GemmSmem<128, 128>::BYTES>>>(pd, 1);

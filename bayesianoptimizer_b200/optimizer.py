@@ -130,6 +130,7 @@ class BayesianOptimizer:
         self._engine_factory = engine_factory or (lambda: GPEngine(self.device))
         self._engine = None
         self._hyper = None            # (lengthscale[d], outputscale, noise, linear variance) carried between refits (warm start)
+        self._hyper_fits = 0          # hyper-parameter refits so far (every hyper_full_every-th one is a full multi-start)
         self._y_mean, self._y_std = 0.0, 1.0
         self._suggest_count = 0
         self._rng = np.random.default_rng(self.config.seed)
@@ -271,7 +272,7 @@ class BayesianOptimizer:
             lo, hi = np.append(lo, math.log(1e-4)), np.append(hi, math.log(1e2))
             th0 = np.append(th0, math.log(max(lv0, 1e-4)))
         th0 = np.clip(th0, lo, hi)
-        self._hyper_fits = getattr(self, "_hyper_fits", 0) + 1
+        self._hyper_fits += 1
         warm_only = (self._hyper is not None and int(cfg.hyper_refine_warm) <= 1 and
                      (int(cfg.hyper_full_every) <= 0 or (self._hyper_fits - 1) % int(cfg.hyper_full_every) != 0))
         R = 1 if warm_only else max(int(cfg.hyper_restarts), 1)      # warm refits skip the screening of random restarts
