@@ -74,6 +74,8 @@ int bo_release_workspace(bo_handle* h) {
     h->panel2 = nullptr; h->panel2_bytes = 0;
     if (h->cand_stage) cudaFree(h->cand_stage);
     h->cand_stage = nullptr; h->cand_stage_bytes = 0;
+    if (h->panel8) cudaFree(h->panel8);
+    h->panel8 = nullptr; h->panel8_bytes = 0;
     lml_release(h);
     return 0;
 }
@@ -86,7 +88,7 @@ void bo_destroy(bo_handle* h) {
     lml_release(h);
     void* ptrs[] = {h->qbuf, h->split_ws, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
-                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws};
+                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws, h->Lp8, h->rowscale};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->info_host) cudaFreeHost(h->info_host);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -106,6 +106,11 @@ struct bo_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool sweep_timed = false;
 
+    // INT8-sliced sweep (sweep_i8.cuh): slices of L^-1 in stage-tile order, power-of-two row scales, per-CTA int8 panels
+    int8_t* Lp8 = nullptr; size_t Lp8_bytes = 0;
+    double* rowscale = nullptr; size_t rowscale_cap = 0;
+    int8_t* panel8 = nullptr; size_t panel8_bytes = 0;
+
     void* select_ws = nullptr; size_t select_bytes = 0;  // large top-K (select.cu)
 
     // K5-K7 workspaces

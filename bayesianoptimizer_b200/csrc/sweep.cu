@@ -472,6 +472,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
     }
 }
 
+__global__ void topk_merge_kernel(double* __restrict__ pv, long long* __restrict__ pi, int total, int topk, double* __restrict__ vals,
+                                  long long* __restrict__ idx);
+
 // ---- merge of the per-CTA top-k lists (k rounds of a block-wide arg-best) ------------------
 __global__ void __launch_bounds__(1024) topk_merge_kernel(double* __restrict__ pv, long long* __restrict__ pi,
                                                           int total, int topk, double* __restrict__ vals,
@@ -734,6 +737,8 @@ static int launch_sobol_points(bo_handle* h, const int64_t* idx, int64_t N, doub
      (dp) == 6 ? fn<6>(__VA_ARGS__) : (dp) == 8 ? fn<8>(__VA_ARGS__) :  \
      (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
 
+#include "sweep_i8.cuh"
+
 static int upload_sobol(bo_handle* h, const bo_sobol* sobol_host, cudaStream_t st) {
     if (sobol_host->d < h->d) return fail(h, BO_E_INVALID, "sobol state has fewer dimensions than the fitted model");
     if (!h->sobol_dev) BO_CUDA(h, cudaMalloc(&h->sobol_dev, sizeof(bo_sobol)));
@@ -798,6 +803,12 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
         BO_CUDA(h, cudaStreamSynchronize(st));
         if (tm) cudaFree(tm); if (tv) cudaFree(tv); if (ta) cudaFree(ta);
         return 0;
+    }
+
+    if (impl && strcmp(impl, "i8") == 0 && sweep_i8_eligible(h, a)) {
+        const char* sl = getenv("BO_B200_I8_SLICES");
+        a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
+        return sweep_i8_run(h, a, (sl && atoi(sl) == 8) ? 8 : 7, vals_dev, idx_dev, st);
     }
 
     {

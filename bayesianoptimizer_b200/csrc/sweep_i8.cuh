@@ -1,0 +1,508 @@
+// K4-i8: the sweep's variance contraction u = L^-1 k* as an error-free (Ozaki scheme I) product of signed 7-bit
+// slices on the INT8 tensor path (tcgen05.mma kind::i8, INT32 accumulators in TMEM) -- included by sweep.cu.
+//
+// Why: the FP64 sweep (sweep_kernel) sits at 0.95 of the DMMA roof (37 TFLOP/s); INT8 tcgen05 runs at 4.4 POP/s
+// (tools/i8_probe.cu).  Every row of L^-1 is scaled by a power of two to |x| < 1 and cut into S balanced radix-128
+// digits x ~= sum_s d_s 2^(-6-7s), d_s in [-64, 64]; the candidates' K(X, x*) columns likewise (fixed scale, the
+// kernel is bounded by the output scale).  Digit products are exact integers; products with equal s + t share one
+// INT32 accumulator (|sum| <= S * 64 * 64 * n < 2^31 for n <= 74 000); the S accumulators are recombined in FP64
+// (Horner in 2^-7) when a 128-row block is complete, squared and summed per candidate.  Pairs with s + t >= S are
+// dropped: S (S + 1) / 2 products per FP64 multiply-add.  tools/ozaki_feasibility.py: S = 7 reproduces sigma^2 to
+// 6e-10 relative at the C3 shape (bar: 1e-8), S = 8 is indistinguishable from the FP64 product.
+//
+// Shape: TMEM holds 512 columns, so S accumulators allow N = 64 candidates per CTA tile (M = 128 rows of L^-1).
+// Per block of 64 candidates:
+//   phase A  (warps 0-3) candidates, K(X, X*) in FP64, posterior mean, digits -> this CTA's int8 panel in HBM/L2;
+//   phase B  warp 4 streams stage tiles (S slices of a 128 x 64 piece of L^-1 and of a 64 x 64 piece of the panel,
+//            pre-arranged in the tensor core's K-major 8 x 16 B core-matrix order) with TMA bulk copies into a 2-stage
+//            ring; one lane of warp 5 issues the S (S + 1) / 2 x 2 MMAs of a stage and commits to the ring's empty barrier and,
+//            per row block, to the accumulator-full barrier; warps 0-3 (one TMEM lane = one row of L^-1 each) drain the
+//            accumulators with tcgen05.ld, recombine and keep sum_i u_i^2 for their row in registers;
+//   epilogue variance, acquisition, CTA-local top-k (as sweep_kernel).
+// Replaces the same reference code as sweep_kernel (optimization/Bayesian7.py:664-682, Bayesian.py:105-112).
+
+constexpr int I8_BN      = 64;                 // candidates per CTA tile (TMEM: S * 64 columns)
+constexpr int I8_KC      = 64;                 // contraction bytes per pipeline stage
+constexpr int I8_STAGES  = 2;
+constexpr int I8_THREADS = 192;                // warps 0-3: panel build + drain, warp 4: TMA, warp 5: MMA issue
+constexpr int I8_A_SLICE = SW_BM * I8_KC;      // 8 KB
+constexpr int I8_B_SLICE = I8_BN * I8_KC;      // 4 KB
+
+template <int S>
+struct I8Smem {
+    static constexpr int STAGE_BYTES = S * (I8_A_SLICE + I8_B_SLICE);
+    static constexpr int OFF_BAR   = I8_STAGES * STAGE_BYTES;           // full[2], empty[2], tmem_full, tmem_empty, tmem base
+    static constexpr int OFF_COL   = OFF_BAR + 64;                      // colsum[4][64]
+    static constexpr int OFF_MU    = OFF_COL + 4 * I8_BN * 8;
+    static constexpr int OFF_TKV   = OFF_MU + I8_BN * 8;
+    static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;
+    static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;
+    static constexpr int OFF_CMASK = OFF_ACQ + I8_BN * 8;
+    static constexpr int OFF_SOB   = OFF_CMASK + 32;
+    static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
+};
+
+struct SweepI8Args {
+    const int8_t* Lp8; const double* rowscale; int8_t* panel8;
+    double dig_scale;       // 2^(6 + 7 (S - 1)) / (power-of-two bound of |k*|): k* -> fixed point
+    double eb_scale;        // eb * 2^-12: folded into the row scale at the drain
+};
+
+// S balanced radix-128 digits of x (|x| <= 1): x ~= sum_s d[s] 2^(-6-7s), rounding only in the last place.
+// xs = x * 2^(6 + 7 (S - 1)) (an exact scaling, folded into the caller's power-of-two scale).
+template <int S>
+__device__ __forceinline__ void i8_digits(double xs, int* d) {
+    long long v = __double2ll_rn(xs);
+#pragma unroll
+    for (int s = S - 1; s > 0; --s) {
+        const int dg = (int)((v + 64) & 127) - 64;
+        d[s] = dg;
+        v = (v - dg) >> 7;
+    }
+    d[0] = (int)v;
+}
+
+// bounded mbarrier wait: a protocol bug must end in a trap (launch failure), never in a hung GPU
+__device__ __forceinline__ void i8_wait(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (uint32_t spin = 0;; ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spin & 1023u) == 1023u && clock64() - t0 > 8000000000LL) {
+            printf("sweep_i8_kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {     // K-major, no swizzle: LBO 128 B (next 16 k), SBO 512 B (next 8 rows)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void i8_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- operand preparation: row scales and int8 slices of L^-1 in stage-tile order --------------------------------
+__global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restrict__ Li, int ld, int np, double* __restrict__ rowscale) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= np) return;
+    double m = 0.0;
+    for (int j = lane; j <= i; j += 32) m = fmax(m, fabs(Li[(size_t)i * ld + j]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        int e; frexp(m, &e);                          // m = f 2^e, f in [0.5, 1): |x| = |L^-1| 2^-e < 1
+        rowscale[i] = (m > 0.0) ? ldexp(1.0, e) : 1.0;
+    }
+}
+
+// one thread per (row, 16-column chunk) of a stage tile: S x 16 B, tile (ib, kc) at ((ib (ib + 1) / 2) * 2 + kc) * S * 8 KB
+template <int S>
+__global__ void __launch_bounds__(256) i8_pack_linv_kernel(const double* __restrict__ Li, int ld, const double* __restrict__ rowscale,
+                                                           int8_t* __restrict__ Lp8, int nbm) {
+    const int ib = blockIdx.y;
+    const int kc = blockIdx.x;                        // 0 .. 2 nbm - 1 ; tiles right of the diagonal block do not exist
+    if (kc >= (ib + 1) * (SW_BM / I8_KC)) return;
+    int8_t* tile = Lp8 + ((size_t)ib * (ib + 1) / 2 * (SW_BM / I8_KC) + kc) * (size_t)(S * I8_A_SLICE);
+    for (int e = threadIdx.x; e < SW_BM * (I8_KC / 16); e += 256) {
+        const int r = e / (I8_KC / 16), ch = e % (I8_KC / 16);
+        const int i = ib * SW_BM + r, j0 = kc * I8_KC + ch * 16;
+        const double inv = ldexp(1.0, 6 + 7 * (S - 1)) / rowscale[i];      // exact: both are powers of two
+        uint32_t w[S][4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t acc[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[s] = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = j0 + q4 * 4 + b;
+                const double x = (j <= i) ? Li[(size_t)i * ld + j] * inv : 0.0;
+                int dg[S];
+                i8_digits<S>(x, dg);
+#pragma unroll
+                for (int s = 0; s < S; ++s) acc[s] |= (uint32_t)(uint8_t)(int8_t)dg[s] << (8 * b);
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) w[s][q4] = acc[s];
+        }
+        const size_t off = ((size_t)(r / 8) * (I8_KC / 16) + ch) * 128 + (r % 8) * 16;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            *reinterpret_cast<uint4*>(tile + (size_t)s * I8_A_SLICE + off) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+// ---- the sweep -------------------------------------------------------------------------------------------------
+template <int DP, int KIND, int S>
+__global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs a, const SweepI8Args b) {
+    using SM = I8Smem<S>;
+    static_assert(S * I8_BN <= 512, "TMEM has 512 columns");
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* empty = full + I8_STAGES;
+    uint64_t* tfull = empty + I8_STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 1);
+    double* colsum  = reinterpret_cast<double*>(smem + SM::OFF_COL);
+    double* mu_s    = reinterpret_cast<double*>(smem + SM::OFF_MU);
+    double* tkv     = reinterpret_cast<double*>(smem + SM::OFF_TKV);
+    long long* tki  = reinterpret_cast<long long*>(smem + SM::OFF_TKI);
+    double* acq_s   = reinterpret_cast<double*>(smem + SM::OFF_ACQ);
+    unsigned* cmask = reinterpret_cast<unsigned*>(smem + SM::OFF_CMASK);
+    uint32_t* dirs  = reinterpret_cast<uint32_t*>(smem + SM::OFF_SOB);
+    uint32_t* shift = dirs + BO_MAX_DIM * BO_SOBOL_BITS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int nbm = a.np / SW_BM;
+    constexpr int KCH = SW_BM / I8_KC;                        // stages per 128 columns
+    constexpr int B_STAGE = S * I8_B_SLICE;
+    int8_t* panel = b.panel8 + (size_t)blockIdx.x * (a.np / I8_KC) * B_STAGE;
+
+    if (tid == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1); mbar_init(tempty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < BO_MAX_TOPK) { tkv[tid] = -INFINITY; tki[tid] = IDX_EMPTY; }
+    if (a.sobol) {
+        for (int e = tid; e < DP * BO_SOBOL_BITS; e += I8_THREADS)
+            dirs[e] = a.sobol->direction[e / BO_SOBOL_BITS][e % BO_SOBOL_BITS];
+        if (tid < DP) shift[tid] = a.sobol->shift[tid];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    int stage = 0; uint32_t phase = 0;        // ring position of the role this thread plays (producer or MMA issuer)
+    uint32_t rb = 0;                          // running row-block counter (accumulator full/empty phases)
+
+    for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+        // ================= phase A: candidates, K(X, X*) digits, posterior mean (warps 0-3) =================
+        if (warp < 4) {
+            double xc[2][DP];
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                long long li = blk * I8_BN + (warp + 4 * gi) * 8 + g;
+                if (li >= a.N) li = a.N - 1;
+                if (a.cand) {
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) xc[gi][k] = (k < a.d) ? a.cand[(size_t)li * a.d + k] : 0.0;
+                } else {
+                    sobol_point<DP>(dirs, shift, a.d, a.first_index + li, xc[gi]);
+                }
+#pragma unroll
+                for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
+            }
+            double mu0 = 0.0, mu1 = 0.0;
+            // X~ and alpha staged through the idle stage buffers (double-buffered cp.async chunks), as in sweep_kernel
+            constexpr int XCH = 512, XP = DP + 2, XBUF = XCH * XP + XCH;
+            static_assert(2 * XBUF * 8 <= I8_STAGES * SM::STAGE_BYTES, "X~ staging must fit into the stage buffers");
+            double* xstage = reinterpret_cast<double*>(smem);
+            const int nrows = a.np;
+            const int nchunks = nrows / XCH + ((nrows % XCH) ? 1 : 0);
+            auto load_chunk = [&](int c) {
+                double* xb = xstage + (c & 1) * XBUF;
+                double* ab = xb + XCH * XP;
+                const int r0 = c * XCH, rows = min(XCH, nrows - r0);
+                for (int e = tid; e < rows * (DP / 2); e += 128) {
+                    const int r = e / (DP / 2), k = e % (DP / 2);
+                    cp_async16(xb + r * XP + 2 * k, a.Xs + (size_t)(r0 + r) * BO_MAX_DIM + 2 * k);
+                }
+                for (int e = tid; e < rows / 2; e += 128) cp_async16(ab + 2 * e, a.alpha + r0 + 2 * e);
+                cp_async_commit();
+            };
+            load_chunk(0);
+            for (int c = 0; c < nchunks; ++c) {
+                if (c + 1 < nchunks) { load_chunk(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const double* xb = xstage + (c & 1) * XBUF;
+                const double* ab = xb + XCH * XP;
+                const int jend = min(nrows, (c + 1) * XCH);
+                // 32 rows per iteration: this lane evaluates rows j0 + 16 h + 4 q + e (h < 2, e < 4) for its two candidates,
+                // i.e. one 32-bit word (4 consecutive k) of every slice per (candidate, h)
+                for (int j0 = c * XCH; j0 < jend; j0 += 32) {
+                    double kv[2][8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int j = j0 + 16 * (r >> 2) + 4 * q + (r & 3);
+                        const int jr = j - c * XCH;
+                        double x[DP];
+                        const double2* row = reinterpret_cast<const double2*>(xb + jr * XP);
+#pragma unroll
+                        for (int k = 0; k < DP / 2; ++k) { const double2 t = row[k]; x[2 * k] = t.x; x[2 * k + 1] = t.y; }
+                        const double al = ab[jr];
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+                            double sq = 0.0;
+#pragma unroll
+                            for (int k = 0; k < DP; ++k) { const double df = xc[gi][k] - x[k]; sq = fma(df, df, sq); }
+                            const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
+                            kv[gi][r] = (j < a.n) ? v : 0.0;
+                        }
+                        mu0 = fma(kv[0][r], al, mu0); mu1 = fma(kv[1][r], al, mu1);
+                    }
+                    int8_t* st_tile = panel + (size_t)(j0 / I8_KC) * B_STAGE;
+                    const int ch0 = (j0 % I8_KC) / 16;
+#pragma unroll
+                    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t w[S];
+#pragma unroll
+                            for (int s = 0; s < S; ++s) w[s] = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                int dg[S];
+                                i8_digits<S>(kv[gi][hh * 4 + e] * b.dig_scale, dg);
+#pragma unroll
+                                for (int s = 0; s < S; ++s) w[s] |= (uint32_t)(uint8_t)(int8_t)dg[s] << (8 * e);
+                            }
+                            const size_t off = ((size_t)(warp + 4 * gi) * (I8_KC / 16) + ch0 + hh) * 128 + g * 16 + q * 4;
+#pragma unroll
+                            for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t*>(st_tile + (size_t)s * I8_B_SLICE + off) = w[s];
+                        }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // buffer free before chunk c + 2 overwrites it
+            }
+            mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
+            mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
+            if (q == 0) { mu_s[warp * 8 + g] = mu0; mu_s[(warp + 4) * 8 + g] = mu1; }
+            __threadfence();
+            fence_proxy_async();      // generic-proxy writes (panel in global, X~ in the stage buffers) -> async proxy
+        }
+        __syncthreads();
+
+        // ================= phase B: ||L^-1 k*||^2 on the INT8 tensor path ============================
+        if (warp == 4) {
+            if (lane == 0) {
+                for (int ib = 0; ib < nbm; ++ib)
+                    for (int kc = 0; kc < (ib + 1) * KCH; ++kc) {
+                        i8_wait(&empty[stage], phase ^ 1);
+                        unsigned char* sb = smem + stage * SM::STAGE_BYTES;
+                        mbar_expect_tx(&full[stage], SM::STAGE_BYTES);
+                        bulk_g2s(sb, b.Lp8 + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * (size_t)(S * I8_A_SLICE), S * I8_A_SLICE, &full[stage]);
+                        bulk_g2s(sb + S * I8_A_SLICE, panel + (size_t)kc * B_STAGE, B_STAGE, &full[stage]);
+                        if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        } else if (warp == 5) {
+            if (lane == 0) {
+                // D = s32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+                const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
+                for (int ib = 0; ib < nbm; ++ib, ++rb) {
+                    i8_wait(tempty, (rb & 1) ^ 1);             // the drain of the previous row block is done
+                    tc_fence_after();
+                    const int nkc = (ib + 1) * KCH;
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        i8_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + stage * SM::STAGE_BYTES), b0 = a0 + S * I8_A_SLICE;
+#pragma unroll 1
+                        for (int s = 0; s < S; ++s)
+#pragma unroll 1
+                            for (int t = 0; t + s < S; ++t)
+#pragma unroll
+                                for (int kk = 0; kk < I8_KC / 32; ++kk)
+                                    i8_mma(tmem_base + (s + t) * I8_BN, i8_desc(a0 + s * I8_A_SLICE + kk * 256),
+                                           i8_desc(b0 + t * I8_B_SLICE + kk * 256), idesc, (kc > 0 || kk > 0 || s > 0) ? 1u : 0u);
+                        i8_commit(&empty[stage]);                // the slot is free once these MMAs have read it
+                        if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    i8_commit(tfull);                            // the accumulators of row block ib are complete
+                }
+            }
+        } else {
+            double acc[I8_BN];
+#pragma unroll
+            for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
+            for (int ib = 0; ib < nbm; ++ib, ++rb) {
+                const double rs = b.rowscale[ib * SW_BM + tid] * b.eb_scale;
+                i8_wait(tfull, rb & 1);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+                for (int c0 = 0; c0 < I8_BN; c0 += 8) {
+                    int v[S][8];
+#pragma unroll
+                    for (int gq = 0; gq < S; ++gq) tmem_ld8(trow + gq * I8_BN + c0, v[gq]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double t = (double)v[S - 1][j];
+#pragma unroll
+                        for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, (double)v[gq][j]);
+                        const double u = t * rs;
+                        acc[c0 + j] = fma(u, u, acc[c0 + j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty);
+            }
+            // sum over the 32 rows of this warp: halving butterfly (each step trades half of the columns held)
+#pragma unroll
+            for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) {
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int c = 0; c < cnt; ++c) {
+                    const double send = upper ? acc[c] : acc[c + cnt];
+                    const double keep = upper ? acc[c + cnt] : acc[c];
+                    acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            // lane l now holds the warp totals of 2 columns; recover which ones from the butterfly's bit order
+            {
+                int base = 0;
+#pragma unroll
+                for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) base += (lane & o) ? cnt : 0;
+                colsum[warp * I8_BN + base] = acc[0];
+                colsum[warp * I8_BN + base + 1] = acc[1];
+            }
+        }
+        __syncthreads();
+
+        // ================= epilogue: variance, acquisition, CTA-local top-k =====================
+        if (tid < I8_BN) {
+            const long long li = blk * I8_BN + tid;
+            const double ss = (colsum[tid] + colsum[I8_BN + tid]) + (colsum[2 * I8_BN + tid] + colsum[3 * I8_BN + tid]);
+            const double var = fmax(a.hyp.outputscale - ss, a.min_var);
+            const double mean = a.hyp.mean + mu_s[tid];
+            double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
+            if (li < a.N) {
+                if (a.mean_out) a.mean_out[li] = mean;
+                if (a.var_out) a.var_out[li] = var;
+                if (a.acq_out) a.acq_out[li] = v;
+            }
+            if (!(v == v)) v = -INFINITY;
+            acq_s[tid] = v;
+            bool beats = false;
+            if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
+            const unsigned m = __ballot_sync(0xffffffffu, beats);
+            if (lane == 0) cmask[warp] = m;
+        }
+        __syncthreads();
+        if (tid == 0 && a.topk > 0) {
+            const int K = a.topk;
+            for (int w = 0; w < I8_BN / 32; ++w) {
+                unsigned m = cmask[w];
+                while (m) {
+                    const int c = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const double v = acq_s[c];
+                    const long long gi = a.first_index + blk * I8_BN + c;
+                    if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
+                    int p = K - 1;
+                    while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
+                    tkv[p] = v; tki[p] = gi;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < BO_MAX_TOPK && a.part_val) {
+        a.part_val[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tkv[tid];
+        a.part_idx[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tki[tid];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+static bool sweep_i8_eligible(const bo_handle* h, const SweepArgs& a) {
+    if (h->svgp || a.hyp.kind == BO_KERNEL_LINEAR_MATERN52) return false;       // stationary kinds: |k*| <= output scale
+    if (a.np / SW_BM < 1) return false;
+    const long long nblocks = (a.N + I8_BN - 1) / I8_BN;
+    return nblocks >= 2LL * h->sm_count;          // whole-block work items only (small pools keep the row-split FP64 path)
+}
+
+template <int S>
+static int ensure_i8_ws(bo_handle* h, int grid) {
+    const int nbm = h->np / SW_BM;
+    const size_t a_bytes = (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
+    if (a_bytes > h->Lp8_bytes) {
+        if (h->Lp8) cudaFree(h->Lp8);
+        h->Lp8 = nullptr; h->Lp8_bytes = 0;
+        BO_CUDA(h, cudaMalloc(&h->Lp8, a_bytes));
+        h->Lp8_bytes = a_bytes;
+    }
+    if ((size_t)h->np > h->rowscale_cap) {
+        if (h->rowscale) cudaFree(h->rowscale);
+        h->rowscale = nullptr; h->rowscale_cap = 0;
+        BO_CUDA(h, cudaMalloc(&h->rowscale, (size_t)h->cap_np * sizeof(double)));
+        h->rowscale_cap = h->cap_np;
+    }
+    const size_t p_bytes = (size_t)grid * (h->np / I8_KC) * (size_t)(S * I8_B_SLICE);
+    if (p_bytes > h->panel8_bytes) {
+        if (h->panel8) cudaFree(h->panel8);
+        h->panel8 = nullptr; h->panel8_bytes = 0;
+        BO_CUDA(h, cudaMalloc(&h->panel8, p_bytes));
+        h->panel8_bytes = p_bytes;
+    }
+    return 0;
+}
+
+template <int DP, int KIND, int S>
+static int launch_sweep_i8_k(bo_handle* h, const SweepArgs& a, const SweepI8Args& b, int grid, cudaStream_t st) {
+    BO_CUDA(h, cudaFuncSetAttribute(sweep_i8_kernel<DP, KIND, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Smem<S>::BYTES));
+    sweep_i8_kernel<DP, KIND, S><<<grid, I8_THREADS, I8Smem<S>::BYTES, st>>>(a, b);
+    BO_LAUNCH_CHECK(h);
+    return 0;
+}
+template <int DP>
+static int launch_sweep_i8(bo_handle* h, const SweepArgs& a, const SweepI8Args& b, int S, int grid, cudaStream_t st) {
+    if (a.hyp.kind == BO_KERNEL_MATERN52)
+        return S == 8 ? launch_sweep_i8_k<DP, BO_KERNEL_MATERN52, 8>(h, a, b, grid, st) : launch_sweep_i8_k<DP, BO_KERNEL_MATERN52, 7>(h, a, b, grid, st);
+    return S == 8 ? launch_sweep_i8_k<DP, BO_KERNEL_RBF, 8>(h, a, b, grid, st) : launch_sweep_i8_k<DP, BO_KERNEL_RBF, 7>(h, a, b, grid, st);
+}
+
+// a: as prepared by sweep_impl (G == 1).  Packs the int8 operands of the current factor, then sweeps.
+static int sweep_i8_run(bo_handle* h, SweepArgs a, int S, double* vals_dev, int64_t* idx_dev, cudaStream_t st) {
+    a.nblocks = (a.N + I8_BN - 1) / I8_BN;
+    const int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
+    int rc;
+    if ((rc = ensure_sweep_ws(h, grid))) return rc;           // per-CTA top-k lists (the FP64 panel is not used)
+    if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid) : ensure_i8_ws<7>(h, grid)))) return rc;
+    const int nbm = h->np / SW_BM;
+    // the factor may have changed since the last call (fit, append, refit): re-slice it every time (~0.1 ms at n = 4096)
+    i8_rowscale_kernel<<<(h->np + 3) / 4, 128, 0, st>>>(h->Li, h->cap_np, h->np, h->rowscale);
+    BO_LAUNCH_CHECK(h);
+    if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
+    else        i8_pack_linv_kernel<7><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
+    BO_LAUNCH_CHECK(h);
+    SweepI8Args b{};
+    b.Lp8 = h->Lp8; b.rowscale = h->rowscale; b.panel8 = h->panel8;
+    int e; frexp(a.hyp.outputscale, &e);                      // |k*| <= outputscale < 2^e
+    b.dig_scale = ldexp(1.0, 6 + 7 * (S - 1) - e);
+    b.eb_scale = ldexp(1.0, e - 12);
+    a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
+    BO_CUDA(h, cudaEventRecord(h->ev0, st));
+    if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep_i8, h, a, b, S, grid, st))) return rc;
+    BO_CUDA(h, cudaEventRecord(h->ev1, st));
+    h->sweep_timed = true;
+    if (a.topk > 0) {
+        topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, a.topk, vals_dev, (long long*)idx_dev);
+        BO_LAUNCH_CHECK(h);
+    }
+    return 0;
+}
