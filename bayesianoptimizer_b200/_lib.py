@@ -63,6 +63,10 @@ SIGNATURES = {
     "bo_fps": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "bo_fp64_peak": (C.c_int, [_vp, _i32, _f64, _pd]),
     "bo_gemm_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _pd]),
+    "bo_set_sweep_mode": (C.c_int, [_vp, _i32]),
+    "bo_resolve_sweep_mode": (C.c_int, [_vp, _i64]),
+    "bo_last_sweep_path": (C.c_int, [_vp]),
+    "bo_i8_peak": (C.c_int, [_vp, _f64, _pd]),
     "bo_launch_count": (C.c_int64, [_vp]),
     "bo_last_sweep_ms": (C.c_double, [_vp]),
 }

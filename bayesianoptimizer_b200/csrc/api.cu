@@ -252,6 +252,26 @@ int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, in
     return gemm_probe_impl(h, m, n, k, cfg, reps, tflops_host);
 }
 
+int bo_set_sweep_mode(bo_handle* h, int32_t mode) {
+    if (!h) return BO_E_INVALID;
+    if (mode < BO_SWEEP_AUTO || mode > BO_SWEEP_I8X8) return fail(h, BO_E_INVALID, "bo_set_sweep_mode: unknown mode");
+    h->sweep_mode = mode;
+    return 0;
+}
+
+int bo_resolve_sweep_mode(const bo_handle* h, int64_t pool_total) {
+    if (!h) return BO_E_INVALID;
+    if (!h->fitted) return BO_E_NOTFIT;
+    return resolve_sweep_mode(h, h->sweep_mode, pool_total);
+}
+
+int bo_last_sweep_path(const bo_handle* h) { return (h && h->sweep_timed) ? h->sweep_path : -1; }
+
+int bo_i8_peak(bo_handle* h, double seconds, double* tops_host) {
+    if (!h || !tops_host) return BO_E_INVALID;
+    return i8_peak_impl(h, seconds, tops_host);
+}
+
 double bo_last_sweep_ms(bo_handle* h) {
     if (!h || !h->sweep_timed) return -1.0;
     cudaSetDevice(h->device);

@@ -110,6 +110,8 @@ struct bo_handle {
     int8_t* Lp8 = nullptr; size_t Lp8_bytes = 0;
     double* rowscale = nullptr; size_t rowscale_cap = 0;
     int8_t* panel8 = nullptr; size_t panel8_bytes = 0;
+    int sweep_mode = BO_SWEEP_AUTO;   // bo_set_sweep_mode
+    int sweep_path = 0;               // contraction of the last sweep: 0 = FP64 DMMA, 7 / 8 = INT8 slices
 
     void* select_ws = nullptr; size_t select_bytes = 0;  // large top-K (select.cu)
 
@@ -287,6 +289,8 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
 int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,
                       double* out_dev, cudaStream_t st);
 int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);
+int i8_peak_impl(bo_handle* h, double seconds, double* tops);
+int resolve_sweep_mode(const bo_handle* h, int mode, long long pool);
 int refit_factor(bo_handle* h, cudaStream_t st);
 int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, const double* ls_host, double outputscale,
                    double linear_variance, double mean, double noise, double jitter, const double* var_mean_dev,

@@ -805,10 +805,20 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
         return 0;
     }
 
-    if (impl && strcmp(impl, "i8") == 0 && sweep_i8_eligible(h, a)) {
-        const char* sl = getenv("BO_B200_I8_SLICES");
-        a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
-        return sweep_i8_run(h, a, (sl && atoi(sl) == 8) ? 8 : 7, vals_dev, idx_dev, st);
+    {
+        // which contraction: the handle's mode (bo_set_sweep_mode), overridable for triage by BO_B200_SWEEP_IMPL=fp64|i8
+        int mode = h->sweep_mode;
+        if (impl && strcmp(impl, "fp64") == 0) mode = BO_SWEEP_FP64;
+        if (impl && strcmp(impl, "i8") == 0) {
+            const char* sl = getenv("BO_B200_I8_SLICES");
+            mode = (sl && atoi(sl) == 8) ? BO_SWEEP_I8X8 : (sl && atoi(sl) == 7) ? BO_SWEEP_I8X7 : BO_SWEEP_AUTO;
+        }
+        mode = resolve_sweep_mode(h, mode, N);
+        if (mode != BO_SWEEP_FP64) {
+            const int S = mode == BO_SWEEP_I8X7 ? 7 : 8;
+            a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
+            return sweep_i8_run(h, a, S, vals_dev, idx_dev, st);
+        }
     }
 
     {
@@ -848,7 +858,7 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     BO_CUDA(h, cudaEventRecord(h->ev0, st));
     if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep, h, a, grid, st))) return rc;
     BO_CUDA(h, cudaEventRecord(h->ev1, st));
-    h->sweep_timed = true;
+    h->sweep_timed = true; h->sweep_path = 0;
     if (topk > 0) {
         topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, topk, vals_dev, (long long*)idx_dev);
         BO_LAUNCH_CHECK(h);

@@ -27,6 +27,7 @@ constexpr int I8_STAGES  = 2;
 constexpr int I8_THREADS = 192;                // warps 0-3: panel build + drain, warp 4: TMA, warp 5: MMA issue
 constexpr int I8_A_SLICE = SW_BM * I8_KC;      // 8 KB
 constexpr int I8_B_SLICE = I8_BN * I8_KC;      // 4 KB
+constexpr int I8_MIN_NP  = 256;                // below this the stage pipeline is all start-up
 
 template <int S>
 struct I8Smem {
@@ -192,11 +193,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
 
+    // flags bit 2: clock64 accounting of where each role waits (printed by CTA 0 at the end; triage only)
+    const bool prof = (a.flags & 4) != 0;
+    long long t_a = 0, t_b = 0, t_w0 = 0, t_w1 = 0;
     int stage = 0; uint32_t phase = 0;        // ring position of the role this thread plays (producer or MMA issuer)
     uint32_t rb = 0;                          // running row-block counter (accumulator full/empty phases)
 
     for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
         // ================= phase A: candidates, K(X, X*) digits, posterior mean (warps 0-3) =================
+        const long long tA0 = prof ? clock64() : 0;
         if (warp < 4) {
             double xc[2][DP];
 #pragma unroll
@@ -290,13 +295,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             fence_proxy_async();      // generic-proxy writes (panel in global, X~ in the stage buffers) -> async proxy
         }
         __syncthreads();
+        const long long tB0 = prof ? clock64() : 0;
+        t_a += tB0 - tA0;
 
         // ================= phase B: ||L^-1 k*||^2 on the INT8 tensor path ============================
         if (warp == 4) {
             if (lane == 0) {
                 for (int ib = 0; ib < nbm; ++ib)
                     for (int kc = 0; kc < (ib + 1) * KCH; ++kc) {
+                        const long long w0 = prof ? clock64() : 0;
                         i8_wait(&empty[stage], phase ^ 1);
+                        if (prof) t_w0 += clock64() - w0;
                         unsigned char* sb = smem + stage * SM::STAGE_BYTES;
                         mbar_expect_tx(&full[stage], SM::STAGE_BYTES);
                         bulk_g2s(sb, b.Lp8 + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * (size_t)(S * I8_A_SLICE), S * I8_A_SLICE, &full[stage]);
@@ -309,11 +318,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                 // D = s32, A = B = signed 8 bit, both K-major, N = 64, M = 128
                 const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
                 for (int ib = 0; ib < nbm; ++ib, ++rb) {
+                    const long long w1 = prof ? clock64() : 0;
                     i8_wait(tempty, (rb & 1) ^ 1);             // the drain of the previous row block is done
+                    if (prof) t_w1 += clock64() - w1;
                     tc_fence_after();
                     const int nkc = (ib + 1) * KCH;
                     for (int kc = 0; kc < nkc; ++kc) {
+                        const long long w0 = prof ? clock64() : 0;
                         i8_wait(&full[stage], phase);
+                        if (prof) t_w0 += clock64() - w0;
                         tc_fence_after();
                         const uint32_t a0 = smem_u32(smem + stage * SM::STAGE_BYTES), b0 = a0 + S * I8_A_SLICE;
 #pragma unroll 1
@@ -336,7 +349,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
             for (int ib = 0; ib < nbm; ++ib, ++rb) {
                 const double rs = b.rowscale[ib * SW_BM + tid] * b.eb_scale;
+                const long long w0 = prof ? clock64() : 0;
                 i8_wait(tfull, rb & 1);
+                if (prof) t_w0 += clock64() - w0;
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
@@ -357,6 +372,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty);
+                if (prof) t_w1 += clock64() - w0;
             }
             // sum over the 32 rows of this warp: halving butterfly (each step trades half of the columns held)
 #pragma unroll
@@ -379,6 +395,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             }
         }
         __syncthreads();
+        if (prof) t_b += clock64() - tB0;
 
         // ================= epilogue: variance, acquisition, CTA-local top-k =====================
         if (tid < I8_BN) {
@@ -418,6 +435,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
         }
         __syncthreads();
     }
+    if (prof && blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 160))
+        printf("sweep_i8 CTA 0 %s: phase A %lld clk, phase B %lld clk; waits: %s %lld clk, %s %lld clk\n",
+               tid == 0 ? "drain warp 0" : tid == 128 ? "TMA producer" : "MMA issuer", t_a, t_b,
+               tid == 0 ? "accumulators-full" : tid == 128 ? "slot-empty" : "stage-full", t_w0,
+               tid == 0 ? "(drain total incl. wait)" : tid == 128 ? "-" : "accumulators-drained", t_w1);
     if (tid < BO_MAX_TOPK && a.part_val) {
         a.part_val[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tkv[tid];
         a.part_idx[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tki[tid];
@@ -429,11 +451,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
-static bool sweep_i8_eligible(const bo_handle* h, const SweepArgs& a) {
-    if (h->svgp || a.hyp.kind == BO_KERNEL_LINEAR_MATERN52) return false;       // stationary kinds: |k*| <= output scale
-    if (a.np / SW_BM < 1) return false;
-    const long long nblocks = (a.N + I8_BN - 1) / I8_BN;
-    return nblocks >= 2LL * h->sm_count;          // whole-block work items only (small pools keep the row-split FP64 path)
+// the model side of eligibility: exact GP with a stationary kernel (|k*| <= output scale), more than one stage of rows
+static bool sweep_i8_model_ok(const bo_handle* h) {
+    return h->fitted && !h->svgp && h->hyp.kind != BO_KERNEL_LINEAR_MATERN52 && h->np >= I8_MIN_NP;
+}
+
+// Slice count from the error model (tools/ozaki_feasibility.py): the relative error of sigma^2 is the slicing
+// error of u (~ 2^(-7 S) times the row scales of L^-1 ~ (noise)^-1/2) over the smallest variance the model can
+// return (~ noise), i.e. ~ (noise / outputscale)^-3/2: 3e-10 at ratio 1e-3 with 7 slices (C3 shape, measured), 1e-8 at
+// ratio 1e-4.  7 slices while the model keeps 10x margin to the 1e-8 bar; 8 slices (as accurate as the FP64 product,
+// 36 instead of 28 slice products) otherwise.
+static int sweep_i8_slices(const Hyper& hyp) {
+    const double ratio = (hyp.noise + hyp.jitter) / hyp.outputscale;
+    return ratio >= 1e-3 ? 7 : 8;
+}
+
+// The pinned mode a sweep over a pool of `pool` candidates runs in.  Pinned modes depend on the model only, so every
+// shard of a pool takes the same path and the per-candidate values are bit-identical for every shard layout; AUTO also
+// looks at the pool size (small pools keep the row-split FP64 kernel, which fills the SMs with fewer than two waves of
+// 64-candidate blocks) -- callers that shard a pool resolve AUTO once on the global size (bo_resolve_sweep_mode).
+int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
+    if (mode == BO_SWEEP_FP64 || !sweep_i8_model_ok(h)) return BO_SWEEP_FP64;
+    if (mode == BO_SWEEP_I8X7 || mode == BO_SWEEP_I8X8) return mode;
+    if ((pool + I8_BN - 1) / I8_BN < 2LL * h->sm_count) return BO_SWEEP_FP64;
+    return sweep_i8_slices(h->hyp) == 7 ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;
 }
 
 template <int S>
@@ -499,10 +540,85 @@ static int sweep_i8_run(bo_handle* h, SweepArgs a, int S, double* vals_dev, int6
     BO_CUDA(h, cudaEventRecord(h->ev0, st));
     if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep_i8, h, a, b, S, grid, st))) return rc;
     BO_CUDA(h, cudaEventRecord(h->ev1, st));
-    h->sweep_timed = true;
+    h->sweep_timed = true; h->sweep_path = S;
     if (a.topk > 0) {
         topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, a.topk, vals_dev, (long long*)idx_dev);
         BO_LAUNCH_CHECK(h);
     }
+    return 0;
+}
+
+// ---- INT8 tensor-pipe peak probe (roofline denominator for the sliced sweep): 128 x 256 x 32 MMAs on resident operands ----
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
+    constexpr int N = 256, KC = 64;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (SW_BM + N) * KC / 4; i += 128) {
+        uint32_t hsh = (uint32_t)i * 0x9E3779B1u; hsh ^= hsh >> 15; hsh *= 0x2C1B3C6Du; hsh ^= hsh >> 12;
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) w |= (uint32_t)(uint8_t)(int8_t)((int)((hsh >> (8 * b)) & 127u) - 64) << (8 * b);
+        reinterpret_cast<uint32_t*>(smem)[i] = w;
+    }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + SW_BM * KC;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int kk = 0; kk < KC / 32; ++kk)
+                    i8_mma(tmem_base + (r & 1) * N, i8_desc(a0 + kk * 256), i8_desc(b0 + kk * 256), idesc, (it | r | kk) ? 1u : 0u);
+            i8_commit(&bars[it & 1]);
+            if (it > 0) i8_wait(&bars[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        }
+        i8_wait(&bars[(iters - 1) & 1], ((iters - 1) >> 1) & 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+int i8_peak_impl(bo_handle* h, double seconds, double* tops) {
+    BO_CUDA(h, cudaSetDevice(h->device));
+    const int smem_bytes = (SW_BM + 256) * 64, iters = 4000;
+    BO_CUDA(h, cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const double ops_per_launch = (double)h->sm_count * iters * 16.0 * SW_BM * 256 * 32 * 2.0;
+    cudaEvent_t e0, e1;
+    BO_CUDA(h, cudaEventCreate(&e0));
+    BO_CUDA(h, cudaEventCreate(&e1));
+    auto launch = [&]() { i8_peak_kernel<<<h->sm_count, 128, smem_bytes>>>(iters); h->launches++; };
+    launch();
+    BO_CUDA(h, cudaDeviceSynchronize());
+    BO_CUDA(h, cudaEventRecord(e0));
+    launch();
+    BO_CUDA(h, cudaEventRecord(e1));
+    BO_CUDA(h, cudaEventSynchronize(e1));
+    float ms1 = 0.f;
+    BO_CUDA(h, cudaEventElapsedTime(&ms1, e0, e1));
+    int reps = (int)(seconds * 1e3 / (ms1 > 0.01f ? ms1 : 0.01f));
+    reps = reps < 1 ? 1 : reps > 2000 ? 2000 : reps;
+    BO_CUDA(h, cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) launch();
+    BO_CUDA(h, cudaEventRecord(e1));
+    BO_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    BO_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+    BO_CUDA(h, cudaGetLastError());
+    *tops = ops_per_launch * reps / (ms * 1e-3) * 1e-12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }

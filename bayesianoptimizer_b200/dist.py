@@ -60,11 +60,18 @@ def sharded_sweep(engine, acq, best_f, beta, sobol, total: int, topk: int, rank:
                   group=None, host: bool = False):
     """Score this rank's shard of a Sobol pool of ``total`` candidates and return the GLOBAL top-k."""
     first, count = shard_range(total, rank, world)
-    if host:
-        v, i = engine.sweep_host(acq, best_f, beta, sobol=sobol, first_index=first, count=count, topk=topk)
-        v, i = v.to(engine.device), i.to(engine.device)
-    else:
-        v, i = engine.sweep(acq, best_f, beta, sobol=sobol, first_index=first, count=count, topk=topk)
+    # the contraction mode is resolved on the GLOBAL pool size and pinned, so every rank takes the same path whatever
+    # its shard size (per-candidate values are then bit-identical for every GPU count)
+    saved = engine.sweep_mode
+    engine.set_sweep_mode(engine.resolve_sweep_mode(total))
+    try:
+        if host:
+            v, i = engine.sweep_host(acq, best_f, beta, sobol=sobol, first_index=first, count=count, topk=topk)
+            v, i = v.to(engine.device), i.to(engine.device)
+        else:
+            v, i = engine.sweep(acq, best_f, beta, sobol=sobol, first_index=first, count=count, topk=topk)
+    finally:
+        engine.set_sweep_mode(saved)
     if world == 1:
         return v, i
     return allgather_topk(v, i, topk, group)

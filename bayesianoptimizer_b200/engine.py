@@ -23,6 +23,7 @@ MIN_VARIANCE = 1e-6   # gpytorch settings.min_variance (double)
 _KERNELS = {"matern52": KERNEL_MATERN52, "matern": KERNEL_MATERN52, "rbf": KERNEL_RBF,
             "linear_matern52": KERNEL_LINEAR_MATERN52, "linear+matern52": KERNEL_LINEAR_MATERN52,
             KERNEL_MATERN52: KERNEL_MATERN52, KERNEL_RBF: KERNEL_RBF, KERNEL_LINEAR_MATERN52: KERNEL_LINEAR_MATERN52}
+SWEEP_MODES = {"auto": 0, "fp64": 1, "i8x7": 2, "i8x8": 3}   # BO_SWEEP_* of include/bo_b200.h
 _ACQS = {"ei": ACQ_EI, "logei": ACQ_LOGEI, "ucb": ACQ_UCB, "var": ACQ_VAR, "mean": ACQ_MEAN,
          ACQ_EI: ACQ_EI, ACQ_LOGEI: ACQ_LOGEI, ACQ_UCB: ACQ_UCB, ACQ_VAR: ACQ_VAR, ACQ_MEAN: ACQ_MEAN}
 
@@ -67,6 +68,7 @@ class GPEngine:
         if rc != 0:
             raise BoError(rc, "bo_create failed (no usable sm_100 device?)")
         self._h = h
+        self.sweep_mode = "auto"
         self.n = 0
         self.d = 0
 
@@ -326,6 +328,28 @@ class GPEngine:
         out = C.c_double(0.0)
         self._check(self._lib.bo_gemm_probe(self._h, m, n, k, cfg, reps, C.byref(out)))
         return out.value
+
+    def i8_peak_tops(self, seconds: float = 0.3) -> float:
+        out = C.c_double(0.0)
+        self._check(self._lib.bo_i8_peak(self._h, float(seconds), C.byref(out)))
+        return out.value
+
+    def set_sweep_mode(self, mode: str = "auto"):
+        """Contraction of the sweep's variance term: "auto" (INT8-sliced tensor path for large pools, FP64 DMMA otherwise),
+        "fp64", "i8x7", "i8x8" (bo_set_sweep_mode)."""
+        self._check(self._lib.bo_set_sweep_mode(self._h, SWEEP_MODES[mode]))
+        self.sweep_mode = mode
+
+    def resolve_sweep_mode(self, pool_total: int) -> str:
+        """The pinned mode the current mode resolves to for a pool of ``pool_total`` candidates (bo_resolve_sweep_mode):
+        sharded callers resolve once on the global pool size and pin the result for every shard."""
+        rc = int(self._lib.bo_resolve_sweep_mode(self._h, int(pool_total)))
+        self._check(min(rc, 0))
+        return {v: k for k, v in SWEEP_MODES.items()}[rc]
+
+    def last_sweep_path(self) -> int:
+        """0 = FP64 DMMA, 7 / 8 = INT8-sliced with that many slices, -1 = no sweep yet."""
+        return int(self._lib.bo_last_sweep_path(self._h))
 
     def launch_count(self) -> int:
         return int(self._lib.bo_launch_count(self._h))

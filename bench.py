@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--pool", type=int, default=POOL, help="candidate pool size (default: the BASELINE 10^7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-mode", default="auto", choices=["auto", "fp64", "i8x7", "i8x8"],
+                    help="variance contraction of the sweep (bo_set_sweep_mode); auto resolves on the global pool size")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -243,6 +245,12 @@ def main():
     refit_ms = float(np.median(fit_ms))
 
     peak_tflops = eng.fp64_peak_tflops(True, 0.5)     # FP64 DMMA roof, measured live (MEASURED_PEAKS.json has no FP64 entry)
+    # contraction mode: resolved once on the GLOBAL pool size and pinned, so every rank's shard takes the same path
+    eng.set_sweep_mode(args.sweep_mode)
+    mode = eng.resolve_sweep_mode(pool)
+    eng.set_sweep_mode(mode)
+    slices = {"fp64": 0, "i8x7": 7, "i8x8": 8}[mode]
+    peak_tops = eng.i8_peak_tops(0.5) if slices else None       # INT8 tensor-pipe roof (tcgen05 kind::i8), measured live
 
     def step_resident():
         v, i = eng.sweep("ei", best_f, 2.0, sobol=sob, first_index=first, count=count, topk=TOPK)
@@ -291,6 +299,19 @@ def main():
     e2e_local_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
+    # the FP64 DMMA contraction beside the sliced one (N = 1 only): one warm + one timed sweep over a tenth of the pool
+    fp64_side = None
+    if slices and world == 1:
+        eng.set_sweep_mode("fp64")
+        sub = max(pool // 10, 1)
+        for _ in range(2):
+            eng.sweep("ei", best_f, 2.0, sobol=sob, first_index=0, count=sub, topk=TOPK)
+            torch.cuda.synchronize()
+        ms = eng.last_sweep_ms()
+        fp64_side = {"value": sub / (ms * 1e-3), "unit": UNIT, "pool": sub, "kernel_ms": ms,
+                     "frac_of_fp64_dmma_peak": sub * flops_per_candidate(N_OBS, DIM) / (ms * 1e-3) * 1e-12 / peak_tflops}
+        eng.set_sweep_mode(mode)
+
     t = torch.tensor([elapsed_ms, e2e_local_ms, float(np.mean(kernel_ms)), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -311,9 +332,37 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_candidate") * count     # per launch of this shard
+                tj = json.load(open(tpath))
+                per_cand = tj.get("i8", {}).get("dram_bytes_per_candidate") if slices else tj.get("dram_bytes_per_candidate")
+                traffic = per_cand * count if per_cand else None                              # per launch of this shard
             except Exception:
                 traffic = None
+        kms = float(np.mean(kernel_ms))
+        if slices:
+            # dominant kernel = sweep_i8_kernel: it runs on the INT8 tensor pipe.  Ops it executes per candidate: every
+            # 128 x 64 stage of the lower-triangular block structure, S (S + 1) / 2 slice products, 2 ops per MAC.
+            npad = (N_OBS + 127) // 128 * 128
+            int8_ops_per_cand = 2.0 * (slices * (slices + 1) // 2) * npad * (npad + 128) / 2
+            a_tops = count * int8_ops_per_cand / (kms * 1e-3) * 1e-12
+            roofline = {"bound": "tensor", "achieved": a_tops, "peak": peak_tops, "unit": "TOP/s", "frac": a_tops / peak_tops,
+                        "traffic": traffic,
+                        "kernel": f"sweep_i8_kernel<8, matern52, {slices}> (tcgen05.mma kind::i8, INT32 accumulators in TMEM)",
+                        "peak_source": "INT8 tensor-pipe peak measured live by bo_i8_peak (tcgen05.mma kind::i8 128x256x32 on resident "
+                                       "operands); MEASURED_PEAKS.json has no INT8 entry",
+                        "int8_ops_per_candidate": int8_ops_per_cand, "kernel_ms": kms,
+                        "note": "the FP64 contraction u = L^-1 k* runs as an error-free product of signed 7-bit slices; TMEM (512 "
+                                "columns) limits the tile to 64 candidates x S accumulators, an MMA shape that reaches about half of "
+                                "the INT8 peak (profiles/r01_int8_tcgen05_probe.log)",
+                        "fp64_equivalent": {"achieved_tflops": achieved, "fp64_dmma_peak_tflops": peak_tflops,
+                                            "ratio_to_fp64_dmma_peak": achieved / peak_tflops, "flop_per_candidate": fpc,
+                                            "fp64_dmma_path": fp64_side}}
+        else:
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                        "frac": achieved / peak_tflops, "traffic": traffic,
+                        "kernel": "sweep_kernel<8> (FP64 DMMA.8x8x4 pipe)",
+                        "peak_source": "FP64 DMMA peak measured live by bo_fp64_peak (register-resident DMMA.8x8x4 loop); "
+                                       "MEASURED_PEAKS.json has no FP64 entry",
+                        "flop_per_candidate": fpc, "kernel_ms": kms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -321,19 +370,18 @@ def main():
             "config": {"workload": "C3: synthetic d=8 n_obs=4096 Matern-5/2 ARD, EI over a 10^7 in-kernel scrambled-Sobol "
                                    "pool sharded contiguously over the GPUs, top-1 + one (value,index) all-gather",
                        "n_obs": N_OBS, "d": DIM, "pool": pool, "acq": "EI", "parallelism": f"candidate-shard x{world}",
-                       "l2": "inputs larger than L2: 67 MB packed L^-1 + 620 MB K* panels streamed every wave"},
+                       "contraction": ("FP64 DMMA" if not slices else
+                                       f"{slices} signed 7-bit slices per operand on INT8 tensor cores, exact INT32 accumulation, "
+                                       f"FP64 recombination (bo_set_sweep_mode {mode}, resolved from --sweep-mode {args.sweep_mode})"),
+                       "l2": ("inputs larger than L2: 67 MB packed L^-1 + 620 MB K* panels streamed every wave" if not slices else
+                              "inputs larger than L2: 59 MB of L^-1 slices + 266 MB of K* slice panels streamed every wave")},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(world * (N_OBS * DIM * 8 + N_OBS * 8 + 2052)),
                     "d2h_bytes_per_step": int(world * TOPK * 16),
                     "includes": "bo_fit_host (H2D X,y + refit) + bo_sweep_host (sweep + D2H winner) + all-gather"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": traffic,
-                         "kernel": "sweep_kernel<8> (FP64 DMMA.8x8x4 pipe)",
-                         "peak_source": "FP64 DMMA peak measured live by bo_fp64_peak (register-resident DMMA.8x8x4 loop); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
-                         "flop_per_candidate": fpc, "kernel_ms": float(np.mean(kernel_ms))},
+            "roofline": roofline,
             "refit_ms": refit_ms, "suggest_ms": ms_per_step,
             "argmax": {"value": winner[0], "index": winner[1]},
         }

@@ -52,6 +52,13 @@ extern "C" {
 #define BO_ACQ_VAR   3   /* posterior variance score (active-learning sweep,      Bayesian7.py:670-671) */
 #define BO_ACQ_MEAN  4   /* posterior mean                                                              */
 
+/* contraction used by bo_sweep for the variance term u = L^-1 k* (bo_set_sweep_mode) */
+#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path for large pools of a stationary-kernel exact GP (slice count from
+                           * the error model, see bo_set_sweep_mode), FP64 DMMA otherwise */
+#define BO_SWEEP_FP64 1   /* always the FP64 DMMA contraction */
+#define BO_SWEEP_I8X7 2   /* INT8-sliced with 7 slices wherever eligible */
+#define BO_SWEEP_I8X8 3   /* INT8-sliced with 8 slices wherever eligible */
+
 /* error codes (negative statuses) */
 #define BO_E_INVALID  (-1)  /* bad argument                                  */
 #define BO_E_CUDA     (-2)  /* CUDA runtime error / no usable device         */
@@ -210,6 +217,28 @@ int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_
 /* Throughput probe of the fit's grouped FP64 DMMA GEMM (C = A B^T + C, one m x n x k problem; cfg 0: 64x64 tiles,
  * 1: 128x128, 2: 128x64).  Returns TFLOP/s in *tflops_host.  Diagnostic only. */
 int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, int32_t reps, double* tflops_host);
+
+/* Choose how bo_sweep contracts L^-1 with the K(X, X*) panel (BO_SWEEP_*; default BO_SWEEP_AUTO).  The INT8-sliced path
+ * computes the same FP64 quantity: both operands are cut into S signed 7-bit slices (error-free, Ozaki scheme I), the
+ * S (S + 1) / 2 leading slice products run on the INT8 tensor cores (tcgen05.mma kind::i8) with exact INT32
+ * accumulation and are recombined in FP64.  8 slices reproduce the FP64 product to its own rounding level; 7 slices
+ * (chosen by AUTO when noise / outputscale >= 1e-3) stay below 1e-9 relative on the variance.  Eligible models: exact GP,
+ * Matern-5/2 or RBF kind, at least 256 (padded) observations; every other model runs the FP64 DMMA path in every mode.
+ * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
+ * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates on the FP64 path. */
+int bo_set_sweep_mode(bo_handle* h, int32_t mode);
+
+/* The pinned mode (BO_SWEEP_FP64 / I8X7 / I8X8) the handle's current mode resolves to for a pool of pool_total
+ * candidates of the fitted model: callers that shard one pool over several calls or GPUs resolve once on the global
+ * size and pin the result, so that every shard takes the same path. */
+int bo_resolve_sweep_mode(const bo_handle* h, int64_t pool_total);
+
+/* Contraction the last bo_sweep ran: 0 = FP64 DMMA, 7 / 8 = INT8-sliced with that many slices, -1 = no sweep yet. */
+int bo_last_sweep_path(const bo_handle* h);
+
+/* INT8 tensor-pipe peak probe (tcgen05.mma kind::i8, 128 x 256 x 32 on resident operands): roofline denominator
+ * of the sliced sweep.  Returns TOP/s (multiply and add counted separately) in *tops_host. */
+int bo_i8_peak(bo_handle* h, double seconds, double* tops_host);
 
 /* Kernel-launch counter (own kernels launched through this handle since creation). */
 int64_t bo_launch_count(const bo_handle* h);

@@ -20,11 +20,20 @@ def _sobol_arrays(sob):
 class OracleEngine:
     device = torch.device("cpu")
 
+    sweep_mode = "fp64"
+
     def __init__(self):
         self.gp = None
         self.svgp = None
         self.n = self.d = 0
         self.fits = 0
+
+    # the oracle has one (FP64) contraction; the mode interface of GPEngine is accepted and ignored
+    def set_sweep_mode(self, mode="auto"):
+        self.sweep_mode = mode
+
+    def resolve_sweep_mode(self, pool_total):
+        return "fp64"
 
     def fit(self, X, y, kernel="matern52", lengthscale=1.0, outputscale=1.0, noise=1e-3, mean=0.0, jitter=0.0,
             linear_variance=0.0):

@@ -181,24 +181,30 @@ def test_not_positive_definite_status_and_jitter_retry(engine):
 
 
 def test_shard_merge_equals_single_sweep(engine):
-    """Candidate sharding invariant: merging per-shard top-k lists reproduces the G=1 result."""
+    """Candidate sharding invariant: merging per-shard top-k lists reproduces the G=1 result.  The
+    contraction mode is resolved once on the global pool size and pinned, as dist.sharded_sweep does (AUTO alone would
+    send shards below its pool threshold down the FP64 path); tests/test_gpu_i8.py repeats this for every pinned mode."""
     from bayesianoptimizer_b200 import sobol_state
     X, y = synth_problem(384, 6, 21, 22)
     engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", 0.7, 1.0, 1e-3)
     st = sobol_state(6, 17)
     N, k = 50_000, 8
-    v1, i1 = engine.sweep("ei", float(y.max()), sobol=st, first_index=0, count=N, topk=k)
-    for G in (2, 3, 8):
-        per = -(-N // G)
-        vs, is_ = [], []
-        for r in range(G):
-            lo = r * per
-            cnt = max(0, min(per, N - lo))
-            v, i = engine.sweep("ei", float(y.max()), sobol=st, first_index=lo, count=cnt, topk=k)
-            vs.append(v.cpu().numpy()); is_.append(i.cpu().numpy())
-        mv, mi = o.merge_topk(vs, is_, k)
-        assert mi.tolist() == i1.cpu().tolist()
-        assert np.array_equal(mv, v1.cpu().numpy())
+    engine.set_sweep_mode(engine.resolve_sweep_mode(N))
+    try:
+        v1, i1 = engine.sweep("ei", float(y.max()), sobol=st, first_index=0, count=N, topk=k)
+        for G in (2, 3, 8):
+            per = -(-N // G)
+            vs, is_ = [], []
+            for r in range(G):
+                lo = r * per
+                cnt = max(0, min(per, N - lo))
+                v, i = engine.sweep("ei", float(y.max()), sobol=st, first_index=lo, count=cnt, topk=k)
+                vs.append(v.cpu().numpy()); is_.append(i.cpu().numpy())
+            mv, mi = o.merge_topk(vs, is_, k)
+            assert mi.tolist() == i1.cpu().tolist()
+            assert np.array_equal(mv, v1.cpu().numpy())
+    finally:
+        engine.set_sweep_mode("auto")
 
 
 def test_full_size_c3_sample_against_oracle(engine):
