@@ -57,3 +57,14 @@ def assert_acq_close(kind, val, ref):
     else:
         err = np.abs(val - ref) / (RTOL_ACQ * np.abs(ref) + 1e-300)
     assert err.max() <= 1.0, f"{kind} off by {err.max():.3g}x tolerance at {err.argmax()}"
+
+
+def assert_ei_close_conditioned(kind, val, ref, mu_ref, var_ref, best_f):
+    """EI / LogEI deep in the tail are ill-conditioned: d log EI / d u ~ -u with u = (mu - best_f) / sigma, so the relative
+    error of EI (= the absolute error of LogEI) inherits the 1e-8 relative tolerance of mean and sigma amplified by
+    1 + |u| + u^2 (same rule as tools/fuzz_parity.py)."""
+    val, ref = np.asarray(val, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    u = (np.asarray(mu_ref) - best_f) / np.sqrt(np.asarray(var_ref))
+    tol = RTOL_ACQ + 3.0 * RTOL_POST * (1.0 + np.abs(u) + u * u)
+    err = np.abs(val - ref) / (tol if kind == "logei" else tol * np.abs(ref) + 1e-300)
+    assert err.max() <= 1.0, f"{kind} off by {err.max():.3g}x conditioned tolerance at {err.argmax()} (u = {u[err.argmax()]:.3g})"

@@ -4,7 +4,7 @@ identical top-k unless the oracle's own gap is below tolerance)."""
 import numpy as np
 import pytest
 
-from conftest import assert_acq_close, assert_posterior_close, synth_problem
+from conftest import assert_acq_close, assert_ei_close_conditioned, assert_posterior_close, synth_problem
 from oracle import gp_oracle as o
 
 pytestmark = pytest.mark.gpu
@@ -54,7 +54,10 @@ def test_i8_sobol_sweep_against_oracle(engine, n, d, N, kind, mode, path):
         vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, sobol=st, first_index=first, count=N, topk=k, return_all=True)
         assert engine.last_sweep_path() == path
         assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
-        assert_acq_close(acq, ga.cpu().numpy(), av)
+        if acq in ("ei", "logei"):
+            assert_ei_close_conditioned(acq, ga.cpu().numpy(), av, mu, var, bf)
+        else:
+            assert_acq_close(acq, ga.cpu().numpy(), av)
         got = idx.cpu().numpy()
         for r in range(k):
             if got[r] != ti[r]:
