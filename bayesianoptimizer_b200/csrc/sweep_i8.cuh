@@ -84,6 +84,11 @@ __device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ bool i8_elect() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void i8_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -314,33 +319,40 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                     }
             }
         } else if (warp == 5) {
-            if (lane == 0) {
-                // D = s32, A = B = signed 8 bit, both K-major, N = 64, M = 128
-                const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
-                for (int ib = 0; ib < nbm; ++ib, ++rb) {
-                    const long long w1 = prof ? clock64() : 0;
-                    i8_wait(tempty, (rb & 1) ^ 1);             // the drain of the previous row block is done
-                    if (prof) t_w1 += clock64() - w1;
+            // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
+            // lane issues.  The slice-pair loops are fully unrolled: every descriptor is the stage's base descriptor plus a
+            // compile-time constant, so an MMA costs a few integer instructions to issue -- with rolled loops the issuing
+            // thread, not the tensor core, set the pace (a 64-column MMA lasts ~34 cycles).
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
+            const bool leader = i8_elect();
+            for (int ib = 0; ib < nbm; ++ib, ++rb) {
+                const long long w1 = prof ? clock64() : 0;
+                i8_wait(tempty, (rb & 1) ^ 1);             // the drain of the previous row block is done
+                if (prof) t_w1 += clock64() - w1;
+                tc_fence_after();
+                const int nkc = (ib + 1) * KCH;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    const long long w0 = prof ? clock64() : 0;
+                    i8_wait(&full[stage], phase);
+                    if (prof) t_w0 += clock64() - w0;
                     tc_fence_after();
-                    const int nkc = (ib + 1) * KCH;
-                    for (int kc = 0; kc < nkc; ++kc) {
-                        const long long w0 = prof ? clock64() : 0;
-                        i8_wait(&full[stage], phase);
-                        if (prof) t_w0 += clock64() - w0;
-                        tc_fence_after();
-                        const uint32_t a0 = smem_u32(smem + stage * SM::STAGE_BYTES), b0 = a0 + S * I8_A_SLICE;
-#pragma unroll 1
+                    const uint32_t a0 = smem_u32(smem + stage * SM::STAGE_BYTES);
+                    const uint64_t da0 = i8_desc(a0), db0 = i8_desc(a0 + S * I8_A_SLICE);
+                    const uint32_t acc0 = kc > 0 ? 1u : 0u;
+                    if (leader) {
+#pragma unroll
                         for (int s = 0; s < S; ++s)
-#pragma unroll 1
+#pragma unroll
                             for (int t = 0; t + s < S; ++t)
 #pragma unroll
                                 for (int kk = 0; kk < I8_KC / 32; ++kk)
-                                    i8_mma(tmem_base + (s + t) * I8_BN, i8_desc(a0 + s * I8_A_SLICE + kk * 256),
-                                           i8_desc(b0 + t * I8_B_SLICE + kk * 256), idesc, (kc > 0 || kk > 0 || s > 0) ? 1u : 0u);
+                                    i8_mma(tmem_base + (s + t) * I8_BN, da0 + (uint64_t)((s * I8_A_SLICE + kk * 256) >> 4),
+                                           db0 + (uint64_t)((t * I8_B_SLICE + kk * 256) >> 4), idesc, (kk > 0 || s > 0) ? 1u : acc0);
                         i8_commit(&empty[stage]);                // the slot is free once these MMAs have read it
-                        if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+                        if (kc == nkc - 1) i8_commit(tfull);     // the accumulators of row block ib are complete
                     }
-                    i8_commit(tfull);                            // the accumulators of row block ib are complete
+                    __syncwarp();
+                    if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         } else {
