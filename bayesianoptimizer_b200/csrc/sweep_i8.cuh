@@ -24,25 +24,30 @@
 constexpr int I8_BN      = 64;                 // candidates per CTA tile (TMEM: S * 64 columns)
 constexpr int I8_KC      = 64;                 // contraction bytes per pipeline stage
 constexpr int I8_STAGES  = 2;
-constexpr int I8_THREADS = 192;                // warps 0-3: panel build + drain, warp 4: TMA, warp 5: MMA issue
+constexpr int I8_THREADS = 384;                // warpgroup 0 (warps 0-3): drain + epilogue; 1: warp 4 TMA, warp 5 MMA issue, 6-7 idle; 2 (warps 8-11): panel builders
 constexpr int I8_A_SLICE = SW_BM * I8_KC;      // 8 KB
 constexpr int I8_B_SLICE = I8_BN * I8_KC;      // 4 KB
 constexpr int I8_MIN_NP  = 256;                // below this the stage pipeline is all start-up
 
-template <int S>
+template <int S, int DP>
 struct I8Smem {
     static constexpr int STAGE_BYTES = S * (I8_A_SLICE + I8_B_SLICE);
-    static constexpr int OFF_BAR   = I8_STAGES * STAGE_BYTES;           // full[2], empty[2], tmem_full, tmem_empty, tmem base
-    static constexpr int OFF_COL   = OFF_BAR + 64;                      // colsum[4][64]
-    static constexpr int OFF_MU    = OFF_COL + 4 * I8_BN * 8;
-    static constexpr int OFF_TKV   = OFF_MU + I8_BN * 8;
+    static constexpr int OFF_BAR   = I8_STAGES * STAGE_BYTES;           // full[2], empty[2], tmem full/empty, panel full[2]/empty[2], tmem base
+    static constexpr int OFF_COL   = OFF_BAR + 128;                     // colsum[4][64]
+    static constexpr int OFF_MU    = OFF_COL + 4 * I8_BN * 8;           // mu[2][64]
+    static constexpr int OFF_TKV   = OFF_MU + 2 * I8_BN * 8;
     static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;
     static constexpr int OFF_CMASK = OFF_ACQ + I8_BN * 8;
     static constexpr int OFF_SOB   = OFF_CMASK + 32;
-    static constexpr int BYTES     = OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4;
+    static constexpr int OFF_X     = (OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4 + 127) / 128 * 128;
+    // builders' X~ / alpha staging: two buffers of XCH rows, as many rows as the 227 KB budget leaves
+    static constexpr int X_ROW     = (DP + 2 + 1) * 8;
+    static constexpr int X_FREE    = 232448 - OFF_X;
+    static constexpr int XCH       = X_FREE >= 2 * 512 * X_ROW ? 512 : X_FREE >= 2 * 256 * X_ROW ? 256 : X_FREE >= 2 * 128 * X_ROW ? 128 : 64;
+    static_assert(X_FREE >= 2 * XCH * X_ROW, "no room for the X~ staging buffers");
+    static constexpr int BYTES     = OFF_X + 2 * XCH * X_ROW;
 };
-
 struct SweepI8Args {
     const int8_t* Lp8; const double* rowscale; int8_t* panel8;
     double dig_scale;       // 2^(6 + 7 (S - 1)) / (power-of-two bound of |k*|): k* -> fixed point
@@ -152,18 +157,24 @@ __global__ void __launch_bounds__(256) i8_pack_linv_kernel(const double* __restr
 }
 
 // ---- the sweep -------------------------------------------------------------------------------------------------
+// Warp roles: 0-3 drain the accumulators and run the epilogue, 4 streams stage tiles (TMA), 5 issues the MMAs, 8-11 build
+// the NEXT block's int8 panel (FP64 kernel evaluations + slicing) while the tensor core works on the current one.
+// Roles are warpgroup-aligned so that setmaxnreg can move registers from the TMA/MMA group (48) to the drain (232: 64 FP64
+// column sums + 56 accumulator words per thread) and the builders (208).
 template <int DP, int KIND, int S>
 __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs a, const SweepI8Args b) {
-    using SM = I8Smem<S>;
+    using SM = I8Smem<S, DP>;
     static_assert(S * I8_BN <= 512, "TMEM has 512 columns");
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     uint64_t* empty = full + I8_STAGES;
     uint64_t* tfull = empty + I8_STAGES;
     uint64_t* tempty = tfull + 1;
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tempty + 1);
+    uint64_t* pfull = tempty + 1;             // [2] panel buffer p holds a finished block
+    uint64_t* pempty = pfull + 2;             // [2] panel buffer p has been consumed
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(pempty + 2);
     double* colsum  = reinterpret_cast<double*>(smem + SM::OFF_COL);
-    double* mu_s    = reinterpret_cast<double*>(smem + SM::OFF_MU);
+    double* mu_s    = reinterpret_cast<double*>(smem + SM::OFF_MU);       // [2][64]
     double* tkv     = reinterpret_cast<double*>(smem + SM::OFF_TKV);
     long long* tki  = reinterpret_cast<long long*>(smem + SM::OFF_TKI);
     double* acq_s   = reinterpret_cast<double*>(smem + SM::OFF_ACQ);
@@ -176,11 +187,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
     const int nbm = a.np / SW_BM;
     constexpr int KCH = SW_BM / I8_KC;                        // stages per 128 columns
     constexpr int B_STAGE = S * I8_B_SLICE;
-    int8_t* panel = b.panel8 + (size_t)blockIdx.x * (a.np / I8_KC) * B_STAGE;
+    const size_t panel_bytes = (size_t)(a.np / I8_KC) * B_STAGE;
+    int8_t* panel0 = b.panel8 + (size_t)blockIdx.x * 2 * panel_bytes;      // two buffers per CTA
 
     if (tid == 0) {
         for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tfull, 1); mbar_init(tempty, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -198,20 +211,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
 
-    // flags bit 2: clock64 accounting of where each role waits (printed by CTA 0 at the end; triage only)
-    const bool prof = (a.flags & 4) != 0;
-    long long t_a = 0, t_b = 0, t_w0 = 0, t_w1 = 0;
-    int stage = 0; uint32_t phase = 0;        // ring position of the role this thread plays (producer or MMA issuer)
-    uint32_t rb = 0;                          // running row-block counter (accumulator full/empty phases)
-
-    for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
-        // ================= phase A: candidates, K(X, X*) digits, posterior mean (warps 0-3) =================
-        const long long tA0 = prof ? clock64() : 0;
-        if (warp < 4) {
+    if (warp >= 8) {
+        // ================= builders: candidates, K(X, X*) digits, posterior mean of block it =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
+        const int tb = tid - 256, wb = warp - 8;
+        int it = 0;
+        for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, ++it) {
+            const int p = it & 1;
+            i8_wait(&pempty[p], ((it >> 1) & 1) ^ 1);         // the block that used this buffer two turns ago is done
+            int8_t* panel = panel0 + (size_t)p * panel_bytes;
             double xc[2][DP];
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
-                long long li = blk * I8_BN + (warp + 4 * gi) * 8 + g;
+                long long li = blk * I8_BN + (wb + 4 * gi) * 8 + g;
                 if (li >= a.N) li = a.N - 1;
                 if (a.cand) {
 #pragma unroll
@@ -223,21 +235,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                 for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
             }
             double mu0 = 0.0, mu1 = 0.0;
-            // X~ and alpha staged through the idle stage buffers (double-buffered cp.async chunks), as in sweep_kernel
-            constexpr int XCH = 512, XP = DP + 2, XBUF = XCH * XP + XCH;
-            static_assert(2 * XBUF * 8 <= I8_STAGES * SM::STAGE_BYTES, "X~ staging must fit into the stage buffers");
-            double* xstage = reinterpret_cast<double*>(smem);
+            // X~ and alpha staged through the builders' own shared-memory region in double-buffered cp.async chunks
+            constexpr int XCH = SM::XCH, XP = DP + 2, XBUF = XCH * XP + XCH;
+            double* xstage = reinterpret_cast<double*>(smem + SM::OFF_X);
             const int nrows = a.np;
-            const int nchunks = nrows / XCH + ((nrows % XCH) ? 1 : 0);
+            const int nchunks = (nrows + XCH - 1) / XCH;
             auto load_chunk = [&](int c) {
                 double* xb = xstage + (c & 1) * XBUF;
                 double* ab = xb + XCH * XP;
                 const int r0 = c * XCH, rows = min(XCH, nrows - r0);
-                for (int e = tid; e < rows * (DP / 2); e += 128) {
+                for (int e = tb; e < rows * (DP / 2); e += 128) {
                     const int r = e / (DP / 2), k = e % (DP / 2);
                     cp_async16(xb + r * XP + 2 * k, a.Xs + (size_t)(r0 + r) * BO_MAX_DIM + 2 * k);
                 }
-                for (int e = tid; e < rows / 2; e += 128) cp_async16(ab + 2 * e, a.alpha + r0 + 2 * e);
+                for (int e = tb; e < rows / 2; e += 128) cp_async16(ab + 2 * e, a.alpha + r0 + 2 * e);
                 cp_async_commit();
             };
             load_chunk(0);
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
 #pragma unroll
                                 for (int s = 0; s < S; ++s) w[s] |= (uint32_t)(uint8_t)(int8_t)dg[s] << (8 * e);
                             }
-                            const size_t off = ((size_t)(warp + 4 * gi) * (I8_KC / 16) + ch0 + hh) * 128 + g * 16 + q * 4;
+                            const size_t off = ((size_t)(wb + 4 * gi) * (I8_KC / 16) + ch0 + hh) * 128 + g * 16 + q * 4;
 #pragma unroll
                             for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t*>(st_tile + (size_t)s * I8_B_SLICE + off) = w[s];
                         }
@@ -295,166 +306,196 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             }
             mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
             mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
-            if (q == 0) { mu_s[warp * 8 + g] = mu0; mu_s[(warp + 4) * 8 + g] = mu1; }
+            if (q == 0) { mu_s[p * I8_BN + wb * 8 + g] = mu0; mu_s[p * I8_BN + (wb + 4) * 8 + g] = mu1; }
             __threadfence();
-            fence_proxy_async();      // generic-proxy writes (panel in global, X~ in the stage buffers) -> async proxy
+            fence_proxy_async();      // generic-proxy panel writes -> visible to the async-proxy (TMA) reads
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tb == 0) mbar_arrive(&pfull[p]);
         }
-        __syncthreads();
-        const long long tB0 = prof ? clock64() : 0;
-        t_a += tB0 - tA0;
-
-        // ================= phase B: ||L^-1 k*||^2 on the INT8 tensor path ============================
-        if (warp == 4) {
-            if (lane == 0) {
-                for (int ib = 0; ib < nbm; ++ib)
-                    for (int kc = 0; kc < (ib + 1) * KCH; ++kc) {
+    } else if (warp >= 4) {
+        // ================= warpgroup 1: TMA producer (warp 4), MMA issuer (warp 5) =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
+        if (warp < 6) {
+        // flags bit 2: clock64 accounting of where the MMA issuer waits (printed by CTA 0 at the end; triage only)
+        const bool prof = (a.flags & 4) != 0;
+        long long t_tot = 0, t_w0 = 0, t_w1 = 0, t_w2 = 0;
+        unsigned long long ns0 = 0, ns1 = 0;
+        if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+        const long long c0 = prof ? clock64() : 0;
+        int stage = 0; uint32_t phase = 0;        // ring position of the role this thread plays (producer or MMA issuer)
+        uint32_t rb = 0;                          // running row-block counter (accumulator full/empty phases)
+        int it = 0;
+        for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, ++it) {
+            const int p = it & 1;
+            const int8_t* panel = panel0 + (size_t)p * panel_bytes;
+            const long long tB0 = prof ? clock64() : 0;
+            i8_wait(&pfull[p], (it >> 1) & 1);            // the builders have finished this block (acquire: panel)
+            if (prof) t_w2 += clock64() - tB0;
+            if (warp == 4) {
+                if (lane == 0) {
+                    for (int ib = 0; ib < nbm; ++ib)
+                        for (int kc = 0; kc < (ib + 1) * KCH; ++kc) {
+                            i8_wait(&empty[stage], phase ^ 1);
+                            unsigned char* sb = smem + stage * SM::STAGE_BYTES;
+                            mbar_expect_tx(&full[stage], SM::STAGE_BYTES);
+                            bulk_g2s(sb, b.Lp8 + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * (size_t)(S * I8_A_SLICE), S * I8_A_SLICE, &full[stage]);
+                            bulk_g2s(sb + S * I8_A_SLICE, panel + (size_t)kc * B_STAGE, B_STAGE, &full[stage]);
+                            if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                }
+            } else {
+                // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
+                // lane issues.  The slice-pair loops are fully unrolled: every descriptor is the stage's base descriptor plus a
+                // compile-time constant, so an MMA costs a few integer instructions to issue -- with rolled loops the issuing
+                // thread, not the tensor core, set the pace (a 64-column MMA lasts ~34 cycles).
+                const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
+                const bool leader = i8_elect();
+                for (int ib = 0; ib < nbm; ++ib, ++rb) {
+                    const long long w1 = prof ? clock64() : 0;
+                    i8_wait(tempty, (rb & 1) ^ 1);             // the drain of the previous row block is done
+                    if (prof) t_w1 += clock64() - w1;
+                    tc_fence_after();
+                    const int nkc = (ib + 1) * KCH;
+                    for (int kc = 0; kc < nkc; ++kc) {
                         const long long w0 = prof ? clock64() : 0;
-                        i8_wait(&empty[stage], phase ^ 1);
+                        i8_wait(&full[stage], phase);
                         if (prof) t_w0 += clock64() - w0;
-                        unsigned char* sb = smem + stage * SM::STAGE_BYTES;
-                        mbar_expect_tx(&full[stage], SM::STAGE_BYTES);
-                        bulk_g2s(sb, b.Lp8 + ((size_t)ib * (ib + 1) / 2 * KCH + kc) * (size_t)(S * I8_A_SLICE), S * I8_A_SLICE, &full[stage]);
-                        bulk_g2s(sb + S * I8_A_SLICE, panel + (size_t)kc * B_STAGE, B_STAGE, &full[stage]);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + stage * SM::STAGE_BYTES);
+                        const uint64_t da0 = i8_desc(a0), db0 = i8_desc(a0 + S * I8_A_SLICE);
+                        const uint32_t acc0 = kc > 0 ? 1u : 0u;
+                        if (leader) {
+#pragma unroll
+                            for (int s = 0; s < S; ++s)
+#pragma unroll
+                                for (int t = 0; t + s < S; ++t)
+#pragma unroll
+                                    for (int kk = 0; kk < I8_KC / 32; ++kk)
+                                        i8_mma(tmem_base + (s + t) * I8_BN, da0 + (uint64_t)((s * I8_A_SLICE + kk * 256) >> 4),
+                                               db0 + (uint64_t)((t * I8_B_SLICE + kk * 256) >> 4), idesc, (kk > 0 || s > 0) ? 1u : acc0);
+                            i8_commit(&empty[stage]);                // the slot is free once these MMAs have read it
+                            if (kc == nkc - 1) i8_commit(tfull);     // the accumulators of row block ib are complete
+                        }
+                        __syncwarp();
                         if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
                     }
-            }
-        } else if (warp == 5) {
-            // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
-            // lane issues.  The slice-pair loops are fully unrolled: every descriptor is the stage's base descriptor plus a
-            // compile-time constant, so an MMA costs a few integer instructions to issue -- with rolled loops the issuing
-            // thread, not the tensor core, set the pace (a 64-column MMA lasts ~34 cycles).
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(SW_BM >> 4) << 24);
-            const bool leader = i8_elect();
-            for (int ib = 0; ib < nbm; ++ib, ++rb) {
-                const long long w1 = prof ? clock64() : 0;
-                i8_wait(tempty, (rb & 1) ^ 1);             // the drain of the previous row block is done
-                if (prof) t_w1 += clock64() - w1;
-                tc_fence_after();
-                const int nkc = (ib + 1) * KCH;
-                for (int kc = 0; kc < nkc; ++kc) {
-                    const long long w0 = prof ? clock64() : 0;
-                    i8_wait(&full[stage], phase);
-                    if (prof) t_w0 += clock64() - w0;
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(smem + stage * SM::STAGE_BYTES);
-                    const uint64_t da0 = i8_desc(a0), db0 = i8_desc(a0 + S * I8_A_SLICE);
-                    const uint32_t acc0 = kc > 0 ? 1u : 0u;
-                    if (leader) {
-#pragma unroll
-                        for (int s = 0; s < S; ++s)
-#pragma unroll
-                            for (int t = 0; t + s < S; ++t)
-#pragma unroll
-                                for (int kk = 0; kk < I8_KC / 32; ++kk)
-                                    i8_mma(tmem_base + (s + t) * I8_BN, da0 + (uint64_t)((s * I8_A_SLICE + kk * 256) >> 4),
-                                           db0 + (uint64_t)((t * I8_B_SLICE + kk * 256) >> 4), idesc, (kk > 0 || s > 0) ? 1u : acc0);
-                        i8_commit(&empty[stage]);                // the slot is free once these MMAs have read it
-                        if (kc == nkc - 1) i8_commit(tfull);     // the accumulators of row block ib are complete
-                    }
-                    __syncwarp();
-                    if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-        } else {
-            double acc[I8_BN];
-#pragma unroll
-            for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
-            for (int ib = 0; ib < nbm; ++ib, ++rb) {
-                const double rs = b.rowscale[ib * SW_BM + tid] * b.eb_scale;
-                const long long w0 = prof ? clock64() : 0;
-                i8_wait(tfull, rb & 1);
-                if (prof) t_w0 += clock64() - w0;
-                tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-                for (int c0 = 0; c0 < I8_BN; c0 += 8) {
-                    int v[S][8];
-#pragma unroll
-                    for (int gq = 0; gq < S; ++gq) tmem_ld8(trow + gq * I8_BN + c0, v[gq]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        double t = (double)v[S - 1][j];
-#pragma unroll
-                        for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, (double)v[gq][j]);
-                        const double u = t * rs;
-                        acc[c0 + j] = fma(u, u, acc[c0 + j]);
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty);
-                if (prof) t_w1 += clock64() - w0;
-            }
-            // sum over the 32 rows of this warp: halving butterfly (each step trades half of the columns held)
-#pragma unroll
-            for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) {
-                const bool upper = (lane & o) != 0;
-#pragma unroll
-                for (int c = 0; c < cnt; ++c) {
-                    const double send = upper ? acc[c] : acc[c + cnt];
-                    const double keep = upper ? acc[c + cnt] : acc[c];
-                    acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                }
-            }
-            // lane l now holds the warp totals of 2 columns; recover which ones from the butterfly's bit order
+            asm volatile("bar.sync 2, 192;" ::: "memory");
+            if (prof) t_tot += clock64() - tB0;
+            asm volatile("bar.sync 2, 192;" ::: "memory");
+            asm volatile("bar.sync 2, 192;" ::: "memory");
+        }
+        if (prof && blockIdx.x == 0 && tid == 160) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+            const long long c1 = clock64();
+            printf("sweep_i8 CTA 0 MMA issuer: %d blocks, %lld clk in the contraction; waits: panel-ready %lld, stage-full %lld, accumulators-drained %lld; "
+                   "SM clock over the kernel %.0f MHz\n", it, t_tot, t_w2, t_w0, t_w1, (double)(c1 - c0) / (double)(ns1 - ns0) * 1e3);
+        }
+        }
+    } else {
+        // ================= warpgroup 0: accumulator drain + epilogue =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        uint32_t rb = 0;
+        int it = 0;
+        for (long long blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x, ++it) {
+            const int p = it & 1;
+            i8_wait(&pfull[p], (it >> 1) & 1);            // acquire: mu_s[p]
             {
-                int base = 0;
+                double acc[I8_BN];
 #pragma unroll
-                for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) base += (lane & o) ? cnt : 0;
-                colsum[warp * I8_BN + base] = acc[0];
-                colsum[warp * I8_BN + base + 1] = acc[1];
-            }
-        }
-        __syncthreads();
-        if (prof) t_b += clock64() - tB0;
-
-        // ================= epilogue: variance, acquisition, CTA-local top-k =====================
-        if (tid < I8_BN) {
-            const long long li = blk * I8_BN + tid;
-            const double ss = (colsum[tid] + colsum[I8_BN + tid]) + (colsum[2 * I8_BN + tid] + colsum[3 * I8_BN + tid]);
-            const double var = fmax(a.hyp.outputscale - ss, a.min_var);
-            const double mean = a.hyp.mean + mu_s[tid];
-            double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
-            if (li < a.N) {
-                if (a.mean_out) a.mean_out[li] = mean;
-                if (a.var_out) a.var_out[li] = var;
-                if (a.acq_out) a.acq_out[li] = v;
-            }
-            if (!(v == v)) v = -INFINITY;
-            acq_s[tid] = v;
-            bool beats = false;
-            if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
-            const unsigned m = __ballot_sync(0xffffffffu, beats);
-            if (lane == 0) cmask[warp] = m;
-        }
-        __syncthreads();
-        if (tid == 0 && a.topk > 0) {
-            const int K = a.topk;
-            for (int w = 0; w < I8_BN / 32; ++w) {
-                unsigned m = cmask[w];
-                while (m) {
-                    const int c = w * 32 + __ffs(m) - 1;
-                    m &= m - 1;
-                    const double v = acq_s[c];
-                    const long long gi = a.first_index + blk * I8_BN + c;
-                    if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
-                    int p = K - 1;
-                    while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
-                    tkv[p] = v; tki[p] = gi;
+                for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
+                for (int ib = 0; ib < nbm; ++ib, ++rb) {
+                    const double rs = b.rowscale[ib * SW_BM + tid] * b.eb_scale;
+                    i8_wait(tfull, rb & 1);
+                    tc_fence_after();
+                    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+                    for (int c0 = 0; c0 < I8_BN; c0 += 8) {
+                        int v[S][8];
+#pragma unroll
+                        for (int gq = 0; gq < S; ++gq) tmem_ld8(trow + gq * I8_BN + c0, v[gq]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            double t = (double)v[S - 1][j];
+#pragma unroll
+                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, (double)v[gq][j]);
+                            const double u = t * rs;
+                            acc[c0 + j] = fma(u, u, acc[c0 + j]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty);
+                }
+                // sum over the 32 rows of this warp: halving butterfly (each step trades half of the columns held)
+#pragma unroll
+                for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) {
+                    const bool upper = (lane & o) != 0;
+#pragma unroll
+                    for (int c = 0; c < cnt; ++c) {
+                        const double send = upper ? acc[c] : acc[c + cnt];
+                        const double keep = upper ? acc[c + cnt] : acc[c];
+                        acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+                // lane l now holds the warp totals of 2 columns; recover which ones from the butterfly's bit order
+                {
+                    int base = 0;
+#pragma unroll
+                    for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) base += (lane & o) ? cnt : 0;
+                    colsum[warp * I8_BN + base] = acc[0];
+                    colsum[warp * I8_BN + base + 1] = acc[1];
                 }
             }
+            asm volatile("bar.sync 2, 192;" ::: "memory");
+
+            // ================= epilogue: variance, acquisition, CTA-local top-k =====================
+            if (tid < I8_BN) {
+                const long long li = blk * I8_BN + tid;
+                const double ss = (colsum[tid] + colsum[I8_BN + tid]) + (colsum[2 * I8_BN + tid] + colsum[3 * I8_BN + tid]);
+                const double var = fmax(a.hyp.outputscale - ss, a.min_var);
+                const double mean = a.hyp.mean + mu_s[p * I8_BN + tid];
+                double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
+                if (li < a.N) {
+                    if (a.mean_out) a.mean_out[li] = mean;
+                    if (a.var_out) a.var_out[li] = var;
+                    if (a.acq_out) a.acq_out[li] = v;
+                }
+                if (!(v == v)) v = -INFINITY;
+                acq_s[tid] = v;
+                bool beats = false;
+                if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
+                const unsigned m = __ballot_sync(0xffffffffu, beats);
+                if (lane == 0) cmask[warp] = m;
+            }
+            asm volatile("bar.sync 2, 192;" ::: "memory");
+            if (tid == 0) {
+                mbar_arrive(&pempty[p]);           // panel p and mu_s[p] are free for the builders (block it + 2)
+                if (a.topk > 0) {
+                    const int K = a.topk;
+                    for (int w = 0; w < I8_BN / 32; ++w) {
+                        unsigned m = cmask[w];
+                        while (m) {
+                            const int c = w * 32 + __ffs(m) - 1;
+                            m &= m - 1;
+                            const double v = acq_s[c];
+                            const long long gi = a.first_index + blk * I8_BN + c;
+                            if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
+                            int pp = K - 1;
+                            while (pp > 0 && tk_better(v, gi, tkv[pp - 1], tki[pp - 1])) { tkv[pp] = tkv[pp - 1]; tki[pp] = tki[pp - 1]; --pp; }
+                            tkv[pp] = v; tki[pp] = gi;
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 2, 192;" ::: "memory");
         }
-        __syncthreads();
-    }
-    if (prof && blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 160))
-        printf("sweep_i8 CTA 0 %s: phase A %lld clk, phase B %lld clk; waits: %s %lld clk, %s %lld clk\n",
-               tid == 0 ? "drain warp 0" : tid == 128 ? "TMA producer" : "MMA issuer", t_a, t_b,
-               tid == 0 ? "accumulators-full" : tid == 128 ? "slot-empty" : "stage-full", t_w0,
-               tid == 0 ? "(drain total incl. wait)" : tid == 128 ? "-" : "accumulators-drained", t_w1);
-    if (tid < BO_MAX_TOPK && a.part_val) {
-        a.part_val[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tkv[tid];
-        a.part_idx[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tki[tid];
+        if (tid < BO_MAX_TOPK && a.part_val) {
+            a.part_val[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tkv[tid];
+            a.part_idx[(size_t)blockIdx.x * BO_MAX_TOPK + tid] = tki[tid];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -505,7 +546,7 @@ static int ensure_i8_ws(bo_handle* h, int grid) {
         BO_CUDA(h, cudaMalloc(&h->rowscale, (size_t)h->cap_np * sizeof(double)));
         h->rowscale_cap = h->cap_np;
     }
-    const size_t p_bytes = (size_t)grid * (h->np / I8_KC) * (size_t)(S * I8_B_SLICE);
+    const size_t p_bytes = (size_t)grid * 2 * (h->np / I8_KC) * (size_t)(S * I8_B_SLICE);      // two panel buffers per CTA
     if (p_bytes > h->panel8_bytes) {
         if (h->panel8) cudaFree(h->panel8);
         h->panel8 = nullptr; h->panel8_bytes = 0;
@@ -517,8 +558,8 @@ static int ensure_i8_ws(bo_handle* h, int grid) {
 
 template <int DP, int KIND, int S>
 static int launch_sweep_i8_k(bo_handle* h, const SweepArgs& a, const SweepI8Args& b, int grid, cudaStream_t st) {
-    BO_CUDA(h, cudaFuncSetAttribute(sweep_i8_kernel<DP, KIND, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Smem<S>::BYTES));
-    sweep_i8_kernel<DP, KIND, S><<<grid, I8_THREADS, I8Smem<S>::BYTES, st>>>(a, b);
+    BO_CUDA(h, cudaFuncSetAttribute(sweep_i8_kernel<DP, KIND, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Smem<S, DP>::BYTES));
+    sweep_i8_kernel<DP, KIND, S><<<grid, I8_THREADS, I8Smem<S, DP>::BYTES, st>>>(a, b);
     BO_LAUNCH_CHECK(h);
     return 0;
 }
@@ -532,7 +573,8 @@ static int launch_sweep_i8(bo_handle* h, const SweepArgs& a, const SweepI8Args& 
 // a: as prepared by sweep_impl (G == 1).  Packs the int8 operands of the current factor, then sweeps.
 static int sweep_i8_run(bo_handle* h, SweepArgs a, int S, double* vals_dev, int64_t* idx_dev, cudaStream_t st) {
     a.nblocks = (a.N + I8_BN - 1) / I8_BN;
-    const int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
+    int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
+    { const char* gs = getenv("BO_B200_I8_GRID"); if (gs && atoi(gs) >= 1 && atoi(gs) < grid) grid = atoi(gs); }   // triage: fewer CTAs
     int rc;
     if ((rc = ensure_sweep_ws(h, grid))) return rc;           // per-CTA top-k lists (the FP64 panel is not used)
     if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid) : ensure_i8_ws<7>(h, grid)))) return rc;

@@ -29,11 +29,7 @@ def main():
     best = float(y.max())
     res = {}
     for impl in ("fp64", "i8"):
-        if impl == "i8":
-            os.environ["BO_B200_SWEEP_IMPL"] = "i8"
-            os.environ["BO_B200_I8_SLICES"] = S
-        else:
-            os.environ.pop("BO_B200_SWEEP_IMPL", None)
+        eng.set_sweep_mode("fp64" if impl == "fp64" else "i8x" + S)
         for rep in range(2):
             out = eng.sweep("ei", best, sobol=st, count=N, topk=8, return_all=True)
             torch.cuda.synchronize()
