@@ -439,6 +439,137 @@ static void feed(const char* what, size_t buf_bytes, uint32_t tile, int sms, int
     cudaFree(d); cudaFree(d_err);
 }
 
+// ---- the real kernel's stage pattern, issue loop fully unrolled (warp-uniform, one elected lane), in SM cycles:
+// MODE 0: SS - 28 slice pairs x 2 K-steps with both operands from shared memory (what sweep_i8_kernel does);
+// MODE 1: TS - per K-step the 7 A slices are first copied smem -> TMEM (tcgen05.cp 128x256b into the 56 columns the
+//         accumulators leave free) and the 28 MMAs read A from TMEM, B from shared memory. ----
+template <int S, int MODE>
+__global__ void __launch_bounds__(128, 1)
+probe_kernel_stage(int iters, int32_t* __restrict__ out, int* __restrict__ err, long long* __restrict__ cycles) {
+    constexpr int M = 128, N = 64, KC = 64;
+    constexpr int A_TILE = M * KC, B_TILE = N * KC;
+    static_assert(S * N + S * 8 <= 512, "TMEM has 512 columns");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    int8_t* sA = reinterpret_cast<int8_t*>(smem);
+    int8_t* sB = sA + S * A_TILE;
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < S * A_TILE; i += 128) {
+        int s = i / A_TILE, o = i % A_TILE, cm = o / 128, w = o % 128;
+        sA[i] = (int8_t)digit(s, 0, (cm / (KC / 16)) * 8 + w / 16, (cm % (KC / 16)) * 16 + w % 16);
+    }
+    for (int i = tid; i < S * B_TILE; i += 128) {
+        int s = i / B_TILE, o = i % B_TILE, cm = o / 128, w = o % 128;
+        sB[i] = (int8_t)digit(s, 1, (cm / (KC / 16)) * 8 + w / 16, (cm % (KC / 16)) * 16 + w % 16);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t a_col0 = S * N;
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint64_t da0 = make_desc(smem_u32(sA), 128, 512), db0 = make_desc(smem_u32(sB), 128, 512);
+    if (warp == 1) {
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(leader));
+        bool ok = true;
+        const long long c0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t acc0 = it > 0 ? 1u : 0u;
+            if (leader) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 32; ++kk) {
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;"
+                                         ::"r"(tmem_base + a_col0 + s * 8), "l"(da0 + (uint64_t)((s * A_TILE + kk * 256) >> 4)) : "memory");
+                    }
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+#pragma unroll
+                        for (int t = 0; t + s < S; ++t) {
+                            const uint32_t accf = (kk > 0 || s > 0) ? 1u : acc0;
+                            if (MODE == 1)
+                                mma_i8_ts(tmem_base + (s + t) * N, tmem_base + a_col0 + s * 8, db0 + (uint64_t)((t * B_TILE + kk * 256) >> 4), idesc, accf);
+                            else
+                                mma_i8(tmem_base + (s + t) * N, da0 + (uint64_t)((s * A_TILE + kk * 256) >> 4),
+                                       db0 + (uint64_t)((t * B_TILE + kk * 256) >> 4), idesc, accf);
+                        }
+                }
+                commit(&bars[it & 1]);
+            }
+            __syncwarp();
+            if (it > 0) ok = ok && mbar_wait_bounded(&bars[(it - 1) & 1], ((it - 1) >> 1) & 1);
+            if (!ok) break;
+        }
+        if (ok) ok = mbar_wait_bounded(&bars[(iters - 1) & 1], ((iters - 1) >> 1) & 1);
+        const long long c1 = clock64();
+        if (!ok && leader) atomicAdd(err, 1);
+        if (leader && blockIdx.x == 0 && cycles) *cycles = c1 - c0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (out != nullptr && blockIdx.x == 0) {
+        for (int c0 = 0; c0 < S * N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[(size_t)(warp * 32 + (tid & 31)) * (S * N) + c0 + j] = (int32_t)v[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+template <int S, int MODE>
+static void stage_probe(int sms) {
+    constexpr int M = 128, N = 64, KC = 64;
+    size_t smem = (size_t)S * (M + N) * KC;
+    CK(cudaFuncSetAttribute(probe_kernel_stage<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int32_t* d_out; int* d_err; long long* d_cyc;
+    CK(cudaMalloc(&d_out, sizeof(int32_t) * M * S * N)); CK(cudaMemset(d_out, 0xff, sizeof(int32_t) * M * S * N));
+    CK(cudaMalloc(&d_err, sizeof(int))); CK(cudaMemset(d_err, 0, sizeof(int)));
+    CK(cudaMalloc(&d_cyc, sizeof(long long)));
+    probe_kernel_stage<S, MODE><<<1, 128, smem>>>(1, d_out, d_err, d_cyc);
+    CK(cudaDeviceSynchronize());
+    std::vector<int32_t> out((size_t)M * S * N);
+    CK(cudaMemcpy(out.data(), d_out, out.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    long bad = 0;
+    for (int g = 0; g < S; ++g)
+        for (int r = 0; r < M; ++r)
+            for (int c = 0; c < N; ++c) {
+                long ref = 0;
+                for (int s = 0; s <= g; ++s)
+                    for (int k = 0; k < KC; ++k) ref += (long)digit(s, 0, r, k) * digit(g - s, 1, c, k);
+                if ((long)out[(size_t)r * (S * N) + g * N + c] != ref) ++bad;
+            }
+    const int iters = 4000;
+    probe_kernel_stage<S, MODE><<<sms, 128, smem>>>(iters, nullptr, d_err, d_cyc);
+    CK(cudaDeviceSynchronize());
+    long long cyc = 0; int err = 0;
+    CK(cudaMemcpy(&cyc, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    const int mmas = S * (S + 1) / 2 * (KC / 32);
+    printf("stage %s S=%d: %ld of %d accumulators differ; %.0f clk per stage = %.1f clk per MMA (%d MMAs%s)%s\n", MODE ? "TS (A slices copied smem -> TMEM per K-step)" : "SS (both operands from smem)",
+           S, bad, M * S * N, (double)cyc / iters, (double)cyc / iters / mmas, mmas, MODE ? " + 14 tcgen05.cp" : "", err ? "  [TIMEOUT]" : "");
+    cudaFree(d_out); cudaFree(d_err); cudaFree(d_cyc);
+}
+
 int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     printf("%s, %d SMs, cc %d.%d\n", p.name, p.multiProcessorCount, p.major, p.minor);
@@ -447,6 +578,8 @@ int main() {
     if (!ok0 && !ok1) { printf("no descriptor variant reproduces the integer reference - stopping before the rate runs\n"); return 1; }
     const int swap = ok0 ? 0 : 1;
     const int sms = p.multiProcessorCount;
+    stage_probe<7, 0>(sms);
+    stage_probe<7, 1>(sms);
     rate<64, 7, 64, 7>(swap, sms, 4000);     // the Ozaki shape: 7 group accumulators x 64 columns = 448 TMEM columns
     rate<64, 8, 64, 8>(swap, sms, 4000);     // 8 slices (FP64-equal accuracy): 512 columns
     rate<128, 7, 64, 4>(swap, sms, 2000);    // rate only (groups folded mod 4): what N=128 would give if TMEM were larger
