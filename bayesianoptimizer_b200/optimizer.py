@@ -39,6 +39,7 @@ class GPConfig:
     acquisition: str = "logei"           # "logei" (Bayesian.py:101) | "ei" | "ucb" | "var" (Bayesian7.py:670-671)
     beta: float = 2.0                    # UCB exploration weight
     candidates_pool_size: int = 1_000_000  # Sobol pool scored per suggestion (reference: 1024 raw / 10^4 LHS)
+    sweep_mode: str = "auto"             # variance contraction of the pool sweep (bo_set_sweep_mode): "auto" | "fp64" | "i8x7" | "i8x8"
     num_restarts: int = 10               # starts refined per suggestion (Bayesian.py:108)
     refine_iters: int = 200              # refinement iterations (maxiter, Bayesian.py:111)
     believer_max_q: int = 16             # q <= this: Kriging-believer batch; larger q: top-K -> FPS (Bayesian7.py:676-688)
@@ -248,6 +249,8 @@ class BayesianOptimizer:
     def _engine_get(self):
         if self._engine is None:
             self._engine = self._engine_factory()
+            if self.config.sweep_mode != "auto":
+                self._engine.set_sweep_mode(self.config.sweep_mode)
         return self._engine
 
     def _fit_hyperparameters(self, eng, X, y):
