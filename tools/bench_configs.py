@@ -28,11 +28,15 @@ X, y = synth(512, 5, 1, 2)
 Xd, yd = torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev)
 fit_ms = wall(lambda: eng.fit(Xd, yd, "matern52", 0.5, 1.0, 1e-3))
 st = sobol_state(5, 3)
-for _ in range(3): eng.sweep("ei", float(y.max()), sobol=st, count=1_000_000, topk=1)
-torch.cuda.synchronize(); ms = eng.last_sweep_ms()
 F = 512 * 512 + 512 * (3 * 5 + 12.0)
-rep["C2"] = {"n": 512, "d": 5, "pool": 1_000_000, "refit_ms": fit_ms, "sweep_ms": ms, "cand_per_s": 1e6 / ms * 1e3,
-             "tflops_alg": 1e6 * F / ms * 1e-9, "frac_of_fp64_peak": 1e6 * F / ms * 1e-9 / peak}
+rep["C2"] = {"n": 512, "d": 5, "pool": 1_000_000, "refit_ms": fit_ms}
+for mode in ("fp64", "auto"):          # the FP64 DMMA contraction, then what AUTO picks for this pool (INT8-sliced, 7 slices)
+    eng.set_sweep_mode(mode)
+    for _ in range(3): eng.sweep("ei", float(y.max()), sobol=st, count=1_000_000, topk=1)
+    torch.cuda.synchronize(); ms = eng.last_sweep_ms()
+    rep["C2"][mode] = {"path": eng.last_sweep_path(), "sweep_ms": ms, "cand_per_s": 1e6 / ms * 1e3, "tflops_alg": 1e6 * F / ms * 1e-9,
+                       "ratio_to_fp64_dmma_peak": 1e6 * F / ms * 1e-9 / peak}
+eng.set_sweep_mode("auto")
 
 # ---- C1 shape: n=3000, d=5, 10^4 candidates: refit + suggest ms ----
 X, y = synth(3000, 5, 11, 12)
@@ -49,10 +53,14 @@ st8 = sobol_state(8, 6)
 N = 148 * 128 * 8
 F = 4096 * 4096 + 4096 * (3 * 8 + 12.0)
 out = {}
-for acq in ("ei", "ucb", "logei"):
-    for _ in range(2): eng.sweep(acq, float(y.max()), 2.0, sobol=st8, count=N, topk=1)
-    torch.cuda.synchronize(); ms = eng.last_sweep_ms()
-    out[acq] = {"sweep_ms": ms, "cand_per_s": N / ms * 1e3, "frac_of_fp64_peak": N * F / ms * 1e-9 / peak}
+for mode in ("fp64", "auto", "i8x8"):
+    eng.set_sweep_mode(mode)
+    for acq in ("ei", "ucb", "logei"):
+        for _ in range(2): eng.sweep(acq, float(y.max()), 2.0, sobol=st8, count=N, topk=1)
+        torch.cuda.synchronize(); ms = eng.last_sweep_ms()
+        out[f"{acq}/{mode}"] = {"path": eng.last_sweep_path(), "sweep_ms": ms, "cand_per_s": N / ms * 1e3,
+                                "ratio_to_fp64_dmma_peak": N * F / ms * 1e-9 / peak}
+eng.set_sweep_mode("auto")
 rep["C3"] = {"n": 4096, "d": 8, "pool_timed": N, "refit_ms": fit_ms, "sweeps": out,
              "chol_flops": 4096 ** 3 / 3, "note": "refit = Gram + Cholesky + explicit inverse + alpha + repack"}
 
