@@ -506,7 +506,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
 // ---- host side -------------------------------------------------------------------------------------------------
 // the model side of eligibility: exact GP with a stationary kernel (|k*| <= output scale), more than one stage of rows
 static bool sweep_i8_model_ok(const bo_handle* h) {
-    return h->fitted && !h->svgp && h->hyp.kind != BO_KERNEL_LINEAR_MATERN52 && h->np >= I8_MIN_NP;
+    // np < 2^16: the INT32 group accumulators hold at most 8 * 64 * 64 * np
+    return h->fitted && !h->svgp && h->hyp.kind != BO_KERNEL_LINEAR_MATERN52 && h->np >= I8_MIN_NP && h->np < 65536;
 }
 
 // Slice count from the error model (tools/ozaki_feasibility.py): the relative error of sigma^2 is the slicing
