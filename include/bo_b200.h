@@ -53,8 +53,8 @@ extern "C" {
 #define BO_ACQ_MEAN  4   /* posterior mean                                                              */
 
 /* contraction used by bo_sweep for the variance term u = L^-1 k* (bo_set_sweep_mode) */
-#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path for large pools of a stationary-kernel exact GP (slice count from
-                           * the error model, see bo_set_sweep_mode), FP64 DMMA otherwise */
+#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path (8 slices) for large pools of a stationary-kernel exact GP,
+                           * FP64 DMMA otherwise (see bo_set_sweep_mode) */
 #define BO_SWEEP_FP64 1   /* always the FP64 DMMA contraction */
 #define BO_SWEEP_I8X7 2   /* INT8-sliced with 7 slices wherever eligible */
 #define BO_SWEEP_I8X8 3   /* INT8-sliced with 8 slices wherever eligible */
@@ -221,11 +221,13 @@ int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, in
 /* Choose how bo_sweep contracts L^-1 with the K(X, X*) panel (BO_SWEEP_*; default BO_SWEEP_AUTO).  The INT8-sliced path
  * computes the same FP64 quantity: both operands are cut into S signed 7-bit slices (error-free, Ozaki scheme I), the
  * S (S + 1) / 2 leading slice products run on the INT8 tensor cores (tcgen05.mma kind::i8) with exact INT32
- * accumulation and are recombined in FP64.  8 slices reproduce the FP64 product to its own rounding level; 7 slices
- * (chosen by AUTO when noise / outputscale >= 1e-3) stay below 1e-9 relative on the variance.  Eligible models: exact GP,
+ * accumulation and are recombined in FP64.  8 slices (what AUTO uses) reproduce the FP64 product to its own rounding
+ * level; 7 slices (opt-in, 1.25x faster) hold 1e-9 relative on the variance of well-separated data but reach 2e-8 next
+ * to clusters of training rows (sigma^2 << noise).  Eligible models: exact GP,
  * Matern-5/2 or RBF kind, at least 256 (padded) observations; every other model runs the FP64 DMMA path in every mode.
  * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
- * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates on the FP64 path. */
+ * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates, and models with
+ * noise / outputscale < 1e-5, on the FP64 path. */
 int bo_set_sweep_mode(bo_handle* h, int32_t mode);
 
 /* The pinned mode (BO_SWEEP_FP64 / I8X7 / I8X8) the handle's current mode resolves to for a pool of pool_total
