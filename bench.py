@@ -333,7 +333,10 @@ def main():
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
-                per_cand = tj.get("i8", {}).get("dram_bytes_per_candidate") if slices else tj.get("dram_bytes_per_candidate")
+                per_cand = tj.get("dram_bytes_per_candidate")
+                if slices:      # captured with 7 slices; both operand streams scale with the slice count
+                    per_cand = tj.get("i8", {}).get("dram_bytes_per_candidate")
+                    per_cand = per_cand * slices / 7.0 if per_cand else None
                 traffic = per_cand * count if per_cand else None                              # per launch of this shard
             except Exception:
                 traffic = None
