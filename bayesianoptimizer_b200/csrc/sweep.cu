@@ -671,8 +671,9 @@ static int ensure_split_ws(bo_handle* h, long long nblocks, int G, int nbm) {
     return 0;
 }
 
-static int ensure_sweep_ws(bo_handle* h, int grid) {
-    const size_t need = (size_t)grid * (h->np / SW_BK) * SW_TILE * sizeof(double);
+static int ensure_sweep_ws(bo_handle* h, int grid, bool fp64_panel = true) {
+    // the sliced sweep keeps its own int8 panels: it only needs the per-CTA top-k lists from here
+    const size_t need = fp64_panel ? (size_t)grid * (h->np / SW_BK) * SW_TILE * sizeof(double) : 0;
     if (need > h->panel_bytes) {
         if (h->panel) cudaFree(h->panel);
         h->panel = nullptr; h->panel_bytes = 0;

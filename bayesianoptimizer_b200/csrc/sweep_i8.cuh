@@ -578,7 +578,7 @@ static int sweep_i8_run(bo_handle* h, SweepArgs a, int S, double* vals_dev, int6
     int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
     { const char* gs = getenv("BO_B200_I8_GRID"); if (gs && atoi(gs) >= 1 && atoi(gs) < grid) grid = atoi(gs); }   // triage: fewer CTAs
     int rc;
-    if ((rc = ensure_sweep_ws(h, grid))) return rc;           // per-CTA top-k lists (the FP64 panel is not used)
+    if ((rc = ensure_sweep_ws(h, grid, false))) return rc;    // per-CTA top-k lists only (no FP64 panel)
     if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid) : ensure_i8_ws<7>(h, grid)))) return rc;
     const int nbm = h->np / SW_BM;
     // the factor may have changed since the last call (fit, append, refit): re-slice it every time (~0.1 ms at n = 4096)

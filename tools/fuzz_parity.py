@@ -1,6 +1,6 @@
 """Randomised parity sweep on the GPU: random shapes / kernels / hyper-parameters / acquisitions against the CPU oracle
 (fit, fused sweep incl. row-split, explicit and Sobol pools, appends, SVGP state, batched LML, large top-K).
-Usage: python tools/fuzz_parity.py [cases] [seed]"""
+Usage: python tools/fuzz_parity.py [cases] [seed] [sweep mode: auto | fp64 | i8x7 | i8x8]"""
 import os, sys, time, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -12,6 +12,7 @@ from conftest import assert_posterior_close, assert_acq_close
 cases, seed = int(sys.argv[1]) if len(sys.argv) > 1 else 100, int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rng = np.random.default_rng(seed)
 eng = GPEngine(torch.device("cuda", 0))
+eng.set_sweep_mode(sys.argv[3] if len(sys.argv) > 3 else "auto")     # pinned INT8 modes: every eligible model takes the sliced path
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 KN = {o.KERNEL_MATERN52: "matern52", o.KERNEL_RBF: "rbf", o.KERNEL_LINEAR_MATERN52: "linear_matern52"}
 AC = {"ei": o.ACQ_EI, "logei": o.ACQ_LOGEI, "ucb": o.ACQ_UCB, "var": o.ACQ_VAR, "mean": o.ACQ_MEAN}
