@@ -147,7 +147,8 @@ int bo_posterior_multi(bo_handle* h, const double* Y_dev, int32_t m, const doubl
 /* Acquisition sweep over candidates [first_index, first_index + N) of a pool:
  *   cand_dev != NULL : explicit pool, cand_dev[N,d] holds exactly this shard's rows;
  *   cand_dev == NULL : in-kernel scrambled Sobol from `sobol_host` keyed by the global index.
- * Fused on device: K(X*,X) panel -> mean -> variance (FP64 DMMA contraction with packed L^-1) ->
+ * Fused on device: K(X*,X) panel -> mean -> variance (contraction with packed L^-1: FP64 DMMA, or exact INT8 slice
+ * products on tcgen05 for large pools -- bo_set_sweep_mode) ->
  * EI/LogEI/UCB -> top-k by (value desc, global index asc).  Outputs (device): vals_dev[topk],
  * idx_dev[topk] (entries beyond N are -inf / -1); optional per-candidate mean_dev/var_dev/acq_dev[N].
  * Replaces the chunked pool scan + CPU topk of optimization/Bayesian7.py:664-682 and the
