@@ -443,12 +443,12 @@ static void feed(const char* what, size_t buf_bytes, uint32_t tile, int sms, int
 // MODE 0: SS - 28 slice pairs x 2 K-steps with both operands from shared memory (what sweep_i8_kernel does);
 // MODE 1: TS - per K-step the 7 A slices are first copied smem -> TMEM (tcgen05.cp 128x256b into the 56 columns the
 //         accumulators leave free) and the 28 MMAs read A from TMEM, B from shared memory. ----
-template <int S, int MODE>
+template <int S, int MODE, int KC = 64>
 __global__ void __launch_bounds__(128, 1)
 probe_kernel_stage(int iters, int32_t* __restrict__ out, int* __restrict__ err, long long* __restrict__ cycles) {
-    constexpr int M = 128, N = 64, KC = 64;
+    constexpr int M = 128, N = 64;
     constexpr int A_TILE = M * KC, B_TILE = N * KC;
-    static_assert(S * N + S * 8 <= 512, "TMEM has 512 columns");
+    static_assert(S * N + (MODE ? S * 8 : 0) <= 512, "TMEM has 512 columns");
     extern __shared__ __align__(1024) uint8_t smem[];
     int8_t* sA = reinterpret_cast<int8_t*>(smem);
     int8_t* sB = sA + S * A_TILE;
@@ -479,7 +479,7 @@ probe_kernel_stage(int iters, int32_t* __restrict__ out, int* __restrict__ err, 
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t a_col0 = S * N;
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-    const uint64_t da0 = make_desc(smem_u32(sA), 128, 512), db0 = make_desc(smem_u32(sB), 128, 512);
+    const uint64_t da0 = make_desc(smem_u32(sA), 128, (KC / 16) * 128), db0 = make_desc(smem_u32(sB), 128, (KC / 16) * 128);
     if (warp == 1) {
         uint32_t leader;
         asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(leader));
@@ -536,16 +536,16 @@ probe_kernel_stage(int iters, int32_t* __restrict__ out, int* __restrict__ err, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-template <int S, int MODE>
+template <int S, int MODE, int KC = 64>
 static void stage_probe(int sms) {
-    constexpr int M = 128, N = 64, KC = 64;
+    constexpr int M = 128, N = 64;
     size_t smem = (size_t)S * (M + N) * KC;
-    CK(cudaFuncSetAttribute(probe_kernel_stage<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(probe_kernel_stage<S, MODE, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int32_t* d_out; int* d_err; long long* d_cyc;
     CK(cudaMalloc(&d_out, sizeof(int32_t) * M * S * N)); CK(cudaMemset(d_out, 0xff, sizeof(int32_t) * M * S * N));
     CK(cudaMalloc(&d_err, sizeof(int))); CK(cudaMemset(d_err, 0, sizeof(int)));
     CK(cudaMalloc(&d_cyc, sizeof(long long)));
-    probe_kernel_stage<S, MODE><<<1, 128, smem>>>(1, d_out, d_err, d_cyc);
+    probe_kernel_stage<S, MODE, KC><<<1, 128, smem>>>(1, d_out, d_err, d_cyc);
     CK(cudaDeviceSynchronize());
     std::vector<int32_t> out((size_t)M * S * N);
     CK(cudaMemcpy(out.data(), d_out, out.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -559,14 +559,14 @@ static void stage_probe(int sms) {
                 if ((long)out[(size_t)r * (S * N) + g * N + c] != ref) ++bad;
             }
     const int iters = 4000;
-    probe_kernel_stage<S, MODE><<<sms, 128, smem>>>(iters, nullptr, d_err, d_cyc);
+    probe_kernel_stage<S, MODE, KC><<<sms, 128, smem>>>(iters, nullptr, d_err, d_cyc);
     CK(cudaDeviceSynchronize());
     long long cyc = 0; int err = 0;
     CK(cudaMemcpy(&cyc, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
     const int mmas = S * (S + 1) / 2 * (KC / 32);
-    printf("stage %s S=%d: %ld of %d accumulators differ; %.0f clk per stage = %.1f clk per MMA (%d MMAs%s)%s\n", MODE ? "TS (A slices copied smem -> TMEM per K-step)" : "SS (both operands from smem)",
-           S, bad, M * S * N, (double)cyc / iters, (double)cyc / iters / mmas, mmas, MODE ? " + 14 tcgen05.cp" : "", err ? "  [TIMEOUT]" : "");
+    printf("stage %s S=%d KC=%d: %ld of %d accumulators differ; %.0f clk per stage = %.1f clk per MMA (%d MMAs%s)%s\n", MODE ? "TS (A slices copied smem -> TMEM per K-step)" : "SS (both operands from smem)",
+           S, KC, bad, M * S * N, (double)cyc / iters, (double)cyc / iters / mmas, mmas, MODE ? " + 14 tcgen05.cp" : "", err ? "  [TIMEOUT]" : "");
     cudaFree(d_out); cudaFree(d_err); cudaFree(d_cyc);
 }
 
@@ -580,6 +580,10 @@ int main() {
     const int sms = p.multiProcessorCount;
     stage_probe<7, 0>(sms);
     stage_probe<7, 1>(sms);
+    stage_probe<8, 0>(sms);
+    stage_probe<7, 0, 32>(sms);      // one K-step per slice pair: would a 4-deep ring of 42 KB stages cost MMA rate?
+    stage_probe<7, 0, 128>(sms);     // four K-steps per slice pair (does not fit twice into shared memory)
+    return 0;
     rate<64, 7, 64, 7>(swap, sms, 4000);     // the Ozaki shape: 7 group accumulators x 64 columns = 448 TMEM columns
     rate<64, 8, 64, 8>(swap, sms, 4000);     // 8 slices (FP64-equal accuracy): 512 columns
     rate<128, 7, 64, 4>(swap, sms, 2000);    // rate only (groups folded mod 4): what N=128 would give if TMEM were larger
