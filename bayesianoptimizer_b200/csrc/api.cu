@@ -76,6 +76,10 @@ int bo_release_workspace(bo_handle* h) {
     h->cand_stage = nullptr; h->cand_stage_bytes = 0;
     if (h->panel8) cudaFree(h->panel8);
     h->panel8 = nullptr; h->panel8_bytes = 0;
+    if (h->Lp8) cudaFree(h->Lp8);                 // re-sliced from L^-1 at every sliced sweep anyway
+    h->Lp8 = nullptr; h->Lp8_bytes = 0;
+    if (h->rowscale) cudaFree(h->rowscale);
+    h->rowscale = nullptr; h->rowscale_cap = 0;
     lml_release(h);
     return 0;
 }
