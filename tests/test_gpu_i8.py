@@ -193,6 +193,21 @@ def test_full_size_c3_sample_i8_against_oracle(engine):
         assert idx.cpu().tolist() == ti.tolist()
 
 
+def test_release_workspace_then_sliced_sweep_is_bit_identical(engine):
+    """bo_release_workspace frees the int8 operand pack and the panels (for the co-resident simulator); the next sliced
+    sweep re-creates them on demand and scores bit-identically (tools/i8_release_check.py)."""
+    from bayesianoptimizer_b200 import sobol_state
+    X, y = synth_problem(700, 6, 31, 32)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", 0.6, 1.0, 1e-3)
+    engine.set_sweep_mode("auto")
+    st = sobol_state(6, 5)
+    v1, i1 = engine.sweep("ei", float(y.max()), sobol=st, count=40_000, topk=8)
+    assert engine.last_sweep_path() == 8
+    engine.release_workspace()
+    v2, i2 = engine.sweep("ei", float(y.max()), sobol=st, count=40_000, topk=8)
+    assert engine.last_sweep_path() == 8 and torch.equal(v1, v2) and torch.equal(i1, i2)
+
+
 def test_i8_peak_probe_reports_a_tensor_rate(engine):
     X, y = synth_problem(256, 3, 1, 2)
     engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "rbf", 0.5, 1.0, 1e-3)
