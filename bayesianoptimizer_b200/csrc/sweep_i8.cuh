@@ -27,7 +27,8 @@ constexpr int I8_STAGES  = 2;
 constexpr int I8_THREADS = 384;                // warpgroup 0 (warps 0-3): drain + epilogue; 1: warp 4 TMA, warp 5 MMA issue, 6-7 idle; 2 (warps 8-11): panel builders
 constexpr int I8_A_SLICE = SW_BM * I8_KC;      // 8 KB
 constexpr int I8_B_SLICE = I8_BN * I8_KC;      // 4 KB
-constexpr int I8_MIN_NP  = 256;                // below this the stage pipeline is all start-up
+constexpr int I8_MIN_NP  = 256;                // below this the stage pipeline is all start-up (pinned modes fall back to FP64)
+constexpr int I8_AUTO_MIN_NP = 512;            // AUTO: smallest padded n the sliced path was measured faster at
 
 template <int S, int DP>
 struct I8Smem {
@@ -528,6 +529,7 @@ int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
     if (mode == BO_SWEEP_FP64 || !sweep_i8_model_ok(h)) return BO_SWEEP_FP64;
     if (mode == BO_SWEEP_I8X7 || mode == BO_SWEEP_I8X8) return mode;
     if ((pool + I8_BN - 1) / I8_BN < 2LL * h->sm_count) return BO_SWEEP_FP64;
+    if (h->np < I8_AUTO_MIN_NP) return BO_SWEEP_FP64;     // measured gain starts at n = 512 (1.33x); below it was not measured
     // far below the reference's noise floor (1e-4 on standardised targets) the model itself is ill-conditioned; the
     // 8-slice product was validated down to ratio 1e-4 (tools/ozaki_feasibility.py) -- keep the FP64 contraction beyond
     if ((h->hyp.noise + h->hyp.jitter) / h->hyp.outputscale < 1e-5) return BO_SWEEP_FP64;
