@@ -131,6 +131,11 @@ def test_auto_mode_policy_and_sharded_resolution(engine):
     assert engine.resolve_sweep_mode(10**6) == "fp64"
     engine.fit(Xd[:100], yd[:100], "rbf", 0.6, 1.0, 1e-3)
     assert engine.resolve_sweep_mode(10**6) == "fp64"            # one stage of rows: not worth a pipeline
+    engine.fit(Xd[:300], yd[:300], "rbf", 0.6, 1.0, 1e-3)        # 384 padded rows: AUTO waits for 512, a pinned mode does not
+    assert engine.resolve_sweep_mode(10**6) == "fp64"
+    engine.set_sweep_mode("i8x8")
+    assert engine.resolve_sweep_mode(10**6) == "i8x8"
+    engine.set_sweep_mode("auto")
     engine.fit(Xd, yd, "matern52", 0.6, 1.0, 1e-3)
     st = sobol_state(5, 3)
     total, k = 60_000, 4
