@@ -20,8 +20,9 @@ def test_randomised_parity_slice():
 
 def test_randomised_parity_slice_on_the_sliced_sweep():
     """The same generator with the contraction pinned to the INT8-sliced path (8 slices): every eligible model (exact GP,
-    Matern / RBF, n > 128) takes it whatever the pool size; 160 cases ran clean during development (seed 21)."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "40", "23", "i8x8"], capture_output=True,
+    Matern / RBF, n > 128) takes it whatever the pool size; 160 cases ran clean during development (seed 21,
+    profiles/r01_fuzz_i8x8.log) -- the suite keeps their first 40."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "40", "21", "i8x8"], capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "40 cases, 0 failures" in r.stdout
