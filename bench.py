@@ -354,8 +354,9 @@ def main():
                                        "operands); MEASURED_PEAKS.json has no INT8 entry",
                         "int8_ops_per_candidate": int8_ops_per_cand, "kernel_ms": kms,
                         "note": "the FP64 contraction u = L^-1 k* runs as an error-free product of signed 7-bit slices; TMEM (512 "
-                                "columns) limits the tile to 64 candidates x S accumulators, an MMA shape that reaches about half of "
-                                "the INT8 peak (profiles/r01_int8_tcgen05_probe.log)",
+                                "columns) limits the tile to 64 candidates x S accumulators; a 128x64x32 kind::i8 MMA takes 50 SM cycles in "
+                                "isolation against 34 at the N=256 rate, i.e. this shape tops out at 0.68 of the pipe's peak "
+                                "(profiles/r01_int8_tcgen05_probe.log, 'stage' lines)",
                         "fp64_equivalent": {"achieved_tflops": achieved, "fp64_dmma_peak_tflops": peak_tflops,
                                             "ratio_to_fp64_dmma_peak": achieved / peak_tflops, "flop_per_candidate": fpc,
                                             "fp64_dmma_path": fp64_side}}
