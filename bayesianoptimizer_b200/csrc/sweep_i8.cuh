@@ -530,9 +530,10 @@ int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
     if (mode == BO_SWEEP_I8X7 || mode == BO_SWEEP_I8X8) return mode;
     if ((pool + I8_BN - 1) / I8_BN < 2LL * h->sm_count) return BO_SWEEP_FP64;
     if (h->np < I8_AUTO_MIN_NP) return BO_SWEEP_FP64;     // measured gain starts at n = 512 (1.33x); below it was not measured
-    // far below the reference's noise floor (1e-4 on standardised targets) the model itself is ill-conditioned; the
-    // 8-slice product was validated down to ratio 1e-4 (tools/ozaki_feasibility.py) -- keep the FP64 contraction beyond
-    if ((h->hyp.noise + h->hyp.jitter) / h->hyp.outputscale < 1e-5) return BO_SWEEP_FP64;
+    // below the reference's noise floor (1e-4 on standardised targets) the model itself is ill-conditioned: on the
+    // reference's n = 3000 rows at ratio 7.7e-5 the 8-slice product is at 6e-9 where the FP64 product is at 2e-9
+    // (tools/ozaki_golden.py) -- still inside 1e-8, but the margin is gone, so AUTO keeps the FP64 contraction there
+    if ((h->hyp.noise + h->hyp.jitter) / h->hyp.outputscale < 1e-4) return BO_SWEEP_FP64;
     return sweep_i8_slices(h->hyp) == 7 ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;
 }
 

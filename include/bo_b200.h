@@ -228,7 +228,7 @@ int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, in
  * Matern-5/2 or RBF kind, at least 256 (padded) observations; every other model runs the FP64 DMMA path in every mode.
  * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
  * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates, models with fewer than 512
- * (padded) observations and models with noise / outputscale < 1e-5 on the FP64 path. */
+ * (padded) observations and models with noise / outputscale < 1e-4 on the FP64 path. */
 int bo_set_sweep_mode(bo_handle* h, int32_t mode);
 
 /* The pinned mode (BO_SWEEP_FP64 / I8X7 / I8X8) the handle's current mode resolves to for a pool of pool_total
