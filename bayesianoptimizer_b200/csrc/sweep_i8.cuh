@@ -11,14 +11,17 @@
 // 6e-10 relative at the C3 shape (bar: 1e-8), S = 8 is indistinguishable from the FP64 product.
 //
 // Shape: TMEM holds 512 columns, so S accumulators allow N = 64 candidates per CTA tile (M = 128 rows of L^-1).
-// Per block of 64 candidates:
-//   phase A  (warps 0-3) candidates, K(X, X*) in FP64, posterior mean, digits -> this CTA's int8 panel in HBM/L2;
-//   phase B  warp 4 streams stage tiles (S slices of a 128 x 64 piece of L^-1 and of a 64 x 64 piece of the panel,
-//            pre-arranged in the tensor core's K-major 8 x 16 B core-matrix order) with TMA bulk copies into a 2-stage
-//            ring; one lane of warp 5 issues the S (S + 1) / 2 x 2 MMAs of a stage and commits to the ring's empty barrier and,
-//            per row block, to the accumulator-full barrier; warps 0-3 (one TMEM lane = one row of L^-1 each) drain the
-//            accumulators with tcgen05.ld, recombine and keep sum_i u_i^2 for their row in registers;
-//   epilogue variance, acquisition, CTA-local top-k (as sweep_kernel).
+// One persistent CTA of 384 threads per SM, three warpgroups (registers re-balanced with setmaxnreg):
+//   builders (warps 8-11)  for the NEXT block of 64 candidates: Sobol point / explicit row, K(X, X*) in FP64, posterior
+//            mean, digits (integer shifts and masks) -> one of this CTA's two int8 panel buffers in HBM/L2;
+//   warp 4   streams stage tiles (S slices of a 128 x 64 piece of L^-1 and of a 64 x 64 piece of the current panel,
+//            both pre-arranged in the tensor core's K-major 8 x 16 B core-matrix order) with TMA bulk copies into a
+//            2-stage ring;
+//   warp 5   one elected lane issues the S (S + 1) / 2 x 2 MMAs of a stage (fully unrolled, descriptors in uniform
+//            registers) and commits to the ring's empty barrier and, per row block, to the accumulators-full barrier;
+//   warps 0-3 (one TMEM lane = one row of L^-1 each) drain the accumulators with tcgen05.ld, recombine, keep
+//            sum_i u_i^2 per candidate in registers, then run the epilogue: variance, acquisition, CTA-local top-k
+//            (as sweep_kernel).
 // Replaces the same reference code as sweep_kernel (optimization/Bayesian7.py:664-682, Bayesian.py:105-112).
 
 constexpr int I8_BN      = 64;                 // candidates per CTA tile (TMEM: S * 64 columns)
