@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbo_b200.so")
+# BO_B200_LIB: A/B builds of the same ABI for the profiling tools (csrc/Makefile `alt`); the product loads libbo_b200.so
+LIB_PATH = os.environ.get("BO_B200_LIB") or os.path.join(_HERE, "libbo_b200.so")
 
 BO_MAX_DIM = 16
 BO_MAX_TOPK = 64
@@ -66,6 +67,7 @@ SIGNATURES = {
     "bo_set_sweep_mode": (C.c_int, [_vp, _i32]),
     "bo_resolve_sweep_mode": (C.c_int, [_vp, _i64]),
     "bo_last_sweep_path": (C.c_int, [_vp]),
+    "bo_last_sweep_flagged": (C.c_int64, [_vp]),
     "bo_i8_peak": (C.c_int, [_vp, _f64, _pd]),
     "bo_launch_count": (C.c_int64, [_vp]),
     "bo_last_sweep_ms": (C.c_double, [_vp]),

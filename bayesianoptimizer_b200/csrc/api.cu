@@ -76,10 +76,12 @@ int bo_release_workspace(bo_handle* h) {
     h->cand_stage = nullptr; h->cand_stage_bytes = 0;
     if (h->panel8) cudaFree(h->panel8);
     h->panel8 = nullptr; h->panel8_bytes = 0;
-    if (h->Lp8) cudaFree(h->Lp8);                 // re-sliced from L^-1 at every sliced sweep anyway
-    h->Lp8 = nullptr; h->Lp8_bytes = 0;
+    if (h->Lp8) cudaFree(h->Lp8);                 // re-sliced from L^-1 by the next sliced sweep
+    h->Lp8 = nullptr; h->Lp8_bytes = 0; h->Lp8_epoch = 0;
     if (h->rowscale) cudaFree(h->rowscale);
     h->rowscale = nullptr; h->rowscale_cap = 0;
+    if (h->flag_idx) cudaFree(h->flag_idx);
+    h->flag_idx = nullptr; h->flag_cap = 0;
     lml_release(h);
     return 0;
 }
@@ -92,9 +94,10 @@ void bo_destroy(bo_handle* h) {
     lml_release(h);
     void* ptrs[] = {h->qbuf, h->split_ws, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
-                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws, h->Lp8, h->rowscale};
+                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws, h->Lp8, h->rowscale, h->guard_dev, h->flag_count_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->info_host) cudaFreeHost(h->info_host);
+    if (h->flag_count_host) cudaFreeHost(h->flag_count_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     cudaGetLastError();
@@ -163,8 +166,10 @@ int bo_posterior(bo_handle* h, const double* Xs_dev, int64_t N, double min_varia
                  double* var_dev, void* stream) {
     if (!h) return BO_E_INVALID;
     if (!Xs_dev && N > 0) return fail(h, BO_E_INVALID, "bo_posterior: null candidates");
+    // model.posterior numerics do not depend on N: AUTO keeps bo_posterior on the FP64 contraction, the sliced path is opt-in
+    // here (a pinned BO_SWEEP_I8X* mode)
     return sweep_impl(h, BO_ACQ_MEAN, 0.0, 0.0, min_variance, Xs_dev, nullptr, 0, N, 0, nullptr, nullptr,
-                      mean_dev, var_dev, nullptr, (cudaStream_t)stream);
+                      mean_dev, var_dev, nullptr, (cudaStream_t)stream, h->sweep_mode == BO_SWEEP_AUTO ? BO_SWEEP_FP64 : -1);
 }
 
 int bo_posterior_multi(bo_handle* h, const double* Y_dev, int32_t m, const double* means_host, const double* Xs_dev,
@@ -270,6 +275,7 @@ int bo_resolve_sweep_mode(const bo_handle* h, int64_t pool_total) {
 }
 
 int bo_last_sweep_path(const bo_handle* h) { return (h && h->sweep_timed) ? h->sweep_path : -1; }
+int64_t bo_last_sweep_flagged(const bo_handle* h) { return (h && h->sweep_timed) ? h->sweep_flagged : 0; }
 
 int bo_i8_peak(bo_handle* h, double seconds, double* tops_host) {
     if (!h || !tops_host) return BO_E_INVALID;

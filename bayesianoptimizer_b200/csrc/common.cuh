@@ -112,6 +112,14 @@ struct bo_handle {
     int8_t* panel8 = nullptr; size_t panel8_bytes = 0;
     int sweep_mode = BO_SWEEP_AUTO;   // bo_set_sweep_mode
     int sweep_path = 0;               // contraction of the last sweep: 0 = FP64 DMMA, 7 / 8 = INT8 slices
+    // the int8 pack of L^-1 is cached: factor_epoch moves whenever L^-1 changes (fit, append, SVGP load)
+    uint64_t factor_epoch = 1, Lp8_epoch = 0; int Lp8_S = 0;
+    // accuracy guard of the sliced sweep: candidates whose variance is too small for the slicing error bound are listed
+    // here by the sweep kernel and re-scored on the FP64 contraction (sweep_i8.cuh)
+    double* guard_dev = nullptr;              // [2]: max_i rowscale_i^2 (i + 1) as a double and its bit pattern (atomicMax)
+    long long* flag_idx = nullptr; size_t flag_cap = 0;
+    int* flag_count_dev = nullptr; int* flag_count_host = nullptr;   // host copy is pinned
+    long long sweep_flagged = 0;      // candidates of the last sweep that went through the FP64 re-score (-1: whole pool)
 
     void* select_ws = nullptr; size_t select_bytes = 0;  // large top-K (select.cu)
 
@@ -285,7 +293,7 @@ int ensure_capacity(bo_handle* h, int np, cudaStream_t st);
 int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
                const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
                int topk, double* vals_dev, int64_t* idx_dev, double* mean_dev, double* var_dev,
-               double* acq_dev, cudaStream_t st);
+               double* acq_dev, cudaStream_t st, int mode_override = -1);     // mode_override: a BO_SWEEP_* mode, -1 = the handle's
 int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,
                       double* out_dev, cudaStream_t st);
 int fp64_peak_impl(bo_handle* h, int use_dmma, double seconds, double* tflops);

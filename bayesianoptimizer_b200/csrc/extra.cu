@@ -537,6 +537,7 @@ int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, c
     if (!x_dev) return fail(h, BO_E_INVALID, "bo_append: null point");
     BO_CUDA(h, cudaSetDevice(h->device));
     int rc;
+    const int np_before = h->np;
     if (h->n == h->np) {
         // open a new padded block row: identity on the diagonal, zeros elsewhere
         const int np_new = h->np + PAD;
@@ -561,9 +562,11 @@ int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, c
     if (*h->info_host != 0) {
         h->err = "bo_append: bordered matrix not positive definite (duplicate point with zero noise?)";
         // the padded row was left untouched (identity) by the finalize kernel; repacked tiles are unchanged
+        if (h->np != np_before) { h->np = np_before; h->plan_np = -1; }      // give the freshly opened block row back
         return *h->info_host;
     }
     h->n += 1;
+    h->factor_epoch++;
     return 0;
 }
 
@@ -713,7 +716,8 @@ int posterior_multi_impl(bo_handle* h, const double* Y_dev, int m, const double*
     }
     if (N > 0 && (rc = BO_DISPATCH_DP(h->dp, launch_multi_mean, h, Xs_dev, N, A, m, means_dev, mean_dev, st))) return rc;
     if (var_dev && N > 0)
-        return sweep_impl(h, BO_ACQ_MEAN, 0.0, 0.0, min_var, Xs_dev, nullptr, 0, N, 0, nullptr, nullptr, nullptr, var_dev, nullptr, st);
+        return sweep_impl(h, BO_ACQ_MEAN, 0.0, 0.0, min_var, Xs_dev, nullptr, 0, N, 0, nullptr, nullptr, nullptr, var_dev, nullptr, st,
+                          h->sweep_mode == BO_SWEEP_AUTO ? BO_SWEEP_FP64 : -1);
     return 0;
 }
 

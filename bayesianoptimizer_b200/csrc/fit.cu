@@ -611,6 +611,7 @@ static int factor_and_pack(bo_handle* h, bool with_alpha, cudaStream_t st) {
         return info > h->n ? h->n : info;
     }
     h->fitted = true;
+    h->factor_epoch++;
     return 0;
 }
 int refit_factor(bo_handle* h, cudaStream_t st) { return factor_and_pack(h, true, st); }

@@ -38,7 +38,11 @@ struct SweepArgs {
     // SVGP predictive mode (SV kernels): second triangular factor J Ls^T J (packed like Lp), the panel that receives the
     // row-reversed interp term u = L^-1 k*, and the constant added to the prior variance (K_uu jitter + likelihood noise)
     const double* Lp2; double* panel2; double sv_add;
+    // re-score pass of the sliced sweep's accuracy guard: candidate li of this launch is pool entry idx_map[li] (coordinates,
+    // dense outputs and top-k index all go through the map); nullptr = the identity
+    const long long* idx_map;
 };
+__device__ __forceinline__ long long pool_index(const SweepArgs& a, long long li) { return a.idx_map ? a.idx_map[li] : li; }
 
 // ---- analytic acquisition (botorch.acquisition.analytic semantics) ------
 __device__ __forceinline__ double log1mexp_d(double x) {
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             for (int gi = 0; gi < 2; ++gi) {
                 long long li = blk * SW_BN + (warp + 8 * gi) * 8 + g;
                 if (li >= a.N) li = a.N - 1;
+                li = pool_index(a, li);
                 if (a.cand) {
 #pragma unroll
                     for (int k = 0; k < DP; ++k) xc[gi][k] = (k < a.d) ? a.cand[(size_t)li * a.d + k] : 0.0;
@@ -432,16 +437,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
             const double var = fmax((SV ? prior + a.sv_add : prior) - ss, a.min_var);
             const double mean = a.hyp.mean + mu_c;
             double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
+            const long long pi = li < a.N ? pool_index(a, li) : li;
             if (li < a.N) {
-                if (a.mean_out) a.mean_out[li] = mean;
-                if (a.var_out) a.var_out[li] = var;
-                if (a.acq_out) a.acq_out[li] = v;
+                if (a.mean_out) a.mean_out[pi] = mean;
+                if (a.var_out) a.var_out[pi] = var;
+                if (a.acq_out) a.acq_out[pi] = v;
             }
             if (!(v == v)) v = -INFINITY;                    // NaN ranks last
             acq_s[tid] = v;
             // only candidates that beat the current k-th entry can enter the list (the list only improves)
             bool beats = false;
-            if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
+            if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + pi, tkv[a.topk - 1], tki[a.topk - 1]);
             const unsigned m = __ballot_sync(0xffffffffu, beats);
             if (lane == 0) cmask[warp] = m;
         }
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     const int c = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
                     const double v = acq_s[c];
-                    const long long gi = a.first_index + blk * SW_BN + c;
+                    const long long gi = a.first_index + pool_index(a, blk * SW_BN + c);
                     if (!tk_better(v, gi, tkv[K - 1], tki[K - 1])) continue;
                     int p = K - 1;
                     while (p > 0 && tk_better(v, gi, tkv[p - 1], tki[p - 1])) { tkv[p] = tkv[p - 1]; tki[p] = tki[p - 1]; --p; }
@@ -671,9 +677,11 @@ static int ensure_split_ws(bo_handle* h, long long nblocks, int G, int nbm) {
     return 0;
 }
 
-static int ensure_sweep_ws(bo_handle* h, int grid, bool fp64_panel = true) {
-    // the sliced sweep keeps its own int8 panels: it only needs the per-CTA top-k lists from here
+static int ensure_sweep_ws(bo_handle* h, int grid, bool fp64_panel = true, int lists = 0) {
+    // the sliced sweep keeps its own int8 panels: it only needs the per-CTA top-k lists from here (`lists` of them when
+    // more than `grid`: its re-score pass appends the FP64 kernel's lists behind its own)
     const size_t need = fp64_panel ? (size_t)grid * (h->np / SW_BK) * SW_TILE * sizeof(double) : 0;
+    if (lists > grid) grid = lists;
     if (need > h->panel_bytes) {
         if (h->panel) cudaFree(h->panel);
         h->panel = nullptr; h->panel_bytes = 0;
@@ -738,6 +746,62 @@ static int launch_sobol_points(bo_handle* h, const int64_t* idx, int64_t N, doub
      (dp) == 6 ? fn<6>(__VA_ARGS__) : (dp) == 8 ? fn<8>(__VA_ARGS__) :  \
      (dp) == 12 ? fn<12>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
 
+// The FP64 DMMA sweep of a prepared argument block (hyper-parameters, pool, outputs).  The per-CTA top-k lists go to
+// slots [part_off, part_off + grid) of the handle's list buffers; `merge` reduces them to vals_dev / idx_dev.  Returns the
+// grid through *grid_out.
+static int sweep_fp64_run(bo_handle* h, SweepArgs a, int part_off, bool merge, double* vals_dev, int64_t* idx_dev, int* grid_out,
+                          cudaStream_t st) {
+    int rc;
+    a.nblocks = (a.N + SW_BN - 1) / SW_BN;
+    {
+        const char* gs = getenv("BO_B200_SWEEP_SEGMENTS");      // test hook: force a segment count
+        a.G = choose_segments(h->sm_count, a.nblocks, h->np / SW_BM, a.seg);
+        if (h->svgp) {                 // the second pass needs the whole interp term of a block in one CTA: no row split
+            a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
+        } else if (gs && atoi(gs) >= 1) {
+            const int nbm = h->np / SW_BM;
+            int G = atoi(gs); if (G > nbm) G = nbm; if (G > SW_MAX_SEG) G = SW_MAX_SEG;
+            // re-use the balancing by pretending a pool that makes G optimal: simple equal-stage split
+            const double total = 0.5 * nbm * (nbm + 1.0);
+            a.seg[0] = 0;
+            for (int s2 = 1; s2 < G; ++s2) {
+                int b = (int)floor((-1.0 + sqrt(1.0 + 8.0 * total * s2 / G)) / 2.0 + 0.5);
+                if (b <= a.seg[s2 - 1]) b = a.seg[s2 - 1] + 1;
+                if (b > nbm - (G - s2)) b = nbm - (G - s2);
+                a.seg[s2] = b;
+            }
+            a.seg[G] = nbm; a.G = G;
+        }
+    }
+    const long long items = a.nblocks * a.G;
+    const int grid = (int)(items < h->sm_count ? items : h->sm_count);
+    if ((rc = ensure_sweep_ws(h, grid, true, part_off + grid))) return rc;
+    if (a.G > 1) {
+        const int nbm = h->np / SW_BM;
+        if ((rc = ensure_split_ws(h, a.nblocks, a.G, nbm))) return rc;
+        a.part_cs = reinterpret_cast<double*>(h->split_ws);              // [nblocks][nbm][2][128] row-block sums
+        a.part_mu = a.part_cs + (size_t)a.nblocks * nbm * 2 * SW_BN;
+        a.part_kss = a.part_mu + (size_t)a.nblocks * SW_BN;
+        a.counters = reinterpret_cast<int*>(a.part_kss + (size_t)a.nblocks * SW_BN);
+        BO_CUDA(h, cudaMemsetAsync(a.counters, 0, (size_t)a.nblocks * sizeof(int), st));
+    }
+    a.panel = h->panel;
+    a.part_val = h->part_val + (size_t)part_off * BO_MAX_TOPK; a.part_idx = (long long*)h->part_idx + (size_t)part_off * BO_MAX_TOPK;
+    if (h->svgp) { a.Lp2 = h->Lp2; a.panel2 = h->panel2; a.sv_add = h->sv_add; }
+    if (merge) BO_CUDA(h, cudaEventRecord(h->ev0, st));
+    if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep, h, a, grid, st))) return rc;
+    if (merge) {
+        BO_CUDA(h, cudaEventRecord(h->ev1, st));
+        h->sweep_timed = true; h->sweep_path = 0; h->sweep_flagged = 0;
+        if (a.topk > 0) {
+            topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, (part_off + grid) * BO_MAX_TOPK, a.topk, vals_dev, (long long*)idx_dev);
+            BO_LAUNCH_CHECK(h);
+        }
+    }
+    if (grid_out) *grid_out = grid;
+    return 0;
+}
+
 #include "sweep_i8.cuh"
 
 static int upload_sobol(bo_handle* h, const bo_sobol* sobol_host, cudaStream_t st) {
@@ -751,7 +815,7 @@ static int upload_sobol(bo_handle* h, const bo_sobol* sobol_host, cudaStream_t s
 int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double min_var,
                const double* cand_dev, const bo_sobol* sobol_host, int64_t first_index, int64_t N,
                int topk, double* vals_dev, int64_t* idx_dev, double* mean_dev, double* var_dev,
-               double* acq_dev, cudaStream_t st) {
+               double* acq_dev, cudaStream_t st, int mode_override) {
     if (!h->fitted) return fail(h, BO_E_NOTFIT, "sweep before a successful bo_fit");
     if (N < 0 || first_index < 0 || topk < 0) return fail(h, BO_E_INVALID, "bo_sweep: negative size");
     if (topk > BO_MAX_TOPK) return fail(h, BO_E_CAPACITY, "bo_sweep: topk exceeds BO_MAX_TOPK");
@@ -808,7 +872,7 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
 
     {
         // which contraction: the handle's mode (bo_set_sweep_mode), overridable for triage by BO_B200_SWEEP_IMPL=fp64|i8
-        int mode = h->sweep_mode;
+        int mode = mode_override >= 0 ? mode_override : h->sweep_mode;
         if (impl && strcmp(impl, "fp64") == 0) mode = BO_SWEEP_FP64;
         if (impl && strcmp(impl, "i8") == 0) {
             const char* sl = getenv("BO_B200_I8_SLICES");
@@ -817,54 +881,11 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
         mode = resolve_sweep_mode(h, mode, N);
         if (mode != BO_SWEEP_FP64) {
             const int S = mode == BO_SWEEP_I8X7 ? 7 : 8;
-            a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
             return sweep_i8_run(h, a, S, vals_dev, idx_dev, st);
         }
     }
 
-    {
-        const char* gs = getenv("BO_B200_SWEEP_SEGMENTS");      // test hook: force a segment count
-        a.G = choose_segments(h->sm_count, a.nblocks, h->np / SW_BM, a.seg);
-        if (h->svgp) {                 // the second pass needs the whole interp term of a block in one CTA: no row split
-            a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
-        } else if (gs && atoi(gs) >= 1) {
-            const int nbm = h->np / SW_BM;
-            int G = atoi(gs); if (G > nbm) G = nbm; if (G > SW_MAX_SEG) G = SW_MAX_SEG;
-            // re-use the balancing by pretending a pool that makes G optimal: simple equal-stage split
-            const double total = 0.5 * nbm * (nbm + 1.0);
-            a.seg[0] = 0;
-            for (int s2 = 1; s2 < G; ++s2) {
-                int b = (int)floor((-1.0 + sqrt(1.0 + 8.0 * total * s2 / G)) / 2.0 + 0.5);
-                if (b <= a.seg[s2 - 1]) b = a.seg[s2 - 1] + 1;
-                if (b > nbm - (G - s2)) b = nbm - (G - s2);
-                a.seg[s2] = b;
-            }
-            a.seg[G] = nbm; a.G = G;
-        }
-    }
-    const long long items = a.nblocks * a.G;
-    const int grid = (int)(items < h->sm_count ? items : h->sm_count);
-    if ((rc = ensure_sweep_ws(h, grid))) return rc;
-    if (a.G > 1) {
-        const int nbm = h->np / SW_BM;
-        if ((rc = ensure_split_ws(h, a.nblocks, a.G, nbm))) return rc;
-        a.part_cs = reinterpret_cast<double*>(h->split_ws);              // [nblocks][nbm][2][128] row-block sums
-        a.part_mu = a.part_cs + (size_t)a.nblocks * nbm * 2 * SW_BN;
-        a.part_kss = a.part_mu + (size_t)a.nblocks * SW_BN;
-        a.counters = reinterpret_cast<int*>(a.part_kss + (size_t)a.nblocks * SW_BN);
-        BO_CUDA(h, cudaMemsetAsync(a.counters, 0, (size_t)a.nblocks * sizeof(int), st));
-    }
-    a.panel = h->panel; a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
-    if (h->svgp) { a.Lp2 = h->Lp2; a.panel2 = h->panel2; a.sv_add = h->sv_add; }
-    BO_CUDA(h, cudaEventRecord(h->ev0, st));
-    if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep, h, a, grid, st))) return rc;
-    BO_CUDA(h, cudaEventRecord(h->ev1, st));
-    h->sweep_timed = true; h->sweep_path = 0;
-    if (topk > 0) {
-        topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, topk, vals_dev, (long long*)idx_dev);
-        BO_LAUNCH_CHECK(h);
-    }
-    return 0;
+    return sweep_fp64_run(h, a, 0, true, vals_dev, idx_dev, nullptr, st);
 }
 
 int sobol_points_impl(bo_handle* h, const bo_sobol* sobol_host, const int64_t* idx_dev, int64_t N,

@@ -25,8 +25,14 @@
 // Replaces the same reference code as sweep_kernel (optimization/Bayesian7.py:664-682, Bayesian.py:105-112).
 
 constexpr int I8_BN      = 64;                 // candidates per CTA tile (TMEM: S * 64 columns)
-constexpr int I8_KC      = 64;                 // contraction bytes per pipeline stage
-constexpr int I8_STAGES  = 2;
+#ifndef BO_I8_KC
+#define BO_I8_KC 64
+#endif
+#ifndef BO_I8_STAGES
+#define BO_I8_STAGES 2
+#endif
+constexpr int I8_KC      = BO_I8_KC;           // contraction bytes per pipeline stage
+constexpr int I8_STAGES  = BO_I8_STAGES;
 constexpr int I8_THREADS = 384;                // warpgroup 0 (warps 0-3): drain + epilogue; 1: warp 4 TMA, warp 5 MMA issue, 6-7 idle; 2 (warps 8-11): panel builders
 constexpr int I8_A_SLICE = SW_BM * I8_KC;      // 8 KB
 constexpr int I8_B_SLICE = I8_BN * I8_KC;      // 4 KB
@@ -56,7 +62,23 @@ struct SweepI8Args {
     const int8_t* Lp8; const double* rowscale; int8_t* panel8;
     double dig_scale;       // 2^(6 + 7 (S - 1)) / (power-of-two bound of |k*|): k* -> fixed point
     double eb_scale;        // eb * 2^-12: folded into the row scale at the drain
+    // accuracy guard: a candidate whose variance s2 - ||u||^2 is below guard_scale * sqrt(W ||u||^2), W = guard_w[0] =
+    // max_i rowscale_i^2 (i + 1), is not scored here: its pool position goes to flag_idx (warp-aggregated append through
+    // flag_count) and the FP64 contraction re-scores it after the kernel
+    double guard_scale; const double* guard_w;
+    long long* flag_idx; int* flag_count; long long flag_cap;
 };
+
+// Slicing error of ||u||^2 (what the guard bounds).  Row i of L^-1 is cut at 2^(-7 S) of its power-of-two scale and the
+// products of slices s + t >= S are dropped: per element product an error of about 2^(-7 S) rowscale_i eb with random sign
+// (eb: the power-of-two bound of |k*|), (S - 1) dropped pairs of rms 1/3 each, i + 1 products per row:
+//     delta u_i ~ 2^(-7 S) eb rowscale_i sqrt((S - 1)(i + 1)) / 3,      delta ||u||^2 = 2 sum_i u_i delta u_i
+//     rms(delta ||u||^2) <= 2 sqrt(S - 1) / 3  2^(-7 S) eb sqrt(W ||u||^2)        (< 1.8 x that expression for S <= 8).
+// tools/ozaki_guard_study.py measures the true 7- and 8-slice errors on the reference's CSV rows against it.  A candidate is
+// flagged when I8_GUARD_KAPPA times the expression exceeds I8_GUARD_RTOL of its variance: unflagged candidates carry a slicing
+// error below 2e-9 relative (4.5 sigma), a fifth of the 1e-8 bar, on top of the FP64 recombination's own rounding.
+constexpr double I8_GUARD_KAPPA = 8.0;
+constexpr double I8_GUARD_RTOL  = 2e-9;
 
 // S balanced radix-128 digits of x (|x| <= 1): x ~= sum_s d[s] 2^(-6-7s), rounding only in the last place.
 // xs = x * 2^(6 + 7 (S - 1)) (an exact scaling, folded into the caller's power-of-two scale).
@@ -86,14 +108,24 @@ __device__ __forceinline__ void i8_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {     // K-major, no swizzle: LBO 128 B (next 16 k), SBO 512 B (next 8 rows)
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46);
+// K-major, no swizzle: LBO 128 B (next 16 k), SBO = one 8-row group of the tile = (K bytes / 16) core matrices of 128 B
+__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr, uint32_t sbo = (I8_KC / 16) * 128) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
+// COLL: use of the A-operand collector buffer (SASS A_KEEP / A_REUSE): 0 none, 1 fill (read A from shared memory and keep
+// it), 2 use (A is the tile the previous MMA kept), 3 lastuse.  In the sweep's issue order slice s of a stage tile of L^-1
+// multiplies S - s panel slices back to back, so A is read from shared memory S times per S (S + 1) / 2 MMAs; without the
+// reuse the 128 x 64 x 32 shape is bound by the 6 KB of operand reads per MMA (50 clk), with it by the tensor pipe
+// (37 clk, floor 32: profiles/r02_i8_collector_probe.log).
+template <int COLL>
 __device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+#define BO_I8_MMA(coll) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8" coll " [%0], %1, %2, %3, p;\n\t}\n" \
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory")
+    if (COLL == 1) BO_I8_MMA(".collector::a::fill");
+    else if (COLL == 2) BO_I8_MMA(".collector::a::use");
+    else if (COLL == 3) BO_I8_MMA(".collector::a::lastuse");
+    else BO_I8_MMA("");
+#undef BO_I8_MMA
 }
 __device__ __forceinline__ bool i8_elect() {
     uint32_t p;
@@ -103,16 +135,29 @@ __device__ __forceinline__ bool i8_elect() {
 __device__ __forceinline__ void i8_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void l2_prefetch(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
 }
+// exact int32 -> FP64 without the quarter-rate I2F.F64: 2^52 + 2^31 + x is exactly representable, so gluing the biased
+// integer under the exponent of 2^52 and subtracting the constant costs one LOP3 and one full-rate DADD
+__device__ __forceinline__ double i8_s32_to_f64(int x) {
+    return __hiloint2double(0x43300000, x ^ (int)0x80000000) - 4503601774854144.0;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- operand preparation: row scales and int8 slices of L^-1 in stage-tile order --------------------------------
-__global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restrict__ Li, int ld, int np, double* __restrict__ rowscale) {
+__global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restrict__ Li, int ld, int np, int n, double* __restrict__ rowscale,
+                                                          double* __restrict__ guard_w) {
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= np) return;
     double m = 0.0;
@@ -121,7 +166,10 @@ __global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restri
     for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
         int e; frexp(m, &e);                          // m = f 2^e, f in [0.5, 1): |x| = |L^-1| 2^-e < 1
-        rowscale[i] = (m > 0.0) ? ldexp(1.0, e) : 1.0;
+        const double rs = (m > 0.0) ? ldexp(1.0, e) : 1.0;
+        rowscale[i] = rs;
+        // W = max over the real rows of rowscale_i^2 (i + 1): positive doubles order like their bit patterns
+        if (i < n) atomicMax(reinterpret_cast<unsigned long long*>(guard_w), (unsigned long long)__double_as_longlong(rs * rs * (double)(i + 1)));
     }
 }
 
@@ -339,8 +387,22 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             if (prof) t_w2 += clock64() - tB0;
             if (warp == 4) {
                 if (lane == 0) {
+                    // The ring holds two stages, i.e. one stage time (~1.8 us) of latency tolerance, and the panel tiles come
+                    // from HBM (148 CTAs x 2 x 2 MB of panels do not fit L2): an L2 prefetch I8_PF stages ahead of the copies
+                    // turns them into L2 hits without costing shared memory (stage-full waits of the MMA issuer: 3.9 % -> see
+                    // profiles/r02_i8_role_wait_accounting.log).
+                    constexpr int I8_PF = 4;
+                    int pib = 0, pkc = 0;                         // prefetch cursor, I8_PF stages ahead of (ib, kc)
+                    auto prefetch = [&]() {
+                        if (pib >= nbm) return;
+                        l2_prefetch(b.Lp8 + ((size_t)pib * (pib + 1) / 2 * KCH + pkc) * (size_t)(S * I8_A_SLICE), S * I8_A_SLICE);
+                        l2_prefetch(panel + (size_t)pkc * B_STAGE, B_STAGE);
+                        if (++pkc == (pib + 1) * KCH) { pkc = 0; ++pib; }
+                    };
+                    for (int i = 0; i < I8_PF; ++i) prefetch();
                     for (int ib = 0; ib < nbm; ++ib)
                         for (int kc = 0; kc < (ib + 1) * KCH; ++kc) {
+                            prefetch();
                             i8_wait(&empty[stage], phase ^ 1);
                             unsigned char* sb = smem + stage * SM::STAGE_BYTES;
                             mbar_expect_tx(&full[stage], SM::STAGE_BYTES);
@@ -372,13 +434,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                         const uint32_t acc0 = kc > 0 ? 1u : 0u;
                         if (leader) {
 #pragma unroll
-                            for (int s = 0; s < S; ++s)
+                            for (int kk = 0; kk < I8_KC / 32; ++kk)
 #pragma unroll
-                                for (int t = 0; t + s < S; ++t)
+                                for (int s = 0; s < S; ++s)
 #pragma unroll
-                                    for (int kk = 0; kk < I8_KC / 32; ++kk)
-                                        i8_mma(tmem_base + (s + t) * I8_BN, da0 + (uint64_t)((s * I8_A_SLICE + kk * 256) >> 4),
-                                               db0 + (uint64_t)((t * I8_B_SLICE + kk * 256) >> 4), idesc, (kk > 0 || s > 0) ? 1u : acc0);
+                                    for (int t = 0; t + s < S; ++t) {
+                                        const uint32_t td = tmem_base + (s + t) * I8_BN;
+                                        const uint64_t da = da0 + (uint64_t)((s * I8_A_SLICE + kk * 256) >> 4);
+                                        const uint64_t db = db0 + (uint64_t)((t * I8_B_SLICE + kk * 256) >> 4);
+                                        const uint32_t accf = (kk > 0 || s > 0) ? 1u : acc0;
+                                        if (s == S - 1)          i8_mma<0>(td, da, db, idesc, accf);     // a run of one
+                                        else if (t == 0)         i8_mma<1>(td, da, db, idesc, accf);
+                                        else if (t == S - 1 - s) i8_mma<3>(td, da, db, idesc, accf);
+                                        else                     i8_mma<2>(td, da, db, idesc, accf);
+                                    }
                             i8_commit(&empty[stage]);                // the slot is free once these MMAs have read it
                             if (kc == nkc - 1) i8_commit(tfull);     // the accumulators of row block ib are complete
                         }
@@ -416,24 +485,48 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                     i8_wait(tfull, rb & 1);
                     tc_fence_after();
                     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+                    // TMEM reads (tcgen05.ld) and the FP64 recombination overlap: chunks of 4 columns x S groups, two register
+                    // sets, the next chunk's loads in flight while this one is recombined; the accumulators are handed back to
+                    // the MMA issuer as soon as the last load has landed, before the last chunk's arithmetic
+                    int va[S][4], vb[S][4];
+                    auto recombine = [&](const int (&v)[S][4], int c0) {
 #pragma unroll
-                    for (int c0 = 0; c0 < I8_BN; c0 += 8) {
-                        int v[S][8];
+                        for (int j = 0; j < 4; ++j) {
+                            double t = i8_s32_to_f64(v[S - 1][j]);
 #pragma unroll
-                        for (int gq = 0; gq < S; ++gq) tmem_ld8(trow + gq * I8_BN + c0, v[gq]);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            double t = (double)v[S - 1][j];
-#pragma unroll
-                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, (double)v[gq][j]);
+                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, i8_s32_to_f64(v[gq][j]));
                             const double u = t * rs;
                             acc[c0 + j] = fma(u, u, acc[c0 + j]);
                         }
+                    };
+                    // (tcgen05.ld writes its registers asynchronously: `landed` ties them to the wait so that no use is
+                    // scheduled ahead of it)
+                    auto landed = [&](int (&v)[S][4]) {
+#pragma unroll
+                        for (int gq = 0; gq < S; ++gq) asm volatile("" : "+r"(v[gq][0]), "+r"(v[gq][1]), "+r"(v[gq][2]), "+r"(v[gq][3]));
+                    };
+#pragma unroll
+                    for (int gq = 0; gq < S; ++gq) tmem_ld4(trow + gq * I8_BN, va[gq]);
+                    tmem_ld_wait();
+                    landed(va);
+#pragma unroll
+                    for (int c0 = 0; c0 < I8_BN; c0 += 8) {
+#pragma unroll
+                        for (int gq = 0; gq < S; ++gq) tmem_ld4(trow + gq * I8_BN + c0 + 4, vb[gq]);
+                        recombine(va, c0);
+                        tmem_ld_wait();
+                        landed(vb);
+                        if (c0 + 8 < I8_BN) {
+#pragma unroll
+                            for (int gq = 0; gq < S; ++gq) tmem_ld4(trow + gq * I8_BN + c0 + 8, va[gq]);
+                        } else {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty);
+                        }
+                        recombine(vb, c0 + 4);
+                        if (c0 + 8 < I8_BN) { tmem_ld_wait(); landed(va); }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty);
                 }
                 // sum over the 32 rows of this warp: halving butterfly (each step trades half of the columns held)
 #pragma unroll
@@ -461,6 +554,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             if (tid < I8_BN) {
                 const long long li = blk * I8_BN + tid;
                 const double ss = (colsum[tid] + colsum[I8_BN + tid]) + (colsum[2 * I8_BN + tid] + colsum[3 * I8_BN + tid]);
+                // accuracy guard: too little variance left for the slicing error bound -> the FP64 contraction scores it
+                const bool flagged = b.flag_count != nullptr && li < a.N &&
+                                     !(a.hyp.outputscale - ss >= b.guard_scale * sqrt(__ldg(b.guard_w) * ss));
+                {
+                    const unsigned fm = __ballot_sync(0xffffffffu, flagged);
+                    if (fm) {
+                        int base = 0;
+                        if (lane == __ffs(fm) - 1) base = atomicAdd(b.flag_count, __popc(fm));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(fm) - 1);
+                        const long long pos = base + __popc(fm & ((1u << lane) - 1u));
+                        if (flagged && pos < b.flag_cap) b.flag_idx[pos] = li;
+                    }
+                }
                 const double var = fmax(a.hyp.outputscale - ss, a.min_var);
                 const double mean = a.hyp.mean + mu_s[p * I8_BN + tid];
                 double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
@@ -472,7 +578,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                 if (!(v == v)) v = -INFINITY;
                 acq_s[tid] = v;
                 bool beats = false;
-                if (a.topk > 0 && li < a.N) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
+                if (a.topk > 0 && li < a.N && !flagged) beats = tk_better(v, a.first_index + li, tkv[a.topk - 1], tki[a.topk - 1]);
                 const unsigned m = __ballot_sync(0xffffffffu, beats);
                 if (lane == 0) cmask[warp] = m;
             }
@@ -518,10 +624,10 @@ static bool sweep_i8_model_ok(const bo_handle* h) {
 
 // Slice count of AUTO.  8 slices reproduce the FP64 product to within ~2x its own rounding error on everything the
 // emulation (tools/ozaki_feasibility.py, tests/test_sliced_numerics.py) was run on, including the reference's CSV rows
-// with duplicate and clustered points at the 1e-4 noise floor.  7 slices are 1.25x faster and hold 3e-10 on the C3
-// shape, but their error grows like (row scales of L^-1) / sigma^2: next to clusters of training rows (sigma^2 ~ 3e-5
-// on the reference's data) it reaches 2e-8 and breaks the 1e-8 bar -- no cheap a-priori test separates the two cases,
-// so 7 slices are opt-in only (BO_SWEEP_I8X7).
+// with duplicate and clustered points at the 1e-4 noise floor; the guard then only flags candidates with sigma^2 below
+// ~1e-4 of the prior variance.  7 slices are 1.25x faster, but their error bound is 128x larger, so the guard sends
+// every candidate with sigma^2 below a few percent of the prior variance to the FP64 pass -- a win only for pools that
+// stay away from the data: opt-in (BO_SWEEP_I8X7).
 static int sweep_i8_slices(const Hyper&) { return 8; }
 
 // The pinned mode a sweep over a pool of `pool` candidates runs in.  Pinned modes depend on the model only, so every
@@ -533,26 +639,25 @@ int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
     if (mode == BO_SWEEP_I8X7 || mode == BO_SWEEP_I8X8) return mode;
     if ((pool + I8_BN - 1) / I8_BN < 2LL * h->sm_count) return BO_SWEEP_FP64;
     if (h->np < I8_AUTO_MIN_NP) return BO_SWEEP_FP64;     // measured gain starts at n = 512 (1.33x); below it was not measured
-    // below the reference's noise floor (1e-4 on standardised targets) the model itself is ill-conditioned: on the
-    // reference's n = 3000 rows at ratio 7.7e-5 the 8-slice product is at 6e-9 where the FP64 product is at 2e-9
-    // (tools/ozaki_golden.py) -- still inside 1e-8, but the margin is gone, so AUTO keeps the FP64 contraction there
-    if ((h->hyp.noise + h->hyp.jitter) / h->hyp.outputscale < 1e-4) return BO_SWEEP_FP64;
+    // no hyper-parameter heuristic: every sliced sweep carries the per-candidate accuracy guard (I8_GUARD_*), which sends
+    // the candidates the slicing error could matter for -- sigma^2 orders of magnitude below the prior variance, next to
+    // training rows -- through the FP64 contraction
     return sweep_i8_slices(h->hyp) == 7 ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;
 }
 
 template <int S>
-static int ensure_i8_ws(bo_handle* h, int grid) {
+static int ensure_i8_ws(bo_handle* h, int grid, long long pool) {
     const int nbm = h->np / SW_BM;
     const size_t a_bytes = (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
     if (a_bytes > h->Lp8_bytes) {
         if (h->Lp8) cudaFree(h->Lp8);
-        h->Lp8 = nullptr; h->Lp8_bytes = 0;
+        h->Lp8 = nullptr; h->Lp8_bytes = 0; h->Lp8_epoch = 0;
         BO_CUDA(h, cudaMalloc(&h->Lp8, a_bytes));
         h->Lp8_bytes = a_bytes;
     }
     if ((size_t)h->np > h->rowscale_cap) {
         if (h->rowscale) cudaFree(h->rowscale);
-        h->rowscale = nullptr; h->rowscale_cap = 0;
+        h->rowscale = nullptr; h->rowscale_cap = 0; h->Lp8_epoch = 0;
         BO_CUDA(h, cudaMalloc(&h->rowscale, (size_t)h->cap_np * sizeof(double)));
         h->rowscale_cap = h->cap_np;
     }
@@ -562,6 +667,18 @@ static int ensure_i8_ws(bo_handle* h, int grid) {
         h->panel8 = nullptr; h->panel8_bytes = 0;
         BO_CUDA(h, cudaMalloc(&h->panel8, p_bytes));
         h->panel8_bytes = p_bytes;
+    }
+    // guard: up to a quarter of the pool (at least 16 Ki entries) may be re-scored; beyond that the whole pool is
+    if (!h->guard_dev) { BO_CUDA(h, cudaMalloc(&h->guard_dev, 2 * sizeof(double))); h->Lp8_epoch = 0; }
+    if (!h->flag_count_dev) BO_CUDA(h, cudaMalloc(&h->flag_count_dev, sizeof(int)));
+    if (!h->flag_count_host) BO_CUDA(h, cudaMallocHost(&h->flag_count_host, sizeof(int)));
+    size_t cap = (size_t)(pool / 4 > 16384 ? pool / 4 : 16384);
+    if (cap > (size_t)pool) cap = (size_t)pool;
+    if (cap > h->flag_cap) {
+        if (h->flag_idx) cudaFree(h->flag_idx);
+        h->flag_idx = nullptr; h->flag_cap = 0;
+        BO_CUDA(h, cudaMalloc(&h->flag_idx, cap * sizeof(long long)));
+        h->flag_cap = cap;
     }
     return 0;
 }
@@ -580,33 +697,65 @@ static int launch_sweep_i8(bo_handle* h, const SweepArgs& a, const SweepI8Args& 
     return S == 8 ? launch_sweep_i8_k<DP, BO_KERNEL_RBF, 8>(h, a, b, grid, st) : launch_sweep_i8_k<DP, BO_KERNEL_RBF, 7>(h, a, b, grid, st);
 }
 
-// a: as prepared by sweep_impl (G == 1).  Packs the int8 operands of the current factor, then sweeps.
-static int sweep_i8_run(bo_handle* h, SweepArgs a, int S, double* vals_dev, int64_t* idx_dev, cudaStream_t st) {
+// a: as prepared by sweep_impl.  Slices the current factor if it changed since the last sliced sweep, sweeps, then re-scores
+// the candidates the accuracy guard flagged on the FP64 contraction (same pool positions, same outputs, same top-k order).
+// Synchronises the stream once (the 4-byte count of flagged candidates decides whether a second pass is needed).
+static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals_dev, int64_t* idx_dev, cudaStream_t st) {
+    SweepArgs a = a_in;
+    a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
     a.nblocks = (a.N + I8_BN - 1) / I8_BN;
     int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
     { const char* gs = getenv("BO_B200_I8_GRID"); if (gs && atoi(gs) >= 1 && atoi(gs) < grid) grid = atoi(gs); }   // triage: fewer CTAs
     int rc;
-    if ((rc = ensure_sweep_ws(h, grid, false))) return rc;    // per-CTA top-k lists only (no FP64 panel)
-    if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid) : ensure_i8_ws<7>(h, grid)))) return rc;
+    if ((rc = ensure_sweep_ws(h, grid, false, grid + h->sm_count))) return rc;    // top-k lists: this kernel's + the re-score pass's
+    if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid, a.N) : ensure_i8_ws<7>(h, grid, a.N)))) return rc;
     const int nbm = h->np / SW_BM;
-    // the factor may have changed since the last call (fit, append, refit): re-slice it every time (~0.1 ms at n = 4096)
-    i8_rowscale_kernel<<<(h->np + 3) / 4, 128, 0, st>>>(h->Li, h->cap_np, h->np, h->rowscale);
-    BO_LAUNCH_CHECK(h);
-    if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
-    else        i8_pack_linv_kernel<7><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
-    BO_LAUNCH_CHECK(h);
+    if (h->Lp8_epoch != h->factor_epoch || h->Lp8_S != S) {
+        // the factor changed since the operands were sliced (fit, append, refit) or the slice count did
+        BO_CUDA(h, cudaMemsetAsync(h->guard_dev, 0, 2 * sizeof(double), st));
+        i8_rowscale_kernel<<<(h->np + 3) / 4, 128, 0, st>>>(h->Li, h->cap_np, h->np, h->n, h->rowscale, h->guard_dev);
+        BO_LAUNCH_CHECK(h);
+        if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
+        else        i8_pack_linv_kernel<7><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
+        BO_LAUNCH_CHECK(h);
+        h->Lp8_epoch = h->factor_epoch; h->Lp8_S = S;
+    }
     SweepI8Args b{};
     b.Lp8 = h->Lp8; b.rowscale = h->rowscale; b.panel8 = h->panel8;
     int e; frexp(a.hyp.outputscale, &e);                      // |k*| <= outputscale < 2^e
     b.dig_scale = ldexp(1.0, 6 + 7 * (S - 1) - e);
     b.eb_scale = ldexp(1.0, e - 12);
+    const char* ng = getenv("BO_B200_I8_NO_GUARD");           // triage only: raw sliced values for every candidate
+    const bool guard = !(ng && atoi(ng) == 1);
+    b.guard_scale = I8_GUARD_KAPPA / I8_GUARD_RTOL * ldexp(1.0, e - 7 * S);
+    b.guard_w = h->guard_dev;
+    b.flag_idx = h->flag_idx; b.flag_count = guard ? h->flag_count_dev : nullptr; b.flag_cap = (long long)h->flag_cap;
     a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
+    BO_CUDA(h, cudaMemsetAsync(h->flag_count_dev, 0, sizeof(int), st));
     BO_CUDA(h, cudaEventRecord(h->ev0, st));
     if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep_i8, h, a, b, S, grid, st))) return rc;
     BO_CUDA(h, cudaEventRecord(h->ev1, st));
-    h->sweep_timed = true; h->sweep_path = S;
+    h->sweep_timed = true;
+    BO_CUDA(h, cudaMemcpyAsync(h->flag_count_host, h->flag_count_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BO_CUDA(h, cudaStreamSynchronize(st));
+    const long long flagged = *h->flag_count_host;
+    int lists = grid;
+    if (flagged > (long long)h->flag_cap) {
+        // most of the pool sits on top of the data: the FP64 contraction scores all of it
+        if ((rc = sweep_fp64_run(h, a_in, 0, true, vals_dev, idx_dev, nullptr, st))) return rc;
+        h->sweep_path = S; h->sweep_flagged = -1;
+        return 0;
+    }
+    if (flagged > 0) {
+        SweepArgs a2 = a_in;
+        a2.N = flagged; a2.idx_map = h->flag_idx;
+        int g2 = 0;
+        if ((rc = sweep_fp64_run(h, a2, grid, false, nullptr, nullptr, &g2, st))) return rc;
+        lists += g2;
+    }
+    h->sweep_path = S; h->sweep_flagged = flagged;
     if (a.topk > 0) {
-        topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, grid * BO_MAX_TOPK, a.topk, vals_dev, (long long*)idx_dev);
+        topk_merge_kernel<<<1, 1024, 0, st>>>(h->part_val, (long long*)h->part_idx, lists * BO_MAX_TOPK, a.topk, vals_dev, (long long*)idx_dev);
         BO_LAUNCH_CHECK(h);
     }
     return 0;
@@ -644,7 +793,7 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int kk = 0; kk < KC / 32; ++kk)
-                    i8_mma(tmem_base + (r & 1) * N, i8_desc(a0 + kk * 256), i8_desc(b0 + kk * 256), idesc, (it | r | kk) ? 1u : 0u);
+                    i8_mma<0>(tmem_base + (r & 1) * N, i8_desc(a0 + kk * 256, 512), i8_desc(b0 + kk * 256, 512), idesc, (it | r | kk) ? 1u : 0u);
             i8_commit(&bars[it & 1]);
             if (it > 0) i8_wait(&bars[(it - 1) & 1], ((it - 1) >> 1) & 1);
         }

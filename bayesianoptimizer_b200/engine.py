@@ -351,6 +351,10 @@ class GPEngine:
         """0 = FP64 DMMA, 7 / 8 = INT8-sliced with that many slices, -1 = no sweep yet."""
         return int(self._lib.bo_last_sweep_path(self._h))
 
+    def last_sweep_flagged(self) -> int:
+        """Candidates of the last sliced sweep its accuracy guard re-scored on the FP64 contraction (-1: the whole pool)."""
+        return int(self._lib.bo_last_sweep_flagged(self._h))
+
     def launch_count(self) -> int:
         return int(self._lib.bo_launch_count(self._h))
 

@@ -53,7 +53,7 @@ extern "C" {
 #define BO_ACQ_MEAN  4   /* posterior mean                                                              */
 
 /* contraction used by bo_sweep for the variance term u = L^-1 k* (bo_set_sweep_mode) */
-#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path (8 slices) for large pools of a stationary-kernel exact GP,
+#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path (8 slices, guarded) for large pools of a stationary-kernel exact GP,
                            * FP64 DMMA otherwise (see bo_set_sweep_mode) */
 #define BO_SWEEP_FP64 1   /* always the FP64 DMMA contraction */
 #define BO_SWEEP_I8X7 2   /* INT8-sliced with 7 slices wherever eligible */
@@ -222,13 +222,18 @@ int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, in
 /* Choose how bo_sweep contracts L^-1 with the K(X, X*) panel (BO_SWEEP_*; default BO_SWEEP_AUTO).  The INT8-sliced path
  * computes the same FP64 quantity: both operands are cut into S signed 7-bit slices (error-free, Ozaki scheme I), the
  * S (S + 1) / 2 leading slice products run on the INT8 tensor cores (tcgen05.mma kind::i8) with exact INT32
- * accumulation and are recombined in FP64.  8 slices (what AUTO uses) reproduce the FP64 product to its own rounding
- * level; 7 slices (opt-in, 1.25x faster) hold 1e-9 relative on the variance of well-separated data but reach 2e-8 next
- * to clusters of training rows (sigma^2 << noise).  Eligible models: exact GP,
- * Matern-5/2 or RBF kind, at least 256 (padded) observations; every other model runs the FP64 DMMA path in every mode.
+ * accumulation and are recombined in FP64.  Every sliced sweep carries a per-candidate accuracy guard: the slicing
+ * error of ||u||^2 is bounded from the row scales of L^-1 and ||u||^2 itself, and a candidate whose variance is not at
+ * least 5e8 x that bound (slicing error <= 2e-9 relative) is re-scored on the FP64 DMMA contraction inside the same
+ * call -- same outputs, same top-k order; bo_last_sweep_flagged() reports how many.  With 8 slices (what AUTO uses) that
+ * is candidates with sigma^2 below ~1e-4 of the prior variance (next to training rows); with 7 slices (opt-in, 1.25x
+ * faster per sliced candidate) the bound is 128x larger.  Eligible models: exact GP, Matern-5/2 or RBF kind, at least 256
+ * (padded) observations; every other model runs the FP64 DMMA path in every mode.
  * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
- * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates, models with fewer than 512
- * (padded) observations and models with noise / outputscale < 1e-4 on the FP64 path. */
+ * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates and models with fewer than 512
+ * (padded) observations on the FP64 path.  bo_posterior / bo_posterior_multi stay on the FP64 contraction under AUTO
+ * (model.posterior numerics must not depend on N) and follow a pinned mode.  A sliced sweep synchronises the stream once
+ * (the count of flagged candidates is read back). */
 int bo_set_sweep_mode(bo_handle* h, int32_t mode);
 
 /* The pinned mode (BO_SWEEP_FP64 / I8X7 / I8X8) the handle's current mode resolves to for a pool of pool_total
@@ -238,6 +243,10 @@ int bo_resolve_sweep_mode(const bo_handle* h, int64_t pool_total);
 
 /* Contraction the last bo_sweep ran: 0 = FP64 DMMA, 7 / 8 = INT8-sliced with that many slices, -1 = no sweep yet. */
 int bo_last_sweep_path(const bo_handle* h);
+
+/* Candidates of the last sliced sweep that its accuracy guard sent through the FP64 contraction (0 for an FP64 sweep;
+ * -1: more than a quarter of the pool was flagged and the whole pool was scored on the FP64 contraction). */
+int64_t bo_last_sweep_flagged(const bo_handle* h);
 
 /* INT8 tensor-pipe peak probe (tcgen05.mma kind::i8, 128 x 256 x 32 on resident operands): roofline denominator
  * of the sliced sweep.  Returns TOP/s (multiply and add counted separately) in *tops_host. */

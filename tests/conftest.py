@@ -42,11 +42,14 @@ def synth_problem(n, d, seed_x, seed_y):
     return X, y
 
 
-def assert_posterior_close(mu, var, mu_ref, var_ref):
+def assert_posterior_close(mu, var, mu_ref, var_ref, var_abs=0.0):
+    """var_abs: absolute floor on the variance tolerance, used only where the test says why (sigma^2 = s2 - ||u||^2 at
+    gpytorch's 1e-6 clamp with n = 3000: the two O(s2) terms carry sqrt(n) 2^-53 s2 ~ 1e-14 of summation rounding each in
+    ANY FP64 evaluation, the oracle's included, which is 1e-8 of such a variance)."""
     mu, var, mu_ref, var_ref = (np.asarray(a, dtype=np.float64) for a in (mu, var, mu_ref, var_ref))
     err_mu = np.abs(mu - mu_ref) / (RTOL_POST * np.abs(mu_ref) + ATOL_MEAN)
     assert err_mu.max() <= 1.0, f"mean off by {err_mu.max():.3g}x tolerance at {err_mu.argmax()}"
-    err_var = np.abs(var - var_ref) / (RTOL_POST * np.abs(var_ref))
+    err_var = np.abs(var - var_ref) / (RTOL_POST * np.abs(var_ref) + var_abs)
     assert err_var.max() <= 1.0, f"variance off by {err_var.max():.3g}x tolerance at {err_var.argmax()}"
 
 
@@ -68,3 +71,16 @@ def assert_ei_close_conditioned(kind, val, ref, mu_ref, var_ref, best_f):
     tol = RTOL_ACQ + 3.0 * RTOL_POST * (1.0 + np.abs(u) + u * u)
     err = np.abs(val - ref) / (tol if kind == "logei" else tol * np.abs(ref) + 1e-300)
     assert err.max() <= 1.0, f"{kind} off by {err.max():.3g}x conditioned tolerance at {err.argmax()} (u = {u[err.argmax()]:.3g})"
+
+
+def refdata_pool(X, total=20_000, near=2_400, seed=7, near_min=1e-5):
+    """Explicit candidate pool on the reference's CSV rows: `total - near` uniform points plus `near` points 1e-2 .. near_min
+    away from training rows -- every 7th row plus the duplicated rows {12, 20}, {17, 50} of results/optimization_results.csv
+    (sigma^2 down to ~1e-6 of the prior variance: where a variance contraction loses digits)."""
+    n, d = X.shape
+    rng = np.random.default_rng(seed)
+    rows = np.concatenate([[12, 20, 17, 50], np.arange(0, n, 7)]) % n
+    eps = np.logspace(-2, np.log10(near_min), near)
+    pts = np.clip(X[rows[np.arange(near) % len(rows)]] + eps[:, None] * rng.standard_normal((near, d)), 0.0, 1.0)
+    pool = np.vstack([rng.random((total - near, d)), pts])
+    return pool[rng.permutation(total)]
