@@ -387,22 +387,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             if (prof) t_w2 += clock64() - tB0;
             if (warp == 4) {
                 if (lane == 0) {
-                    // The ring holds two stages, i.e. one stage time (~1.8 us) of latency tolerance, and the panel tiles come
-                    // from HBM (148 CTAs x 2 x 2 MB of panels do not fit L2): an L2 prefetch I8_PF stages ahead of the copies
-                    // turns them into L2 hits without costing shared memory (stage-full waits of the MMA issuer: 3.9 % -> see
-                    // profiles/r02_i8_role_wait_accounting.log).
-                    constexpr int I8_PF = 4;
-                    int pib = 0, pkc = 0;                         // prefetch cursor, I8_PF stages ahead of (ib, kc)
-                    auto prefetch = [&]() {
-                        if (pib >= nbm) return;
-                        l2_prefetch(b.Lp8 + ((size_t)pib * (pib + 1) / 2 * KCH + pkc) * (size_t)(S * I8_A_SLICE), S * I8_A_SLICE);
-                        l2_prefetch(panel + (size_t)pkc * B_STAGE, B_STAGE);
-                        if (++pkc == (pib + 1) * KCH) { pkc = 0; ++pib; }
-                    };
-                    for (int i = 0; i < I8_PF; ++i) prefetch();
+                    // (an L2 prefetch of the tiles four stages ahead was tried: the issuer's stage-full waits fell from 34.2 M to
+                    // 31.7 M cycles per 254 blocks, but the builders slowed down by more -- the ring is bound by shared-memory
+                    // bandwidth, MMA operand reads + TMA writes, not by HBM latency)
                     for (int ib = 0; ib < nbm; ++ib)
                         for (int kc = 0; kc < (ib + 1) * KCH; ++kc) {
-                            prefetch();
                             i8_wait(&empty[stage], phase ^ 1);
                             unsigned char* sb = smem + stage * SM::STAGE_BYTES;
                             mbar_expect_tx(&full[stage], SM::STAGE_BYTES);
@@ -485,47 +474,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                     i8_wait(tfull, rb & 1);
                     tc_fence_after();
                     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-                    // TMEM reads (tcgen05.ld) and the FP64 recombination overlap: chunks of 4 columns x S groups, two register
-                    // sets, the next chunk's loads in flight while this one is recombined; the accumulators are handed back to
-                    // the MMA issuer as soon as the last load has landed, before the last chunk's arithmetic
-                    int va[S][4], vb[S][4];
-                    auto recombine = [&](const int (&v)[S][4], int c0) {
+                    // the accumulators go back to the MMA issuer as soon as the last chunk has landed in registers, before its
+                    // arithmetic (a software-pipelined variant with two x4 register sets measured slower: 50.5 M vs 45.4 M cycles of
+                    // issuer wait per 254 blocks, profiles/r02_i8_role_wait_accounting.log)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                    for (int c0 = 0; c0 < I8_BN; c0 += 8) {
+                        int v[S][8];
+#pragma unroll
+                        for (int gq = 0; gq < S; ++gq) tmem_ld8(trow + gq * I8_BN + c0, v[gq]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int gq = 0; gq < S; ++gq)      // (tcgen05.ld writes asynchronously: no use may be scheduled above the wait)
+                            asm volatile("" : "+r"(v[gq][0]), "+r"(v[gq][1]), "+r"(v[gq][2]), "+r"(v[gq][3]), "+r"(v[gq][4]), "+r"(v[gq][5]), "+r"(v[gq][6]), "+r"(v[gq][7]));
+                        if (c0 + 8 == I8_BN) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
                             double t = i8_s32_to_f64(v[S - 1][j]);
 #pragma unroll
                             for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, i8_s32_to_f64(v[gq][j]));
                             const double u = t * rs;
                             acc[c0 + j] = fma(u, u, acc[c0 + j]);
                         }
-                    };
-                    // (tcgen05.ld writes its registers asynchronously: `landed` ties them to the wait so that no use is
-                    // scheduled ahead of it)
-                    auto landed = [&](int (&v)[S][4]) {
-#pragma unroll
-                        for (int gq = 0; gq < S; ++gq) asm volatile("" : "+r"(v[gq][0]), "+r"(v[gq][1]), "+r"(v[gq][2]), "+r"(v[gq][3]));
-                    };
-#pragma unroll
-                    for (int gq = 0; gq < S; ++gq) tmem_ld4(trow + gq * I8_BN, va[gq]);
-                    tmem_ld_wait();
-                    landed(va);
-#pragma unroll
-                    for (int c0 = 0; c0 < I8_BN; c0 += 8) {
-#pragma unroll
-                        for (int gq = 0; gq < S; ++gq) tmem_ld4(trow + gq * I8_BN + c0 + 4, vb[gq]);
-                        recombine(va, c0);
-                        tmem_ld_wait();
-                        landed(vb);
-                        if (c0 + 8 < I8_BN) {
-#pragma unroll
-                            for (int gq = 0; gq < S; ++gq) tmem_ld4(trow + gq * I8_BN + c0 + 8, va[gq]);
-                        } else {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(tempty);
-                        }
-                        recombine(vb, c0 + 4);
-                        if (c0 + 8 < I8_BN) { tmem_ld_wait(); landed(va); }
                     }
                 }
                 // sum over the 32 rows of this warp: halving butterfly (each step trades half of the columns held)

@@ -31,6 +31,16 @@ from .sobol import sobol_state
 CSV_PARAM_COLS = ["n", "eta", "sigma_y", "width", "height"]
 
 
+def _process_group():
+    """(dist module, rank, world) of an initialised multi-rank process group, else (None, RANK from the launcher's
+    environment, 1): under torchrun every rank runs the same driver script, so everything random or stateful below has to be
+    decided once (rank 0) and shared."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, int(os.environ.get("RANK", "0") or 0), 1
+
+
 @dataclass
 class GPConfig:
     """Knobs of the surrogate / acquisition path (passed as ``gp_config=``, the kwarg of Bayesian7.py:215)."""
@@ -135,6 +145,7 @@ class BayesianOptimizer:
         self._y_mean, self._y_std = 0.0, 1.0
         self._suggest_count = 0
         self._rng = np.random.default_rng(self.config.seed)
+        self._replicas_synced = False
         self._init_results_file()
 
     # ------------------------------------------------------------------ CSV / resume -------------
@@ -146,8 +157,38 @@ class BayesianOptimizer:
         if self.resume and os.path.exists(self.results_file):
             self._load_existing()
             return
+        if _process_group()[1] != 0:
+            return                                    # one writer: rank 0 owns optimization_results.csv
         with open(self.results_file, "w") as f:
             f.write(",".join(self._csv_header()) + "\n")
+
+    def _sync_replicas(self):
+        """Multi-GPU driver mode (torchrun): every rank runs this class on its own GPU and shards the sweeps and
+        the restart screening, so all ranks must hold the same data, the same random stream and the same warm-start state.
+        A seed drawn by rank 0 (GPConfig.seed = None seeds every process differently), its observations and hyper-parameters are
+        broadcast once, the first time a process group is seen; afterwards every rank performs the same draws.  The
+        simulator runs and the CSV is written on rank 0 only (``register``)."""
+        dist, rank, world = _process_group()
+        if dist is None or self._replicas_synced:
+            return
+        payload = [None]
+        if rank == 0:
+            payload[0] = {"rng": int(self._rng.integers(0, 2 ** 63 - 1)), "X": [np.asarray(x) for x in self.original_X],
+                          "D": [np.asarray(v) for v in self.displacements_list], "hyper": self._hyper,
+                          "hyper_fits": self._hyper_fits, "suggest_count": self._suggest_count}
+        dist.broadcast_object_list(payload, src=0)
+        st = payload[0]
+        # every rank (0 included) restarts its generator from the one broadcast seed: SciPy's LHS spawns children from the
+        # generator's seed sequence, which a copied bit-generator state would not carry
+        self._rng = np.random.default_rng(st["rng"])
+        if rank != 0:
+            self.train_X = torch.empty((0, self.dim), dtype=torch.float64, device=self.device)
+            self.train_Y = torch.empty((0, 1), dtype=torch.float64, device=self.device)
+            self.original_X, self.displacements_list = [], []
+            for x, v in zip(st["X"], st["D"]):
+                self._append_observation(x, v, write=False)
+            self._hyper, self._hyper_fits, self._suggest_count = st["hyper"], st["hyper_fits"], st["suggest_count"]
+        self._replicas_synced = True
 
     def _load_existing(self):
         """Reload rows (physical units) and re-normalise; tolerates the legacy ``disp_*`` headers and drops
@@ -209,6 +250,7 @@ class BayesianOptimizer:
     def collect_initial_points(self):
         """Latin-hypercube points in [0,1]^d (Bayesian.py:68-73)."""
         from scipy.stats import qmc
+        self._sync_replicas()
         print(f"Generating {self.n_initial_points} initial points using Latin Hypercube Sampling...")
         sampler = qmc.LatinHypercube(d=self.dim, seed=self._rng)
         pts = sampler.random(n=self.n_initial_points) if self.n_initial_points > 0 else np.empty((0, self.dim))
@@ -311,6 +353,7 @@ class BayesianOptimizer:
 
     def fit_gp_model(self):
         """Fit the exact GP on the normalised data (Bayesian.py:89-94) and return the model handle."""
+        self._sync_replicas()
         if self.train_X.shape[0] == 0:
             raise RuntimeError("fit_gp_model: no observations")
         eng = self._engine_get()
@@ -362,6 +405,7 @@ class BayesianOptimizer:
 
     def suggest(self, q: Optional[int] = None, gp: Optional[GPModel] = None):
         cfg = self.config
+        self._sync_replicas()
         q = self.batch_size if q is None else int(q)
         if gp is None:
             gp = self.fit_gp_model()
@@ -379,15 +423,27 @@ class BayesianOptimizer:
             keep = idx >= 0
             starts = eng.sobol_points(sob, idx[keep])
             x, v = starts, vals[keep]
-            if cfg.refine_iters > 0 and cfg.kernel not in ("linear_matern52", "linear+matern52"):   # pool-based for that kind
+            if cfg.refine_iters > 0:
                 x, v = eng.refine(starts, cfg.acquisition, best_f, cfg.beta, iters=cfg.refine_iters)
-            xb = x[int(torch.argmax(v).item())]
+            order = torch.argsort(v, descending=True).tolist()
+            xb = x[order[0]]
+            for cand in order:                           # best refined point that is not (numerically) already in the batch
+                if all(float(torch.linalg.norm(x[cand].to(self.device) - p)) > 1e-9 for p in out):
+                    xb = x[cand]
+                    break
             out.append(xb.to(self.device))
             if j + 1 < q:
                 try:
                     eng.append(xb)                       # Kriging believer: y = mu(x), alpha' = [alpha; 0]
                 except NotPositiveDefiniteError:
-                    pass                                 # duplicate of an existing point: the next sweep avoids it anyway
+                    # the pick sits on top of an observation (bordered matrix not PD): the model is unchanged, so the next
+                    # sweep would return the same point -- condition on a copy nudged off the duplicate instead
+                    nudged = torch.clamp(xb + 1e-4 * torch.as_tensor(self._rng.standard_normal(self.dim), dtype=xb.dtype,
+                                                                     device=xb.device), 0.0, 1.0)
+                    try:
+                        eng.append(nudged)
+                    except NotPositiveDefiniteError:
+                        print("[suggest] Kriging-believer append failed twice at a duplicate point; the batch may repeat it")
         return torch.stack(out).to(dtype=torch.float64)
 
     def _suggest_topk_fps(self, eng, best_f, q):
@@ -407,11 +463,19 @@ class BayesianOptimizer:
 
     def register(self, x_scaled, displacements=None):
         """Evaluate (if needed) and record one point: the torch.cat + CSV block of Bayesian.py:143-148."""
+        self._sync_replicas()
         x_unit = torch.as_tensor(x_scaled, dtype=torch.float64).detach().cpu().numpy().reshape(-1)
         x_phys = self._unnormalize(x_unit)
-        if displacements is None:
+        dist, rank, world = _process_group()
+        if dist is not None:
+            # one simulation, one CSV row: rank 0 evaluates and writes, the replicas receive the displacements
+            box = [np.asarray(self.run_simulation(x_phys) if displacements is None else displacements, dtype=np.float64)
+                   if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            displacements = box[0]
+        elif displacements is None:
             displacements = self.run_simulation(x_phys)
-        self._append_observation(x_phys, displacements)
+        self._append_observation(x_phys, displacements, write=(rank == 0))
         return self._objective(displacements)
 
     def return_best_result(self):
@@ -432,6 +496,7 @@ class BayesianOptimizer:
         """Batch optimisation loop (Bayesian.py:128-180); with ``target_total`` the loop runs until the global
         evaluation count is reached (Bayesian7.py:614-733, scripts/run_optimization.py:66-98)."""
         print("Starting optimization...")
+        self._sync_replicas()
         n_have = self.train_X.shape[0]
         n_init = max(0, self.n_initial_points - n_have) if self.target_total is not None else self.n_initial_points
         if n_init > 0:

@@ -94,3 +94,47 @@ def test_world_size_2_gloo_sharded_sweep_equals_single(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+_OPT_WORKER = r'''
+import os, sys, json, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from oracle_engine import OracleEngine
+from bayesianoptimizer_b200.optimizer import BayesianOptimizer, GPConfig
+from bayesianoptimizer_b200.simulators import DEFAULT_BOUNDS, CachedCSVSimulator
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+z = np.load(os.path.join(sys.argv[1], "tests", "golden", "csv_cache_rows.npz"))
+sim = CachedCSVSimulator(z["params"], z["outputs"])
+cfg = GPConfig(candidates_pool_size=600, num_restarts=3, refine_iters=4, hyper_restarts=4, hyper_refine=2, hyper_maxiter=3, seed=None)
+opt = BayesianOptimizer(sim, DEFAULT_BOUNDS, sys.argv[2], n_initial_points=12, n_batches=2, batch_size=2, gp_config=cfg,
+                        engine_factory=OracleEngine, device=torch.device("cpu"))
+opt.optimize()
+out = {"X": opt.train_X.numpy().tolist(), "Y": opt.train_Y.numpy().tolist(), "hyper": [np.asarray(h).tolist() for h in opt._hyper],
+       "sim_calls": sim.calls}
+gathered = [None, None]
+dist.all_gather_object(gathered, out)
+assert gathered[0]["X"] == gathered[1]["X"] and gathered[0]["Y"] == gathered[1]["Y"], "replicas diverged (data)"
+assert gathered[0]["hyper"] == gathered[1]["hyper"], "replicas diverged (hyper-parameters)"
+assert gathered[0]["sim_calls"] == 16 and gathered[1]["sim_calls"] == 0, "the simulator must run on rank 0 only"
+dist.barrier()
+if rank == 0:
+    rows = open(opt.results_file).read().strip().split("\n")
+    assert len(rows) == 1 + 16, len(rows)          # header + one row per evaluation, written once
+print("rank", rank, "ok")
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_driver_mode_is_replica_consistent_with_seed_none(tmp_path):
+    """INTEGRATION.md multi-GPU driver mode: two ranks run BayesianOptimizer.optimize with GPConfig.seed = None; LHS points,
+    hyper-parameter restarts and suggestions must agree on both, the simulator and the CSV belong to rank 0."""
+    script = tmp_path / "opt_worker.py"
+    script.write_text(_OPT_WORKER)
+    out = tmp_path / "run"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29741", str(script), ROOT, str(out)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
