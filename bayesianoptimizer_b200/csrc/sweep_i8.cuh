@@ -29,7 +29,10 @@ constexpr int I8_BN      = 64;                 // candidates per CTA tile (TMEM:
 #define BO_I8_KC 64
 #endif
 #ifndef BO_I8_STAGES
-#define BO_I8_STAGES 2
+#define BO_I8_STAGES (BO_I8_KC == 32 ? 4 : 2)
+#endif
+#ifndef BO_P8_STAGES
+#define BO_P8_STAGES (BO_I8_KC == 32 ? 5 : 2)      // CTA-pair kernel (sweep_i8_pair.cuh): 40 KB stages at K = 32
 #endif
 constexpr int I8_KC      = BO_I8_KC;           // contraction bytes per pipeline stage
 constexpr int I8_STAGES  = BO_I8_STAGES;
@@ -60,6 +63,7 @@ struct I8Smem {
 };
 struct SweepI8Args {
     const int8_t* Lp8; const double* rowscale; int8_t* panel8;
+    const int8_t* Lp8_zero;  // one all-zero stage tile of L^-1 slices (CTA-pair kernel: K steps beyond a row block's own extent)
     double dig_scale;       // 2^(6 + 7 (S - 1)) / (power-of-two bound of |k*|): k* -> fixed point
     double eb_scale;        // eb * 2^-12: folded into the row scale at the drain
     // accuracy guard: a candidate whose variance s2 - ||u||^2 is below guard_scale * sqrt(W ||u||^2), W = guard_w[0] =
@@ -300,7 +304,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                 const int r0 = c * XCH, rows = min(XCH, nrows - r0);
                 for (int e = tb; e < rows * (DP / 2); e += 128) {
                     const int r = e / (DP / 2), k = e % (DP / 2);
-                    cp_async16(xb + r * XP + 2 * k, a.Xs + (size_t)(r0 + r) * BO_MAX_DIM + 2 * k);
+                    // rows are staged permuted (slot (r % 4) * (XCH / 4) + r / 4): the rows 4 q + e that the four q-lanes of a
+                    // candidate read together become adjacent slots -> conflict-free LDS.128 (natural order: 2-way conflicts)
+                    cp_async16(xb + ((r & 3) * (XCH / 4) + (r >> 2)) * XP + 2 * k, a.Xs + (size_t)(r0 + r) * BO_MAX_DIM + 2 * k);
                 }
                 for (int e = tb; e < rows / 2; e += 128) cp_async16(ab + 2 * e, a.alpha + r0 + 2 * e);
                 cp_async_commit();
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                         const int j = j0 + 16 * (r >> 2) + 4 * q + (r & 3);
                         const int jr = j - c * XCH;
                         double x[DP];
-                        const double2* row = reinterpret_cast<const double2*>(xb + jr * XP);
+                        const double2* row = reinterpret_cast<const double2*>(xb + ((jr & 3) * (XCH / 4) + (jr >> 2)) * XP);
 #pragma unroll
                         for (int k = 0; k < DP / 2; ++k) { const double2 t = row[k]; x[2 * k] = t.x; x[2 * k + 1] = t.y; }
                         const double al = ab[jr];
@@ -588,6 +594,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+#include "sweep_i8_pair.cuh"
+
 // ---- host side -------------------------------------------------------------------------------------------------
 // the model side of eligibility: exact GP with a stationary kernel (|k*| <= output scale), more than one stage of rows
 static bool sweep_i8_model_ok(const bo_handle* h) {
@@ -621,7 +629,8 @@ int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
 template <int S>
 static int ensure_i8_ws(bo_handle* h, int grid, long long pool) {
     const int nbm = h->np / SW_BM;
-    const size_t a_bytes = (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
+    // packed tiles + one all-zero stage tile behind them (Lp8_zero)
+    const size_t a_bytes = ((size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) + 1) * (size_t)(S * I8_A_SLICE);
     if (a_bytes > h->Lp8_bytes) {
         if (h->Lp8) cudaFree(h->Lp8);
         h->Lp8 = nullptr; h->Lp8_bytes = 0; h->Lp8_epoch = 0;
@@ -677,8 +686,17 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     SweepArgs a = a_in;
     a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
     a.nblocks = (a.N + I8_BN - 1) / I8_BN;
-    int grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
-    { const char* gs = getenv("BO_B200_I8_GRID"); if (gs && atoi(gs) >= 1 && atoi(gs) < grid) grid = atoi(gs); }   // triage: fewer CTAs
+    // CTA pairs (cta_group::2, sweep_i8_pair.cuh) share one 64-candidate block; BO_B200_I8_PAIR=0 keeps the one-CTA kernel (triage / A-B)
+    const char* pe = getenv("BO_B200_I8_PAIR");
+    const bool pairs = !(pe && atoi(pe) == 0) && h->sm_count >= 2;
+    int grid;
+    if (pairs) {
+        const long long np2 = a.nblocks < h->sm_count / 2 ? a.nblocks : h->sm_count / 2;
+        grid = 2 * (int)np2;
+    } else {
+        grid = (int)(a.nblocks < h->sm_count ? a.nblocks : h->sm_count);
+    }
+    { const char* gs = getenv("BO_B200_I8_GRID"); if (gs && atoi(gs) >= 2 && atoi(gs) < grid) grid = atoi(gs) & ~1; }   // triage: fewer CTAs
     int rc;
     if ((rc = ensure_sweep_ws(h, grid, false, grid + h->sm_count))) return rc;    // top-k lists: this kernel's + the re-score pass's
     if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid, a.N) : ensure_i8_ws<7>(h, grid, a.N)))) return rc;
@@ -691,10 +709,12 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
         if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
         else        i8_pack_linv_kernel<7><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
         BO_LAUNCH_CHECK(h);
+        BO_CUDA(h, cudaMemsetAsync(h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE), 0, (size_t)S * I8_A_SLICE, st));
         h->Lp8_epoch = h->factor_epoch; h->Lp8_S = S;
     }
     SweepI8Args b{};
     b.Lp8 = h->Lp8; b.rowscale = h->rowscale; b.panel8 = h->panel8;
+    b.Lp8_zero = h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
     int e; frexp(a.hyp.outputscale, &e);                      // |k*| <= outputscale < 2^e
     b.dig_scale = ldexp(1.0, 6 + 7 * (S - 1) - e);
     b.eb_scale = ldexp(1.0, e - 12);
@@ -706,7 +726,8 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;
     BO_CUDA(h, cudaMemsetAsync(h->flag_count_dev, 0, sizeof(int), st));
     BO_CUDA(h, cudaEventRecord(h->ev0, st));
-    if ((rc = BO_DISPATCH_DP(h->dp, launch_sweep_i8, h, a, b, S, grid, st))) return rc;
+    if ((rc = pairs ? BO_DISPATCH_DP(h->dp, launch_sweep_i8_pair, h, a, b, S, grid, st)
+                    : BO_DISPATCH_DP(h->dp, launch_sweep_i8, h, a, b, S, grid, st))) return rc;
     BO_CUDA(h, cudaEventRecord(h->ev1, st));
     h->sweep_timed = true;
     BO_CUDA(h, cudaMemcpyAsync(h->flag_count_host, h->flag_count_dev, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -72,9 +72,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 // CG: CTAs per MMA (1 or 2; with 2 the launch is a cluster of 2 and the MMA is M = 256, each CTA holding 128 rows of A and
 // N / 2 rows of B); N: MMA N; S slices; G accumulator groups kept (G < S folds groups: rate only); COLL: A-collector reuse;
 // ORDER: 0 = for s, for t (A slice reused back to back), 1 = for t, for s (B slice reused back to back: control)
-template <int CG, int N, int S, int G, int COLL, int ORDER, int KC>
-__global__ void __launch_bounds__(128, 1)
+// side work for the interference runs: warps 4..7 (one per SM sub-partition) spin on independent chains of one instruction
+// class until the issuing warp raises `stop`; EXTRA: 1 = DFMA, 2 = FFMA, 3 = IMAD, 4 = DFMA at 1/4 duty (3 of 4 slots idle)
+__device__ double g_sink;
+template <int CG, int N, int S, int G, int COLL, int ORDER, int KC, int EXTRA = 0>
+__global__ void __launch_bounds__(EXTRA ? 256 : 128, 1)
 probe_kernel(int iters, int32_t* __restrict__ out, int* __restrict__ err, long long* __restrict__ cycles) {
+    __shared__ volatile int stop;
+    if (threadIdx.x == 0) stop = 0;
     constexpr int M = 128;                                  // rows of A per CTA
     constexpr int NB = N / CG;                              // rows of B per CTA
     constexpr int A_TILE = M * KC, B_TILE = NB * KC;
@@ -120,6 +125,27 @@ probe_kernel(int iters, int32_t* __restrict__ out, int* __restrict__ err, long l
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((M * CG) >> 4) << 24);
     const uint64_t da0 = make_desc(smem_u32(sA), 128, (KC / 16) * 128), db0 = make_desc(smem_u32(sB), 128, (KC / 16) * 128);
     bool ok = true;
+    if (EXTRA && warp >= 4) {
+        double d0 = 1.0 + tid, d1 = 2.0, d2 = 3.0, d3 = 4.0, d4 = 5.0, d5 = 6.0, d6 = 7.0, d7 = 8.0;
+        float f0 = 1.f + tid, f1 = 2.f, f2 = 3.f, f3 = 4.f, f4 = 5.f, f5 = 6.f, f6 = 7.f, f7 = 8.f;
+        int i0 = tid, i1 = 2, i2 = 3, i3 = 4, i4 = 5, i5 = 6, i6 = 7, i7 = 8;
+        long long n = 0;
+        while (!stop) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                if (EXTRA == 1 || EXTRA == 4) { d0 = fma(d0, 1.0000001, 1e-9); d1 = fma(d1, 1.0000001, 1e-9); d2 = fma(d2, 1.0000001, 1e-9); d3 = fma(d3, 1.0000001, 1e-9);
+                                  d4 = fma(d4, 1.0000001, 1e-9); d5 = fma(d5, 1.0000001, 1e-9); d6 = fma(d6, 1.0000001, 1e-9); d7 = fma(d7, 1.0000001, 1e-9); }
+                if (EXTRA == 2) { f0 = fmaf(f0, 1.0001f, 1e-5f); f1 = fmaf(f1, 1.0001f, 1e-5f); f2 = fmaf(f2, 1.0001f, 1e-5f); f3 = fmaf(f3, 1.0001f, 1e-5f);
+                                  f4 = fmaf(f4, 1.0001f, 1e-5f); f5 = fmaf(f5, 1.0001f, 1e-5f); f6 = fmaf(f6, 1.0001f, 1e-5f); f7 = fmaf(f7, 1.0001f, 1e-5f); }
+                if (EXTRA == 3) { i0 = i0 * 3 + 1; i1 = i1 * 3 + 1; i2 = i2 * 3 + 1; i3 = i3 * 3 + 1; i4 = i4 * 3 + 1; i5 = i5 * 3 + 1; i6 = i6 * 3 + 1; i7 = i7 * 3 + 1; }
+            }
+            if (EXTRA == 4) __nanosleep(0), n += 0;
+            if (EXTRA == 4) { for (int w = 0; w < 6; ++w) asm volatile("nanosleep.u32 20;"); }
+            n += 128;
+        }
+        if (d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7 + f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7 + i0 + i1 + i2 + i3 + i4 + i5 + i6 + i7 == 12345.678) g_sink = d0;
+        if ((tid & 31) == 0 && blockIdx.x == 0 && cycles) cycles[1 + (warp - 4)] = n;       // side instructions issued per lane
+    }
     if (warp == 1) {
         uint32_t leader;
         asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(leader));
@@ -167,6 +193,7 @@ probe_kernel(int iters, int32_t* __restrict__ out, int* __restrict__ err, long l
         const long long c1 = clock64();
         if (!ok && leader) atomicAdd(err, 1);
         if (leader && blockIdx.x == 0 && cycles) *cycles = c1 - c0;
+        stop = 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -187,20 +214,20 @@ probe_kernel(int iters, int32_t* __restrict__ out, int* __restrict__ err, long l
     }
 }
 
-template <int CG, int N, int S, int G, int COLL, int ORDER, int KC>
+template <int CG, int N, int S, int G, int COLL, int ORDER, int KC, int EXTRA = 0>
 static void run(int sms, const char* what) {
     constexpr int M = 128;
-    auto kern = probe_kernel<CG, N, S, G, COLL, ORDER, KC>;
+    auto kern = probe_kernel<CG, N, S, G, COLL, ORDER, KC, EXTRA>;
     size_t smem = (size_t)S * (M + N / CG) * KC;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int32_t* d_out; int* d_err; long long* d_cyc;
     const size_t nout = (size_t)M * CG * G * N;
     CK(cudaMalloc(&d_out, sizeof(int32_t) * nout)); CK(cudaMemset(d_out, 0xff, sizeof(int32_t) * nout));
     CK(cudaMalloc(&d_err, sizeof(int))); CK(cudaMemset(d_err, 0, sizeof(int)));
-    CK(cudaMalloc(&d_cyc, sizeof(long long)));
+    CK(cudaMalloc(&d_cyc, 8 * sizeof(long long))); CK(cudaMemset(d_cyc, 0, 8 * sizeof(long long)));
     auto launch = [&](int grid, int iters, int32_t* o) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(EXTRA ? 256 : 128); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
@@ -226,8 +253,9 @@ static void run(int sms, const char* what) {
     const int grid = sms / CG * CG;
     launch(grid, iters, nullptr);
     CK(cudaDeviceSynchronize());
-    long long cyc = 0; int e = 0;
-    CK(cudaMemcpy(&cyc, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    long long cyc = 0, side[8] = {0}; int e = 0;
+    CK(cudaMemcpy(side, d_cyc, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cyc = side[0];
     CK(cudaMemcpy(&e, d_err, sizeof(int), cudaMemcpyDeviceToHost));
     const int mmas = S * (S + 1) / 2 * (KC / 32);
     const double clk = (double)cyc / iters / mmas;
@@ -235,6 +263,8 @@ static void run(int sms, const char* what) {
     printf("%-58s cg%d M=%3d N=%3d S=%d G=%d KC=%d: exact %s; %6.1f clk per MMA (math floor %.0f -> %.2f of the pipe)%s\n", what, CG, M * CG, N, S, G, KC,
            bad < 0 ? "n/a (folded)" : bad == 0 ? "yes" : "NO", clk, ideal, ideal / clk, e ? "  [TIMEOUT]" : "");
     if (bad > 0) printf("    %ld accumulators differ\n", bad);
+    if (EXTRA) printf("    side work (warp 4): %.3f instructions per clk per sub-partition; MMA time stolen per side warp-instruction (4 warps): see clk per MMA above\n",
+                      (double)side[1] / (double)cyc);
     cudaFree(d_out); cudaFree(d_err); cudaFree(d_cyc);
 }
 
@@ -254,5 +284,11 @@ int main() {
     run<2, 128, 8, 4, 0, 0, 32>(sms, "CTA pair N=128 (groups folded), plain");
     run<2, 128, 8, 4, 1, 0, 32>(sms, "CTA pair N=128 (groups folded), A collector reuse");
     run<2, 128, 4, 4, 1, 0, 64>(sms, "CTA pair N=128 S=4 exactness, A collector reuse");
+    // interference: what does concurrent scalar work on the other warps cost the tensor pipe?
+    run<1, 64, 8, 8, 1, 0, 64, 1>(sms, "A reuse + 4 warps of DFMA chains");
+    run<1, 64, 8, 8, 1, 0, 64, 4>(sms, "A reuse + 4 warps of DFMA at low duty");
+    run<1, 64, 8, 8, 1, 0, 64, 2>(sms, "A reuse + 4 warps of FFMA chains");
+    run<1, 64, 8, 8, 1, 0, 64, 3>(sms, "A reuse + 4 warps of IMAD chains");
+    run<2, 64, 8, 8, 1, 0, 64, 1>(sms, "CTA pair, A reuse + 4 warps of DFMA chains");
     return 0;
 }
