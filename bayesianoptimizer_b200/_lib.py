@@ -66,6 +66,7 @@ SIGNATURES = {
     "bo_gemm_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _pd]),
     "bo_set_sweep_mode": (C.c_int, [_vp, _i32]),
     "bo_resolve_sweep_mode": (C.c_int, [_vp, _i64]),
+    "bo_set_linear_variance_ard": (C.c_int, [_vp, _pd, _i32]),
     "bo_last_sweep_path": (C.c_int, [_vp]),
     "bo_last_sweep_flagged": (C.c_int64, [_vp]),
     "bo_i8_peak": (C.c_int, [_vp, _f64, _pd]),

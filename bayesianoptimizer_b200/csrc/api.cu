@@ -274,6 +274,17 @@ int bo_resolve_sweep_mode(const bo_handle* h, int64_t pool_total) {
     return resolve_sweep_mode(h, h->sweep_mode, pool_total);
 }
 
+int bo_set_linear_variance_ard(bo_handle* h, const double* variances_host, int32_t d) {
+    if (!h) return BO_E_INVALID;
+    h->lin_v_ard.clear();
+    if (!variances_host || d == 0) return 0;
+    if (d < 0 || d > BO_MAX_DIM) return fail(h, BO_E_CAPACITY, "bo_set_linear_variance_ard: d exceeds BO_MAX_DIM");
+    for (int k = 0; k < d; ++k)
+        if (!(variances_host[k] >= 0.0)) return fail(h, BO_E_INVALID, "bo_set_linear_variance_ard: variances must be >= 0");
+    h->lin_v_ard.assign(variances_host, variances_host + d);
+    return 0;
+}
+
 int bo_last_sweep_path(const bo_handle* h) { return (h && h->sweep_timed) ? h->sweep_path : -1; }
 int64_t bo_last_sweep_flagged(const bo_handle* h) { return (h && h->sweep_timed) ? h->sweep_flagged : 0; }
 

@@ -114,12 +114,14 @@ struct bo_handle {
     int sweep_path = 0;               // contraction of the last sweep: 0 = FP64 DMMA, 7 / 8 = INT8 slices
     // the int8 pack of L^-1 is cached: factor_epoch moves whenever L^-1 changes (fit, append, SVGP load)
     uint64_t factor_epoch = 1, Lp8_epoch = 0; int Lp8_S = 0;
+    // per-dimension LinearKernel variances for the NEXT fit / SVGP load of the linear + Matern kind (bo_set_linear_variance_ard)
+    std::vector<double> lin_v_ard;
     // accuracy guard of the sliced sweep: candidates whose variance is too small for the slicing error bound are listed
     // here by the sweep kernel and re-scored on the FP64 contraction (sweep_i8.cuh)
     double* guard_dev = nullptr;              // [2]: max_i rowscale_i^2 (i + 1) as a double and its bit pattern (atomicMax)
     long long* flag_idx = nullptr; size_t flag_cap = 0;
     int* flag_count_dev = nullptr; int* flag_count_host = nullptr;   // host copy is pinned
-    long long sweep_flagged = 0;      // candidates of the last sweep that went through the FP64 re-score (-1: whole pool)
+    long long sweep_flagged = 0;      // candidates of the last sweep that went through the FP64 re-score
 
     void* select_ws = nullptr; size_t select_bytes = 0;  // large top-K (select.cu)
 

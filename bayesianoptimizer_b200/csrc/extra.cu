@@ -98,14 +98,14 @@ __global__ void __launch_bounds__(256) kq_build_kernel(const double* __restrict_
             sq = fma(df, df, sq);
             lin = fma(hyp.lin_w[k] * xq, xj, lin);
         }
-        if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
-            kval = fma(hyp.outputscale, lin, kernel_value_t<BO_KERNEL_MATERN52>(sq, hyp.outputscale));
-            g = 0.0;                         // gradients are not supported for this kind (pool-based acquisition only)
-        } else if (hyp.kind == BO_KERNEL_MATERN52) {
+        if (hyp.kind == BO_KERNEL_MATERN52 || hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
             const double s5 = 2.23606797749978969640917366873128;
             const double r = sqrt(sq), e = exp(-s5 * r);
             kval = hyp.outputscale * fma(sq, 5.0 / 3.0, fma(s5, r, 1.0)) * e;
             g = -hyp.outputscale * (5.0 / 3.0) * fma(s5, r, 1.0) * e;
+            // linear + Matern kind: k = s2 (v <x, x'> + matern); g stays the Matern factor, the linear term's own
+            // derivative s2 v x'_k is added where the gradient is assembled (acq_grad_finalize_kernel)
+            if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) kval = fma(hyp.outputscale, lin, kval);
         } else {
             kval = hyp.outputscale * exp(-0.5 * sq);
             g = -kval;
@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(256) acq_grad_finalize_kernel(const double* __
             mu = fma(kv[(size_t)qi * np + j], a, mu);
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                const double t = g * (xq[k] - Xs[(size_t)j * BO_MAX_DIM + k]) * hyp.inv_ls[k];
+                const double xj = Xs[(size_t)j * BO_MAX_DIM + k];
+                // dk_j/dx_k = g (x~_k - X~_jk) / l_k  [+ s2 v X_jk for the linear + Matern kind: lin_w = v l^2 on scaled inputs]
+                double t = g * (xq[k] - xj) * hyp.inv_ls[k];
+                if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) t = fma(hyp.outputscale * hyp.lin_w[k] * xj, hyp.inv_ls[k], t);
                 gm[k] = fma(a, t, gm[k]);
                 gs[k] = fma(w, t, gs[k]);
             }
@@ -244,10 +247,21 @@ __global__ void __launch_bounds__(256) acq_grad_finalize_kernel(const double* __
     for (int k = 0; k < DP; ++k) { gm[k] = block_sum_256(gm[k], red); gs[k] = block_sum_256(gs[k], red); }
     if (tid != 0) return;
     const double mean = hyp.mean + mu;
-    double var = hyp.outputscale - ss;
+    double prior = hyp.outputscale;
     double dvar[DP];
 #pragma unroll
     for (int k = 0; k < DP; ++k) dvar[k] = -2.0 * gs[k];
+    if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+        // prior variance s2 (v |x|^2 + 1) moves with x: d/dx_k = 2 s2 v x_k
+        double nn = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            nn = fma(hyp.lin_w[k] * xq[k], xq[k], nn);
+            dvar[k] = fma(2.0 * hyp.outputscale * hyp.lin_w[k] * xq[k], hyp.inv_ls[k], dvar[k]);
+        }
+        prior = hyp.outputscale * (nn + 1.0);
+    }
+    double var = prior - ss;
     if (var < min_var) {
         var = min_var;
 #pragma unroll
@@ -337,9 +351,6 @@ static int eval_acq_grad(bo_handle* h, int acq, double best_f, double beta, doub
 static int check_query_args(bo_handle* h, int acq_kind, double beta, const void* a, const void* b, const void* c, int k) {
     if (!h->fitted) return fail(h, BO_E_NOTFIT, "acquisition gradient / refinement before a successful bo_fit");
     if (h->svgp) return fail(h, BO_E_INVALID, "acquisition gradients / refinement are not defined on an SVGP predictive state");
-    if (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52)
-        return fail(h, BO_E_INVALID, "acquisition gradients / refinement are not implemented for the linear + Matern kernel "
-                                     "(the reference uses it with pool-based acquisition only, Bayesian7.py:650-688)");
     if (acq_kind < BO_ACQ_EI || acq_kind > BO_ACQ_MEAN) return fail(h, BO_E_INVALID, "unknown acquisition kind");
     if (!a || !b || !c || k < 1) return fail(h, BO_E_INVALID, "bad query arguments");
     if (k > 4096) return fail(h, BO_E_CAPACITY, "at most 4096 query points per call");
@@ -494,7 +505,7 @@ __global__ void __launch_bounds__(1024) append_finalize_kernel(int n, int np, in
     double prior = hyp.outputscale;
     if (hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
         double nn = 0.0;
-        for (int k = 0; k < d; ++k) nn = fma(hyp.lin_v * x[k], x[k], nn);
+        for (int k = 0; k < d; ++k) { const double xs = x[k] * hyp.inv_ls[k]; nn = fma(hyp.lin_w[k] * xs, xs, nn); }   // sum_k v_k x_k^2
         prior = hyp.outputscale * (nn + 1.0);
     }
     const double lam2 = prior + hyp.noise + hyp.jitter - ss;

@@ -670,9 +670,21 @@ static int fit_impl_prepare(bo_handle* h, const double* X_dev, const double* y_d
     Hyper& hy = h->hyp;
     hy.kind = kind; hy.d = d; hy.dp = h->dp; hy.outputscale = outputscale; hy.noise = noise; hy.mean = mean; hy.jitter = jitter;
     hy.lin_v = kind == BO_KERNEL_LINEAR_MATERN52 ? linear_variance : 0.0;
+    // gpytorch LinearKernel(ard_num_dims = d) carries one variance per input dimension (raw_variance (..., 1, d),
+    // optimization/Bayesian7.py:162-166): v <x, x'> becomes sum_k v_k x_k x'_k -- on the scaled inputs the weights v_k l_k^2
+    const bool ard_v = kind == BO_KERNEL_LINEAR_MATERN52 && (int)h->lin_v_ard.size() == d;
+    if (kind == BO_KERNEL_LINEAR_MATERN52 && !h->lin_v_ard.empty() && !ard_v) {
+        h->lin_v_ard.clear();
+        return fail(h, BO_E_INVALID, "bo_set_linear_variance_ard: the number of variances does not match the input dimension of this fit");
+    }
     for (int k = 0; k < BO_MAX_DIM; ++k) {
         hy.inv_ls[k] = k < d ? 1.0 / ls_host[k] : 0.0;
-        hy.lin_w[k] = k < d ? hy.lin_v * ls_host[k] * ls_host[k] : 0.0;
+        hy.lin_w[k] = k < d ? (ard_v ? h->lin_v_ard[k] : hy.lin_v) * ls_host[k] * ls_host[k] : 0.0;
+    }
+    if (ard_v) {                                  // lin_v keeps the mean (introspection only); consumed by this fit
+        double sv = 0.0; for (double v : h->lin_v_ard) sv += v;
+        hy.lin_v = sv / d;
+        h->lin_v_ard.clear();
     }
     stage_inputs_kernel<<<(np + 127) / 128, 128, 0, st>>>(X_dev, y_dev, n, d, np, hy, h->Xraw, h->Xs, h->yv);
     BO_LAUNCH_CHECK(h);

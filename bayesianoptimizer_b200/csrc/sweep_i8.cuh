@@ -650,12 +650,12 @@ static int ensure_i8_ws(bo_handle* h, int grid, long long pool) {
         BO_CUDA(h, cudaMalloc(&h->panel8, p_bytes));
         h->panel8_bytes = p_bytes;
     }
-    // guard: up to a quarter of the pool (at least 16 Ki entries) may be re-scored; beyond that the whole pool is
+    // guard: room for every candidate of the pool (8 B each).  The path a candidate takes must depend on the candidate alone --
+    // a "too many flagged, re-score the whole pool" shortcut would make values depend on the shard layout
     if (!h->guard_dev) { BO_CUDA(h, cudaMalloc(&h->guard_dev, 2 * sizeof(double))); h->Lp8_epoch = 0; }
     if (!h->flag_count_dev) BO_CUDA(h, cudaMalloc(&h->flag_count_dev, sizeof(int)));
     if (!h->flag_count_host) BO_CUDA(h, cudaMallocHost(&h->flag_count_host, sizeof(int)));
-    size_t cap = (size_t)(pool / 4 > 16384 ? pool / 4 : 16384);
-    if (cap > (size_t)pool) cap = (size_t)pool;
+    const size_t cap = (size_t)(pool > 0 ? pool : 1);
     if (cap > h->flag_cap) {
         if (h->flag_idx) cudaFree(h->flag_idx);
         h->flag_idx = nullptr; h->flag_cap = 0;
@@ -734,12 +734,6 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     BO_CUDA(h, cudaStreamSynchronize(st));
     const long long flagged = *h->flag_count_host;
     int lists = grid;
-    if (flagged > (long long)h->flag_cap) {
-        // most of the pool sits on top of the data: the FP64 contraction scores all of it
-        if ((rc = sweep_fp64_run(h, a_in, 0, true, vals_dev, idx_dev, nullptr, st))) return rc;
-        h->sweep_path = S; h->sweep_flagged = -1;
-        return 0;
-    }
     if (flagged > 0) {
         SweepArgs a2 = a_in;
         a2.N = flagged; a2.idx_map = h->flag_idx;

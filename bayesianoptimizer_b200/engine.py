@@ -89,6 +89,19 @@ class GPEngine:
             raise BoError(rc, self._lib.bo_last_error(self._h).decode())
         return rc
 
+    def _linear_variance(self, linear_variance, d: int) -> float:
+        """Scalar LinearKernel variance, or one per input dimension (gpytorch ``LinearKernel(ard_num_dims=d)``): the latter
+        is handed to the library for the next fit / load (bo_set_linear_variance_ard) and its mean returned as the scalar."""
+        v = torch.as_tensor(linear_variance, dtype=torch.float64).reshape(-1).cpu()
+        if v.numel() == 1:
+            self._check(self._lib.bo_set_linear_variance_ard(self._h, None, 0))
+            return float(v[0])
+        if v.numel() != d:
+            raise ValueError(f"linear_variance must be a scalar or have d = {d} entries, got {v.numel()}")
+        arr = (C.c_double * d)(*v.tolist())
+        self._check(self._lib.bo_set_linear_variance_ard(self._h, arr, d))
+        return float(v.mean())
+
     def _dev64(self, t, shape=None) -> torch.Tensor:
         t = torch.as_tensor(t, dtype=torch.float64, device=self.device).contiguous()
         if shape is not None:
@@ -118,6 +131,7 @@ class GPEngine:
             yb = self._dev64(y, (-1,))
         if yb.numel() != n:
             raise ValueError("y must have n entries")
+        linear_variance = self._linear_variance(linear_variance, d) if _KERNELS[kernel] == KERNEL_LINEAR_MATERN52 else 0.0
         with torch.cuda.device(self.device):
             rc = self._lib.bo_fit_ex(self._h, Xb.data_ptr(), yb.data_ptr(), n, d, _KERNELS[kernel], ls_arr, float(outputscale),
                                      float(noise), float(mean), float(jitter), float(linear_variance), 1 if host else 0,
@@ -165,6 +179,7 @@ class GPEngine:
         if ls.numel() != d:
             raise ValueError("lengthscale must be a scalar or have d entries")
         ls_arr = (C.c_double * d)(*ls.tolist())
+        linear_variance = self._linear_variance(linear_variance, d) if _KERNELS[kernel] == KERNEL_LINEAR_MATERN52 else 0.0
         with torch.cuda.device(self.device):
             rc = self._lib.bo_svgp_load(self._h, Z.data_ptr(), M, d, _KERNELS[kernel], ls_arr, float(outputscale),
                                         float(linear_variance), float(mean), float(noise), float(jitter), m.data_ptr(),
@@ -352,7 +367,7 @@ class GPEngine:
         return int(self._lib.bo_last_sweep_path(self._h))
 
     def last_sweep_flagged(self) -> int:
-        """Candidates of the last sliced sweep its accuracy guard re-scored on the FP64 contraction (-1: the whole pool)."""
+        """Candidates of the last sliced sweep its accuracy guard re-scored on the FP64 contraction."""
         return int(self._lib.bo_last_sweep_flagged(self._h))
 
     def launch_count(self) -> int:

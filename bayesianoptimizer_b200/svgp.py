@@ -29,7 +29,7 @@ class SVGPTaskState:
     var_chol: torch.Tensor          # (M, M) chol_variational_covar (lower triangle used)
     lengthscale: torch.Tensor       # (d,)
     outputscale: float
-    linear_variance: float
+    linear_variance: object         # float, or a (d,) tensor: one LinearKernel variance per input dimension
     mean: float
     noise: float
 
@@ -47,11 +47,20 @@ def tasks_from_state_dict(model_sd: Dict[str, torch.Tensor], likelihood_sd: Dict
     T, M, d = Z.shape
     const = g("mean_module.raw_constant", "mean_module.constant").to(torch.float64).reshape(T)
     s2 = F.softplus(g("covar_module.raw_outputscale").to(torch.float64)).reshape(T)
-    v = F.softplus(g("covar_module.base_kernel.kernels.0.raw_variance").to(torch.float64)).reshape(T)
+    # LinearKernel(ard_num_dims=d, batch_shape=[T]) (Bayesian7.py:162-166): raw_variance is (T, 1, d) in current gpytorch -- one
+    # variance per input dimension -- and (T, 1, 1) where ard_num_dims is not honoured; both are accepted
+    raw_v = g("covar_module.base_kernel.kernels.0.raw_variance").to(torch.float64)
+    if raw_v.numel() == T:
+        v = F.softplus(raw_v).reshape(T)
+    elif raw_v.numel() == T * d:
+        v = F.softplus(raw_v).reshape(T, d)
+    else:
+        raise ValueError(f"LinearKernel raw_variance has shape {tuple(raw_v.shape)}; expected (T, 1, 1) or (T, 1, d) with T = {T}, d = {d}")
     ls = F.softplus(g("covar_module.base_kernel.kernels.1.raw_lengthscale").to(torch.float64)).reshape(T, d)
     raw_noise = likelihood_sd["noise_covar.raw_noise"].to(torch.float64).reshape(T)
     noise = F.softplus(raw_noise) + noise_lower_bound
-    return [SVGPTaskState(Z[t], m[t], Ls[t], ls[t], float(s2[t]), float(v[t]), float(const[t]), float(noise[t])) for t in range(T)]
+    lin_v = lambda t: float(v[t]) if v.ndim == 1 else v[t].clone()
+    return [SVGPTaskState(Z[t], m[t], Ls[t], ls[t], float(s2[t]), lin_v(t), float(const[t]), float(noise[t])) for t in range(T)]
 
 
 class BatchSVGPPredictor:

@@ -43,7 +43,7 @@ extern "C" {
 #define BO_KERNEL_RBF      1
 #define BO_KERNEL_LINEAR_MATERN52 2   /* ScaleKernel(LinearKernel + MaternKernel(2.5, ard)): outputscale * (v <x,x'> + matern),
                                        * the explicit kernel of optimization/Bayesian6.py:471-473 and Bayesian7.py:162-166;
-                                       * supported by fit / posterior / sweep / append / lml (not by refine / acq_grad) */
+                                       * supported by every entry point (fit / posterior / sweep / append / lml / acq_grad / refine) */
 
 /* acquisition kinds (analytic closed forms; maximisation as in optimization/Bayesian.py:98) */
 #define BO_ACQ_EI    0   /* expected improvement                                  (Bayesian.py:100-101) */
@@ -111,6 +111,13 @@ int bo_fit_host(bo_handle* h, const double* X_host, const double* y_host, int32_
 int bo_fit_ex(bo_handle* h, const double* X, const double* y, int32_t n, int32_t d, int32_t kernel_kind,
               const double* lengthscale_host, double outputscale, double noise, double mean, double jitter,
               double linear_variance, int32_t host_inputs, void* stream);
+
+/* Per-dimension LinearKernel variances v[d] for the NEXT bo_fit_ex / bo_svgp_load of the BO_KERNEL_LINEAR_MATERN52 kind:
+ * k = outputscale * (sum_k v_k x_k x'_k + matern).  gpytorch's LinearKernel(ard_num_dims = D, batch_shape = [T]) of
+ * optimization/Bayesian7.py:162-166 registers raw_variance with shape (T, 1, D), one variance per input dimension; the
+ * scalar `linear_variance` argument of those calls covers the (T, 1, 1) layout.  Consumed by that fit; NULL / d = 0 clears.
+ * The batched LML (bo_lml_grad_batched) keeps one scalar variance as its hyper-parameter. */
+int bo_set_linear_variance_ard(bo_handle* h, const double* variances_host, int32_t d);
 
 /* SVGP predictive state: loads ONE task of the reference's batched sparse variational GP
  * (optimization/Bayesian7.py:129-195: whitened VariationalStrategy, CholeskyVariationalDistribution, kernel
@@ -244,8 +251,8 @@ int bo_resolve_sweep_mode(const bo_handle* h, int64_t pool_total);
 /* Contraction the last bo_sweep ran: 0 = FP64 DMMA, 7 / 8 = INT8-sliced with that many slices, -1 = no sweep yet. */
 int bo_last_sweep_path(const bo_handle* h);
 
-/* Candidates of the last sliced sweep that its accuracy guard sent through the FP64 contraction (0 for an FP64 sweep;
- * -1: more than a quarter of the pool was flagged and the whole pool was scored on the FP64 contraction). */
+/* Candidates of the last sliced sweep that its accuracy guard sent through the FP64 contraction (0 for an FP64 sweep).
+ * Which path a candidate takes depends on the candidate alone, never on the pool or shard it arrives in. */
 int64_t bo_last_sweep_flagged(const bo_handle* h);
 
 /* INT8 tensor-pipe peak probe (tcgen05.mma kind::i8, 128 x 256 x 32 on resident operands): roofline denominator

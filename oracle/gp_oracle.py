@@ -96,13 +96,15 @@ def kernel_from_sqdist(sq, kind, outputscale):
 
 def kernel_matrix(A, B, kind, lengthscale, outputscale, linear_variance=0.0):
     """k(A, B).  Kind 2 is ScaleKernel(LinearKernel + Matern-5/2): s2 * (v <a, b> + matern(a, b)); gpytorch's LinearKernel
-    has ONE scalar variance v and acts on the raw inputs."""
+    acts on the raw inputs; its variance is a scalar, or one per input dimension with ard_num_dims (Bayesian7.py:162-166 asks
+    for that: raw_variance (T, 1, d)), in which case v <a, b> reads sum_k v_k a_k b_k."""
     if kind == KERNEL_LINEAR_MATERN52:
         A = np.asarray(A, dtype=np.float64); B = np.asarray(B, dtype=np.float64)
+        v = np.broadcast_to(np.asarray(linear_variance, dtype=np.float64), (A.shape[1],))     # scalar, or one per dimension (ARD)
         lin = np.zeros((A.shape[0], B.shape[0]))
         for k in range(A.shape[1]):
-            lin += A[:, k:k + 1] * B[:, k].reshape(1, -1)
-        return outputscale * linear_variance * lin + kernel_from_sqdist(scaled_sqdist(A, B, lengthscale), KERNEL_MATERN52, outputscale)
+            lin += v[k] * A[:, k:k + 1] * B[:, k].reshape(1, -1)
+        return outputscale * lin + kernel_from_sqdist(scaled_sqdist(A, B, lengthscale), KERNEL_MATERN52, outputscale)
     return kernel_from_sqdist(scaled_sqdist(A, B, lengthscale), kind, outputscale)
 
 
@@ -110,7 +112,8 @@ def prior_variance(X, kind, outputscale, linear_variance=0.0):
     """k(x, x) per row: s2 for the stationary kinds, s2 (v |x|^2 + 1) for linear + Matern."""
     X = np.asarray(X, dtype=np.float64)
     if kind == KERNEL_LINEAR_MATERN52:
-        return outputscale * (linear_variance * np.sum(X * X, axis=1) + 1.0)
+        v = np.broadcast_to(np.asarray(linear_variance, dtype=np.float64), (X.shape[1],))
+        return outputscale * (np.sum(v[None, :] * X * X, axis=1) + 1.0)
     return np.full(X.shape[0], float(outputscale))
 
 
@@ -165,7 +168,8 @@ def fit(X, y, kind=KERNEL_MATERN52, lengthscale=None, outputscale=1.0, noise=1e-
     K[np.diag_indices(n)] = prior_variance(X, kind, outputscale, linear_variance) + noise + jitter   # exact diagonal (d(x,x)=0)
     L = _cholesky_lower(K)
     alpha = sla.cho_solve((L, True), y - mean)
-    return GPFit(X, y, kind, ls, float(outputscale), float(noise), float(mean), L, alpha, float(linear_variance))
+    lv = float(linear_variance) if np.ndim(linear_variance) == 0 else np.asarray(linear_variance, dtype=np.float64).copy()
+    return GPFit(X, y, kind, ls, float(outputscale), float(noise), float(mean), L, alpha, lv)
 
 
 def posterior(gp: GPFit, Xs, min_variance=MIN_VARIANCE, chunk=2048):
@@ -372,7 +376,7 @@ def posterior_with_grad(gp: GPFit, x):
     ls = gp.lengthscale
     diff = (x[None, :] - gp.X) / ls[None, :]                 # (n, d)  (x - X_j)/l
     sq = np.sum(diff * diff, axis=1)
-    if gp.kind == KERNEL_MATERN52:
+    if gp.kind in (KERNEL_MATERN52, KERNEL_LINEAR_MATERN52):
         r = np.sqrt(sq)
         e = np.exp(-SQRT5 * r)
         k = gp.outputscale * (1.0 + SQRT5 * r + (5.0 / 3.0) * sq) * e
@@ -381,11 +385,19 @@ def posterior_with_grad(gp: GPFit, x):
         k = gp.outputscale * np.exp(-0.5 * sq)
         g = -k
     dk = g[:, None] * diff / ls[None, :]                     # (n, d) dk_j/dx
+    prior, dprior = gp.outputscale, 0.0
+    if gp.kind == KERNEL_LINEAR_MATERN52:
+        # ScaleKernel(Linear + Matern) of optimization/Bayesian6.py:470-478: k = s2 (v <x, x'> + matern)
+        v = np.broadcast_to(np.asarray(gp.linear_variance, dtype=np.float64), x.shape)      # scalar or per dimension
+        k = k + gp.outputscale * (gp.X @ (v * x))
+        dk = dk + gp.outputscale * v[None, :] * gp.X
+        prior = gp.outputscale * (float(np.sum(v * x * x)) + 1.0)
+        dprior = 2.0 * gp.outputscale * v * x
     mu = gp.mean + float(k @ gp.alpha)
     w = sla.cho_solve((gp.L, True), k)                       # K^-1 k
-    var = gp.outputscale - float(k @ w)
+    var = prior - float(k @ w)
     dmu = dk.T @ gp.alpha
-    dvar = -2.0 * (dk.T @ w)
+    dvar = dprior - 2.0 * (dk.T @ w)
     return mu, var, dmu, dvar
 
 

@@ -70,7 +70,7 @@ def test_sliced_sweep_on_reference_rows_strict(engine, name, noise, near_min, va
         vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, candidates=cd, topk=8, return_all=True)
         assert engine.last_sweep_path() == (7 if mode == "i8x7" else 8), "the pool must take the sliced path"
         flagged = engine.last_sweep_flagged()
-        assert flagged != 0, "points next to training rows must reach the guard's FP64 re-score"
+        assert flagged > 0, "points next to training rows must reach the guard's FP64 re-score"
         if mode != "i8x7":
             assert 0 < flagged < 10_000, flagged          # ... and only those: most of the pool stays on the tensor path
         gm, gv, ga = gm.cpu().numpy(), gv.cpu().numpy(), ga.cpu().numpy()
@@ -101,9 +101,10 @@ def test_guard_flags_only_what_it_must(engine):
     assert_acq_close("ei", ga.cpu().numpy(), ref["ei"][var > 1e-3])
 
 
-def test_pool_on_top_of_the_data_falls_back_to_fp64_whole(engine):
-    """More than a quarter of the pool flagged -> the whole pool is scored by the FP64 contraction (flagged == -1): a low-noise
-    model (1e-5) and a pool sitting 1e-6 away from its training rows, sigma^2 ~ 1e-5 everywhere."""
+def test_pool_on_top_of_the_data_is_rescored_almost_entirely(engine):
+    """A low-noise model (1e-5) and a pool sitting 1e-6 away from its training rows, sigma^2 ~ 1e-5 everywhere: the guard
+    sends (nearly) every candidate through the FP64 contraction -- each on its own merits, there is no whole-pool shortcut
+    (that would make values depend on the shard layout)."""
     X, y, kind, ls, s2, cand, mu, var, bf, ref = _problem("csv_n512_matern", 1e-3, 1e-5)
     rng = np.random.default_rng(5)
     pool = np.clip(X[rng.integers(0, len(X), 20_000)] + 1e-6 * rng.standard_normal((20_000, X.shape[1])), 0, 1)
@@ -113,7 +114,7 @@ def test_pool_on_top_of_the_data_falls_back_to_fp64_whole(engine):
     engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "matern52", ls, s2, 1e-5)
     engine.set_sweep_mode("i8x8")
     vals, idx, gm, gv, ga = engine.sweep("ucb", bf, 2.0, candidates=torch.from_numpy(pool).cuda(), topk=8, return_all=True)
-    assert engine.last_sweep_path() == 8 and engine.last_sweep_flagged() == -1
+    assert engine.last_sweep_path() == 8 and engine.last_sweep_flagged() > 15_000
     assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), pm, pv, var_abs=ULP64 * s2)
     tv, ti = o.topk(o.acquisition(pm, pv, o.ACQ_UCB, bf, beta=2.0), 8)
     got = idx.cpu().numpy()

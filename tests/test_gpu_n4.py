@@ -95,14 +95,47 @@ def test_linear_matern_sobol_pool_and_append(engine):
     np.testing.assert_allclose(np.diag(engine.state()[1].cpu().numpy()), np.diag(ref.L), rtol=1e-8)
 
 
-def test_linear_matern_gradient_paths_refuse(engine):
+@pytest.mark.parametrize("acq,ak", [("ei", o.ACQ_EI), ("logei", o.ACQ_LOGEI), ("ucb", o.ACQ_UCB), ("var", o.ACQ_VAR), ("mean", o.ACQ_MEAN)])
+def test_linear_matern_acquisition_gradient_against_oracle(engine, acq, ak):
+    """bo_acq_grad on the reference's explicit kernel ScaleKernel(Linear + Matern) (optimization/Bayesian6.py:470-478 -- the
+    kernel its optimize_acqf call at :905-916 differentiates through autograd): values and gradients against the oracle's
+    analytic formulas, which tests/test_oracle.py pins to finite differences."""
+    X, y = _problem(300, 5, 3)
+    ls = np.array([0.5, 0.4, 0.6, 0.8, 0.7])
+    gp = o.fit(X, y, LIN, ls, 1.3, 1e-3, mean=0.05, linear_variance=0.37)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", ls, 1.3, 1e-3, mean=0.05, linear_variance=0.37)
+    rng = np.random.default_rng(9)
+    Q = np.vstack([rng.random((24, 5)), np.clip(X[:8] + 1e-3 * rng.standard_normal((8, 5)), 0, 1)])
+    bf = float(y.max())
+    val, grad = engine.acq_grad(_cuda(Q), acq, bf, 2.0)
+    val, grad = val.cpu().numpy(), grad.cpu().numpy()
+    for i, x in enumerate(Q):
+        v, g = o.acquisition_with_grad(gp, x, ak, bf, 2.0)
+        assert abs(val[i] - v) <= 1e-6 * max(abs(v), 1e-300) + (1e-6 if acq == "logei" else 0.0), (i, val[i], v)
+        np.testing.assert_allclose(grad[i], g, rtol=2e-6, atol=1e-8 * (1.0 + np.abs(g).max()))
+
+
+def test_linear_matern_refine_matches_scipy_lbfgsb(engine):
+    """bo_refine on the linear + Matern kind vs SciPy L-BFGS-B on the oracle's acquisition from the same starts
+    (the optimize_acqf call of Bayesian6.py:905-916); SURVEY App. A.7 criterion as for the stationary kinds."""
+    import scipy.optimize as so
     from bayesianoptimizer_b200 import BoError
-    X, y = _problem(64, 3, 3)
-    engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.5, 1.0, 1e-3, linear_variance=0.5)
-    with pytest.raises(BoError):
-        engine.refine(_cuda(X[:4]), "ei", 0.0, iters=3)
-    with pytest.raises(BoError):
-        engine.acq_grad(_cuda(X[:4]), "ei", 0.0)
+    X, y = _problem(256, 4, 5)
+    gp = o.fit(X, y, LIN, 0.6, 1.0, 1e-3, linear_variance=0.5)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.6, 1.0, 1e-3, linear_variance=0.5)
+    bf = float(y.max())
+    starts = np.random.default_rng(5).random((12, 4))
+    v0, _ = engine.acq_grad(_cuda(starts), "logei", bf)
+    xr, vr = engine.refine(_cuda(starts), "logei", bf, iters=150)
+    xr, vr, v0 = xr.cpu().numpy(), vr.cpu().numpy(), v0.cpu().numpy()
+    assert np.all(vr >= v0 - 1e-12) and np.all((xr >= 0.0) & (xr <= 1.0))
+    for i in range(12):
+        v, _ = o.acquisition_with_grad(gp, xr[i], o.ACQ_LOGEI, bf)
+        assert abs(v - vr[i]) <= 1e-6
+    ref = np.array([-so.minimize(lambda z: tuple(-np.asarray(t) for t in o.acquisition_with_grad(gp, z, o.ACQ_LOGEI, bf)), s0, jac=True,
+                                 method="L-BFGS-B", bounds=[(0.0, 1.0)] * 4, options={"maxiter": 200}).fun for s0 in starts])
+    assert vr.max() >= ref.max() - 1e-3 * max(1.0, abs(ref.max()))
+    assert np.mean(vr >= ref - 1e-2 * np.maximum(1.0, np.abs(ref))) >= 0.75
     with pytest.raises(BoError):
         engine.fit(_cuda(X), _cuda(y), "linear_matern52", 0.5, 1.0, 1e-3, linear_variance=-1.0)
 
@@ -182,3 +215,34 @@ def test_log_transformed_eight_output_model_predicts_validation_rows(engine):
     omu, ovar = o.posterior_multi(gp, otr.forward(Yraw[:n]), U[n:n + 100])
     np.testing.assert_allclose(pred, otr.inverse_mean(omu, ovar[:, None]), rtol=1e-7)
     assert pred.shape == (100, 8) and np.all(np.isfinite(pred))
+
+
+def test_per_dimension_linear_variance_exact_gp(engine):
+    """LinearKernel(ard_num_dims=d) (Bayesian7.py:162-166: raw_variance (T, 1, d)): one variance per input dimension through
+    fit / posterior / sweep / append / acq_grad against the oracle; a following scalar fit is not affected."""
+    X, y = _problem(260, 5, 21)
+    ls = np.array([0.5, 0.4, 0.6, 0.8, 0.7])
+    v = np.array([0.9, 0.05, 0.4, 1.7, 0.0])
+    gp = o.fit(X, y, LIN, ls, 1.2, 1e-3, mean=0.02, linear_variance=v)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", ls, 1.2, 1e-3, mean=0.02, linear_variance=v)
+    xs = np.random.default_rng(3).random((700, 5))
+    mu, var = engine.posterior(_cuda(xs))
+    omu, ovar = o.posterior(gp, xs)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+    val, grad = engine.acq_grad(_cuda(xs[:16]), "ucb", 0.0, 2.0)
+    for i in range(16):
+        ov, og = o.acquisition_with_grad(gp, xs[i], o.ACQ_UCB, 0.0, 2.0)
+        assert abs(val[i].item() - ov) <= 1e-6 * abs(ov)
+        np.testing.assert_allclose(grad[i].cpu().numpy(), og, rtol=2e-6, atol=1e-8 * (1 + np.abs(og).max()))
+    engine.append(_cuda(xs[0]))
+    gp2 = o.append_point(gp, xs[0])
+    mu, var = engine.posterior(_cuda(xs[1:200]))
+    omu, ovar = o.posterior(gp2, xs[1:200])
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+    with pytest.raises(ValueError):
+        engine.fit(_cuda(X), _cuda(y), "linear_matern52", ls, 1.2, 1e-3, linear_variance=v[:3])
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", ls, 1.2, 1e-3, mean=0.02, linear_variance=0.3)      # scalar again
+    gp3 = o.fit(X, y, LIN, ls, 1.2, 1e-3, mean=0.02, linear_variance=0.3)
+    mu, var = engine.posterior(_cuda(xs[:100]))
+    omu, ovar = o.posterior(gp3, xs[:100])
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)

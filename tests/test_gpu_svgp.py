@@ -149,3 +149,15 @@ def test_batch_svgp_pool_scan_topk_fps_matches_oracle():
         assert idx.cpu().tolist() == ref.tolist()
     assert pts.shape == (500, d) and len(set(idx.cpu().tolist())) == 500
     pred.close()
+
+
+def test_svgp_per_dimension_linear_variance(engine):
+    """The (T, 1, d) raw_variance layout of LinearKernel(ard_num_dims=d) (Bayesian7.py:162-166): predictive mean / variance of
+    a task with one LinearKernel variance per input dimension, against the oracle."""
+    t = _task(200, 5, 77, o.KERNEL_LINEAR_MATERN52)
+    t.linear_variance = np.array([0.6, 0.02, 0.3, 1.1, 0.25])
+    _load(engine, t)
+    xs = np.random.default_rng(9).standard_normal((900, 5))
+    mu, var = engine.posterior(_cuda(xs))
+    omu, ovar = o.svgp_predict(t, xs)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)

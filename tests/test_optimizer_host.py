@@ -266,6 +266,16 @@ def test_svgp_tasks_from_state_dict():
     assert tasks[3].outputscale == pytest.approx(float(F.softplus(msd["covar_module.raw_outputscale"][3].double())))
     assert tasks[5].noise == pytest.approx(float(F.softplus(lsd["noise_covar.raw_noise"][5, 0].double())) + 1e-4)
     np.testing.assert_allclose(tasks[2].lengthscale.numpy(), F.softplus(msd["covar_module.base_kernel.kernels.1.raw_lengthscale"][2, 0].double()).numpy())
+    assert isinstance(tasks[2].linear_variance, float)
+    # LinearKernel(ard_num_dims=d, batch_shape=[T]) (Bayesian7.py:162-166): current gpytorch registers raw_variance as (T, 1, d)
+    msd["covar_module.base_kernel.kernels.0.raw_variance"] = r(T, 1, d)
+    tasks = tasks_from_state_dict(msd, lsd)
+    assert tasks[4].linear_variance.shape == (d,)
+    np.testing.assert_allclose(tasks[4].linear_variance.numpy(),
+                               F.softplus(msd["covar_module.base_kernel.kernels.0.raw_variance"][4, 0].double()).numpy())
+    msd["covar_module.base_kernel.kernels.0.raw_variance"] = r(T, 2, d)
+    with pytest.raises(ValueError):
+        tasks_from_state_dict(msd, lsd)
 
 
 def test_warm_refits_use_one_start_and_periodic_full_multistart(tmp_path):

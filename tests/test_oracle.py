@@ -87,8 +87,8 @@ def test_lml_gradient_against_finite_differences():
 def test_acquisition_gradient_against_finite_differences():
     X, y = synth_problem(150, 5, 1, 2)
     rng = np.random.default_rng(5)
-    for kind in (o.KERNEL_MATERN52, o.KERNEL_RBF):
-        gp = o.fit(X, y, kind, [0.5, 0.4, 0.6, 0.8, 0.7], 1.3, 1e-3)
+    for kind in (o.KERNEL_MATERN52, o.KERNEL_RBF, o.KERNEL_LINEAR_MATERN52):      # kind 2: Bayesian6.py:470-478
+        gp = o.fit(X, y, kind, [0.5, 0.4, 0.6, 0.8, 0.7], 1.3, 1e-3, linear_variance=0.37 if kind == o.KERNEL_LINEAR_MATERN52 else 0.0)
         x0 = rng.random(5)
         for ak in (o.ACQ_EI, o.ACQ_LOGEI, o.ACQ_UCB, o.ACQ_VAR, o.ACQ_MEAN):
             _, gd = o.acquisition_with_grad(gp, x0, ak, 1.0, 2.0)
