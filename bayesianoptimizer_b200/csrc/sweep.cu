@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                     sobol_point<DP>(dirs, shift, a.d, a.first_index + li, xc[gi]);
                 }
 #pragma unroll
-                for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
+                for (int k = 0; k < DP; ++k) xc[gi][k] = __dmul_rn(xc[gi][k], a.hyp.inv_ls[k]);     // (never contracted into the differences below: every code instance must round alike)
             }
             // linear + Matern kind: weighted copies for the inner-product term and the candidates' prior variance
             double xw[2][KIND == BO_KERNEL_LINEAR_MATERN52 ? DP : 1];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const SweepArgs a)
                             double sq = 0.0, lin = 0.0;
 #pragma unroll
                             for (int k = 0; k < DP; ++k) {
-                                const double df = xc[gi][k] - x[r][k];
+                                const double df = __dsub_rn(xc[gi][k], x[r][k]);
                                 sq = fma(df, df, sq);
                                 if (KIND == BO_KERNEL_LINEAR_MATERN52) lin = fma(xw[gi][k], x[r][k], lin);
                             }

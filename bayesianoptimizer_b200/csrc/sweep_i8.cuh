@@ -64,8 +64,11 @@ struct I8Smem {
 struct SweepI8Args {
     const int8_t* Lp8; const double* rowscale; int8_t* panel8;
     const int8_t* Lp8_zero;  // one all-zero stage tile of L^-1 slices (CTA-pair kernel: K steps beyond a row block's own extent)
-    double dig_scale;       // 2^(6 + 7 (S - 1)) / (power-of-two bound of |k*|): k* -> fixed point
-    double eb_scale;        // eb * 2^-12: folded into the row scale at the drain
+    double dig_scale;       // 2^(6 + 7 (S - 1)) / (power-of-two bound eb of |k*|): k* -> fixed point
+    double eb_scale;        // 2^-12: folded into the row scale at the drain (the accumulators count units of 2^-12 eb rowscale)
+    double ss_scale;        // eb^2: applied to the finished column sum (a power of two: exact, commutes with the summation).
+                            // Linear + Matern kind: |k*| has no model-wide bound -- the CTA-pair kernel derives eb per
+                            // candidate from s2 (sqrt(|x*|_w^2 guard_w[1]) + 1) and ignores dig_scale / ss_scale
     // accuracy guard: a candidate whose variance s2 - ||u||^2 is below guard_scale * sqrt(W ||u||^2), W = guard_w[0] =
     // max_i rowscale_i^2 (i + 1), is not scored here: its pool position goes to flag_idx (warp-aggregated append through
     // flag_count) and the FP64 contraction re-scores it after the kernel
@@ -175,6 +178,16 @@ __global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restri
         // W = max over the real rows of rowscale_i^2 (i + 1): positive doubles order like their bit patterns
         if (i < n) atomicMax(reinterpret_cast<unsigned long long*>(guard_w), (unsigned long long)__double_as_longlong(rs * rs * (double)(i + 1)));
     }
+}
+
+// linear + Matern kind: guard_w[1] = max_j sum_k lin_w[k] x~_jk^2 (the largest weighted squared norm of a training row), from
+// which a candidate's bound on |k*| follows by Cauchy-Schwarz
+__global__ void __launch_bounds__(256) i8_xnorm_kernel(const double* __restrict__ Xs, int n, Hyper hyp, double* __restrict__ guard_w) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    double nn = 0.0;
+    for (int k = 0; k < hyp.d; ++k) { const double x = Xs[(size_t)j * BO_MAX_DIM + k]; nn = fma(hyp.lin_w[k] * x, x, nn); }
+    atomicMax(reinterpret_cast<unsigned long long*>(guard_w + 1), (unsigned long long)__double_as_longlong(nn));
 }
 
 // one thread per (row, 16-column chunk) of a stage tile: S x 16 B, tile (ib, kc) at ((ib (ib + 1) / 2) * 2 + kc) * S * 8 KB
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                     sobol_point<DP>(dirs, shift, a.d, a.first_index + li, xc[gi]);
                 }
 #pragma unroll
-                for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
+                for (int k = 0; k < DP; ++k) xc[gi][k] = __dmul_rn(xc[gi][k], a.hyp.inv_ls[k]);     // (never contracted into the differences below: every code instance must round alike)
             }
             double mu0 = 0.0, mu1 = 0.0;
             // X~ and alpha staged through the builders' own shared-memory region in double-buffered cp.async chunks
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                         for (int gi = 0; gi < 2; ++gi) {
                             double sq = 0.0;
 #pragma unroll
-                            for (int k = 0; k < DP; ++k) { const double df = xc[gi][k] - x[k]; sq = fma(df, df, sq); }
+                            for (int k = 0; k < DP; ++k) { const double df = __dsub_rn(xc[gi][k], x[k]); sq = fma(df, df, sq); }
                             const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
                             kv[gi][r] = (j < a.n) ? v : 0.0;
                         }
@@ -532,7 +545,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
             // ================= epilogue: variance, acquisition, CTA-local top-k =====================
             if (tid < I8_BN) {
                 const long long li = blk * I8_BN + tid;
-                const double ss = (colsum[tid] + colsum[I8_BN + tid]) + (colsum[2 * I8_BN + tid] + colsum[3 * I8_BN + tid]);
+                const double ss = ((colsum[tid] + colsum[I8_BN + tid]) + (colsum[2 * I8_BN + tid] + colsum[3 * I8_BN + tid])) * b.ss_scale;
                 // accuracy guard: too little variance left for the slicing error bound -> the FP64 contraction scores it
                 const bool flagged = b.flag_count != nullptr && li < a.N &&
                                      !(a.hyp.outputscale - ss >= b.guard_scale * sqrt(__ldg(b.guard_w) * ss));
@@ -600,7 +613,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
 // the model side of eligibility: exact GP with a stationary kernel (|k*| <= output scale), more than one stage of rows
 static bool sweep_i8_model_ok(const bo_handle* h) {
     // np < 2^16: the INT32 group accumulators hold at most 8 * 64 * 64 * np
-    return h->fitted && !h->svgp && h->hyp.kind != BO_KERNEL_LINEAR_MATERN52 && h->np >= I8_MIN_NP && h->np < 65536;
+    // (the linear + Matern kind runs on the CTA-pair kernel only: per-candidate operand scale)
+    return h->fitted && !h->svgp && h->np >= I8_MIN_NP && h->np < 65536;
 }
 
 // Slice count of AUTO.  8 slices reproduce the FP64 product to within ~2x its own rounding error on everything the
@@ -689,6 +703,8 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     // CTA pairs (cta_group::2, sweep_i8_pair.cuh) share one 64-candidate block; BO_B200_I8_PAIR=0 keeps the one-CTA kernel (triage / A-B)
     const char* pe = getenv("BO_B200_I8_PAIR");
     const bool pairs = !(pe && atoi(pe) == 0) && h->sm_count >= 2;
+    if (!pairs && h->hyp.kind == BO_KERNEL_LINEAR_MATERN52)          // the one-CTA kernel has no per-candidate operand scale
+        return sweep_fp64_run(h, a_in, 0, true, vals_dev, idx_dev, nullptr, st);
     int grid;
     if (pairs) {
         const long long np2 = a.nblocks < h->sm_count / 2 ? a.nblocks : h->sm_count / 2;
@@ -709,6 +725,10 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
         if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
         else        i8_pack_linv_kernel<7><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
         BO_LAUNCH_CHECK(h);
+        if (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52) {
+            i8_xnorm_kernel<<<(h->n + 255) / 256, 256, 0, st>>>(h->Xs, h->n, h->hyp, h->guard_dev);
+            BO_LAUNCH_CHECK(h);
+        }
         BO_CUDA(h, cudaMemsetAsync(h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE), 0, (size_t)S * I8_A_SLICE, st));
         h->Lp8_epoch = h->factor_epoch; h->Lp8_S = S;
     }
@@ -717,10 +737,12 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     b.Lp8_zero = h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
     int e; frexp(a.hyp.outputscale, &e);                      // |k*| <= outputscale < 2^e
     b.dig_scale = ldexp(1.0, 6 + 7 * (S - 1) - e);
-    b.eb_scale = ldexp(1.0, e - 12);
+    b.eb_scale = ldexp(1.0, -12);
+    b.ss_scale = ldexp(1.0, 2 * e);
     const char* ng = getenv("BO_B200_I8_NO_GUARD");           // triage only: raw sliced values for every candidate
     const bool guard = !(ng && atoi(ng) == 1);
-    b.guard_scale = I8_GUARD_KAPPA / I8_GUARD_RTOL * ldexp(1.0, e - 7 * S);
+    // (linear + Matern kind: the pair kernel multiplies by the candidate's own eb instead of 2^e)
+    b.guard_scale = I8_GUARD_KAPPA / I8_GUARD_RTOL * ldexp(1.0, (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52 ? 0 : e) - 7 * S);
     b.guard_w = h->guard_dev;
     b.flag_idx = h->flag_idx; b.flag_count = guard ? h->flag_count_dev : nullptr; b.flag_cap = (long long)h->flag_cap;
     a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;

@@ -34,7 +34,8 @@ struct P8Smem {
     static constexpr int OFF_COL   = OFF_BAR + 256;                     // colsum[4][64]
     static constexpr int OFF_XCH   = OFF_COL + 4 * I8_BN * 8;           // xch[2][32]: partner's partial sums for my candidates
     static constexpr int OFF_MU    = OFF_XCH + 2 * P8_BH * 8;           // mu[2][4][32]: per panel buffer and row quarter
-    static constexpr int OFF_TKV   = OFF_MU + 8 * P8_BH * 8;
+    static constexpr int OFF_PRI   = OFF_MU + 8 * P8_BH * 8;            // pri[2][32] prior variance k(x*, x*), ebc[2][32] operand bound 2^e per candidate
+    static constexpr int OFF_TKV   = OFF_PRI + 4 * P8_BH * 8;
     static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;
     static constexpr int OFF_CMASK = OFF_ACQ + P8_BH * 8;
@@ -125,6 +126,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
     double* colsum  = reinterpret_cast<double*>(smem + SM::OFF_COL);
     double* xch     = reinterpret_cast<double*>(smem + SM::OFF_XCH);      // [2][32]
     double* mu_s    = reinterpret_cast<double*>(smem + SM::OFF_MU);       // [2][4][32]
+    double* pri_s   = reinterpret_cast<double*>(smem + SM::OFF_PRI);      // [2][32]
+    double* ebc_s   = pri_s + 2 * P8_BH;                                  // [2][32]
     double* tkv     = reinterpret_cast<double*>(smem + SM::OFF_TKV);
     long long* tki  = reinterpret_cast<long long*>(smem + SM::OFF_TKI);
     double* acq_s   = reinterpret_cast<double*>(smem + SM::OFF_ACQ);
@@ -190,7 +193,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 sobol_point<DP>(dirs, shift, a.d, a.first_index + li, xc[gi]);
             }
 #pragma unroll
-            for (int k = 0; k < DP; ++k) xc[gi][k] *= a.hyp.inv_ls[k];
+            for (int k = 0; k < DP; ++k) xc[gi][k] = __dmul_rn(xc[gi][k], a.hyp.inv_ls[k]);     // (never contracted into the differences below: every code instance must round alike)
+        }
+        // linear + Matern kind: k* = s2 (sum_k lin_w[k] x~*_k x~_jk + matern) is not bounded by the output scale; by
+        // Cauchy-Schwarz |k*_j| <= s2 (|x*|_w max_j |x_j|_w + 1) =: B, and the candidate's fixed-point scale is the power of
+        // two eb above B (its digits, its column of the accumulators and its guard all use that eb)
+        constexpr bool LIN = KIND == BO_KERNEL_LINEAR_MATERN52;
+        double xw[2][LIN ? DP : 1], dsc[2] = {b.dig_scale, b.dig_scale};
+        if (LIN) {
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                double nn = 0.0;
+#pragma unroll
+                for (int k = 0; k < DP; ++k) { xw[gi][k] = __dmul_rn(a.hyp.lin_w[k], xc[gi][k]); nn = fma(xw[gi][k], xc[gi][k], nn); }
+                const double bound = a.hyp.outputscale * (sqrt(nn * __ldg(b.guard_w + 1)) + 1.0);
+                const int ec = ((__double2hiint(bound) >> 20) & 0x7ff) - 1023 + 1;              // 2^ec > bound
+                dsc[gi] = __hiloint2double((1023 + 6 + 7 * (S - 1) - ec) << 20, 0);
+                if (quarter == 0 && q == 0) {
+                    pri_s[p * P8_BH + cgrp * 16 + gi * 8 + g] = a.hyp.outputscale * (nn + 1.0);
+                    ebc_s[p * P8_BH + cgrp * 16 + gi * 8 + g] = __hiloint2double((1023 + ec) << 20, 0);
+                }
+            }
         }
         double mu0 = 0.0, mu1 = 0.0;
         constexpr int XCH = SM::XCH, XP = DP + 2, XBUF = XCH * XP + XCH;
@@ -237,8 +260,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                     for (int gi = 0; gi < 2; ++gi) {
                         double sq = 0.0;
 #pragma unroll
-                        for (int k = 0; k < DP; ++k) { const double df = xc[gi][k] - x[k]; sq = fma(df, df, sq); }
-                        const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
+                        for (int k = 0; k < DP; ++k) { const double df = __dsub_rn(xc[gi][k], x[k]); sq = fma(df, df, sq); }
+                        double v = kernel_value_t<LIN ? BO_KERNEL_MATERN52 : KIND>(sq, a.hyp.outputscale);
+                        if (LIN) {
+                            double lin = 0.0;
+#pragma unroll
+                            for (int k = 0; k < DP; ++k) lin = fma(xw[gi][k], x[k], lin);
+                            v = fma(a.hyp.outputscale, lin, v);
+                        }
                         kv[gi][r] = (j < a.n) ? v : 0.0;
                     }
                     mu0 = fma(kv[0][r], al, mu0); mu1 = fma(kv[1][r], al, mu1);
@@ -257,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             int dg[S];
-                            i8_digits<S>(kv[gi][hh * 4 + e] * b.dig_scale, dg);
+                            i8_digits<S>(kv[gi][hh * 4 + e] * dsc[gi], dg);
 #pragma unroll
                             for (int s = 0; s < S; ++s) w[s] |= (uint32_t)(uint8_t)(int8_t)dg[s] << (8 * e);
                         }
@@ -472,9 +501,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
             if (tid < P8_BH) {
                 const long long li = blk * I8_BN + rank * P8_BH + tid;
                 const double other = xch[p * P8_BH + tid];
-                const double ss = rank == 0 ? mine + other : other + mine;     // (even row blocks) + (odd row blocks): one order for both CTAs
+                constexpr bool LIN = KIND == BO_KERNEL_LINEAR_MATERN52;
+                const double ebc = LIN ? ebc_s[p * P8_BH + tid] : 1.0;           // (stationary kinds: eb is folded into ss_scale / guard_scale)
+                const double prior = LIN ? pri_s[p * P8_BH + tid] : a.hyp.outputscale;
+                // (even row blocks) + (odd row blocks): one order for both CTAs; then the operand bound squared (a power of two)
+                const double ss = (rank == 0 ? mine + other : other + mine) * (LIN ? ebc * ebc : b.ss_scale);
                 const bool flagged = b.flag_count != nullptr && li < a.N &&
-                                     !(a.hyp.outputscale - ss >= b.guard_scale * sqrt(__ldg(b.guard_w) * ss));
+                                     !(prior - ss >= b.guard_scale * ebc * sqrt(__ldg(b.guard_w) * ss));
                 {
                     const unsigned fm = __ballot_sync(0xffffffffu, flagged);
                     if (fm) {
@@ -485,7 +518,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                         if (flagged && pos < b.flag_cap) b.flag_idx[pos] = li;
                     }
                 }
-                const double var = fmax(a.hyp.outputscale - ss, a.min_var);
+                const double var = fmax(prior - ss, a.min_var);
                 const double mean = a.hyp.mean + ((mu_s[(p * 4) * P8_BH + tid] + mu_s[(p * 4 + 1) * P8_BH + tid]) +
                                                   (mu_s[(p * 4 + 2) * P8_BH + tid] + mu_s[(p * 4 + 3) * P8_BH + tid]));
                 double v = acq_value(a.acq, mean, var, a.best_f, a.sqrt_beta);
@@ -573,5 +606,8 @@ template <int DP>
 static int launch_sweep_i8_pair(bo_handle* h, const SweepArgs& a, const SweepI8Args& b, int S, int grid, cudaStream_t st) {
     if (a.hyp.kind == BO_KERNEL_MATERN52)
         return S == 8 ? launch_sweep_i8_pair_k<DP, BO_KERNEL_MATERN52, 8>(h, a, b, grid, st) : launch_sweep_i8_pair_k<DP, BO_KERNEL_MATERN52, 7>(h, a, b, grid, st);
+    if (a.hyp.kind == BO_KERNEL_LINEAR_MATERN52)
+        return S == 8 ? launch_sweep_i8_pair_k<DP, BO_KERNEL_LINEAR_MATERN52, 8>(h, a, b, grid, st)
+                      : launch_sweep_i8_pair_k<DP, BO_KERNEL_LINEAR_MATERN52, 7>(h, a, b, grid, st);
     return S == 8 ? launch_sweep_i8_pair_k<DP, BO_KERNEL_RBF, 8>(h, a, b, grid, st) : launch_sweep_i8_pair_k<DP, BO_KERNEL_RBF, 7>(h, a, b, grid, st);
 }

@@ -234,8 +234,9 @@ int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, in
  * least 5e8 x that bound (slicing error <= 2e-9 relative) is re-scored on the FP64 DMMA contraction inside the same
  * call -- same outputs, same top-k order; bo_last_sweep_flagged() reports how many.  With 8 slices (what AUTO uses) that
  * is candidates with sigma^2 below ~1e-4 of the prior variance (next to training rows); with 7 slices (opt-in, 1.25x
- * faster per sliced candidate) the bound is 128x larger.  Eligible models: exact GP, Matern-5/2 or RBF kind, at least 256
- * (padded) observations; every other model runs the FP64 DMMA path in every mode.
+ * faster per sliced candidate) the bound is 128x larger.  Eligible models: exact GP of any kernel kind (the linear + Matern
+ * kind scales each candidate's operand by its own bound on |k*|) with at least 256 (padded) observations; SVGP handles run
+ * the FP64 DMMA path in every mode.
  * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
  * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates and models with fewer than 512
  * (padded) observations on the FP64 path.  bo_posterior / bo_posterior_multi stay on the FP64 contraction under AUTO

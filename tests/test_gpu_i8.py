@@ -126,7 +126,7 @@ def test_auto_mode_policy_and_sharded_resolution(engine):
     assert engine.resolve_sweep_mode(10**6) == "i8x7" and engine.resolve_sweep_mode(10) == "i8x7"   # pinned: the model decides
     engine.set_sweep_mode("auto")
     engine.fit(Xd, yd, "linear_matern52", 0.6, 1.0, 1e-3, linear_variance=0.3)
-    assert engine.resolve_sweep_mode(10**6) == "fp64"
+    assert engine.resolve_sweep_mode(10**6) == "i8x8"            # per-candidate operand scale (CTA-pair kernel)
     engine.fit(Xd[:100], yd[:100], "rbf", 0.6, 1.0, 1e-3)
     assert engine.resolve_sweep_mode(10**6) == "fp64"            # one stage of rows: not worth a pipeline
     engine.fit(Xd[:300], yd[:300], "rbf", 0.6, 1.0, 1e-3)        # 384 padded rows: AUTO waits for 512, a pinned mode does not

@@ -246,3 +246,39 @@ def test_per_dimension_linear_variance_exact_gp(engine):
     mu, var = engine.posterior(_cuda(xs[:100]))
     omu, ovar = o.posterior(gp3, xs[:100])
     assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+
+
+@pytest.mark.parametrize("mode,path", [("i8x8", 8), ("i8x7", 7), ("auto", 8)])
+def test_linear_matern_sliced_sweep_against_oracle(engine, mode, path):
+    """The reference's explicit kernel ScaleKernel(Linear + Matern) (Bayesian6.py:470-478) on the INT8-sliced tensor path: |k*|
+    is not bounded by the output scale, so every candidate carries its own power-of-two operand scale (Cauchy-Schwarz bound);
+    dense outputs and top-k against the oracle at the north-star tolerances, incl. a per-dimension linear variance."""
+    from bayesianoptimizer_b200 import sobol_state
+    n, d, N = 700, 5, 30_000
+    X, y = _problem(n, d, 13)
+    ls = np.array([0.5, 0.4, 0.6, 0.8, 0.7])
+    v = np.array([0.9, 0.05, 0.4, 1.7, 0.2])
+    gp = o.fit(X, y, LIN, ls, 1.3, 1e-3, mean=0.05, linear_variance=v)
+    engine.fit(_cuda(X), _cuda(y), "linear_matern52", ls, 1.3, 1e-3, mean=0.05, linear_variance=v)
+    engine.set_sweep_mode(mode)
+    try:
+        se = torch.quasirandom.SobolEngine(d, scramble=True, seed=4)
+        pts = o.sobol_points(se.sobolstate.numpy(), se.shift.numpy(), 0, N)
+        st = sobol_state(d, 4)
+        bf = float(y.max())
+        for acq, ak in (("ei", o.ACQ_EI), ("ucb", o.ACQ_UCB), ("var", o.ACQ_VAR)):
+            tv, ti, mu, var, av = o.sweep(gp, pts, ak, bf, 2.0, k=8)
+            vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, sobol=st, count=N, topk=8, return_all=True)
+            assert engine.last_sweep_path() == path
+            assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
+            if acq == "ei":
+                from conftest import assert_ei_close_conditioned
+                assert_ei_close_conditioned(acq, ga.cpu().numpy(), av, mu, var, bf)
+            else:
+                # (UCB = mu + sqrt(beta) sigma crosses zero inside a 30 000-candidate pool: relative to its two terms there)
+                np.testing.assert_allclose(ga.cpu().numpy(), av, rtol=1e-6, atol=1e-6 * 1e-3 if acq == "ucb" else 0)
+            got = idx.cpu().numpy()
+            for r in range(8):
+                assert got[r] == ti[r] or abs(av[got[r]] - tv[r]) <= 1e-6 * abs(tv[r])
+    finally:
+        engine.set_sweep_mode("auto")
