@@ -40,6 +40,7 @@ constexpr int I8_THREADS = 384;                // warpgroup 0 (warps 0-3): drain
 constexpr int I8_A_SLICE = SW_BM * I8_KC;      // 8 KB
 constexpr int I8_B_SLICE = I8_BN * I8_KC;      // 4 KB
 constexpr int I8_MIN_NP  = 256;                // below this the stage pipeline is all start-up (pinned modes fall back to FP64)
+constexpr int I8_PAIR_MIN_NP = 2048;           // from here up the CTA-pair kernel (sweep_i8_pair.cuh) is the faster one
 constexpr int I8_AUTO_MIN_NP = 512;            // AUTO: smallest padded n the sliced path was measured faster at
 
 template <int S, int DP>
@@ -701,8 +702,11 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
     a.nblocks = (a.N + I8_BN - 1) / I8_BN;
     // CTA pairs (cta_group::2, sweep_i8_pair.cuh) share one 64-candidate block; BO_B200_I8_PAIR=0 keeps the one-CTA kernel (triage / A-B)
+    // The pair kernel builds a block's panel BEFORE its MMAs (FP64 crawls under the INT8 tensor pipe), which pays once the MMA
+    // phase dominates; small models (few row blocks per candidate block) keep the one-CTA kernel, whose build overlaps the
+    // MMAs: n = 512: 121 M cand/s one-CTA vs 74 M pair; n = 1024: 49 vs 35; n = 4096: 3.8 vs 4.1 (profiles/r02_*).
     const char* pe = getenv("BO_B200_I8_PAIR");
-    const bool pairs = !(pe && atoi(pe) == 0) && h->sm_count >= 2;
+    const bool pairs = h->sm_count >= 2 && (pe ? atoi(pe) != 0 : (h->np >= I8_PAIR_MIN_NP || h->hyp.kind == BO_KERNEL_LINEAR_MATERN52));
     if (!pairs && h->hyp.kind == BO_KERNEL_LINEAR_MATERN52)          // the one-CTA kernel has no per-candidate operand scale
         return sweep_fp64_run(h, a_in, 0, true, vals_dev, idx_dev, nullptr, st);
     int grid;

@@ -216,3 +216,32 @@ def test_i8_peak_probe_reports_a_tensor_rate(engine):
     engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), "rbf", 0.5, 1.0, 1e-3)
     tops = engine.i8_peak_tops(0.2)
     assert 1000.0 < tops < 6000.0, tops          # B200 nominal dense INT8: 4500 TOP/s
+
+
+@pytest.mark.parametrize("variant", ["1", "0"])
+@pytest.mark.parametrize("n,d,N,kind,mode", [(512, 5, 4133, o.KERNEL_MATERN52, "i8x8"), (300, 16, 515, o.KERNEL_RBF, "i8x7"),
+                                             (129, 3, 1, o.KERNEL_RBF, "i8x8"), (2304, 6, 9000, o.KERNEL_MATERN52, "i8x8")])
+def test_both_sliced_kernels_on_ragged_shapes(engine, monkeypatch, n, d, N, kind, mode, variant):
+    """The library picks the CTA-pair kernel (cta_group::2) from 2048 padded observations up and the one-CTA kernel below;
+    BO_B200_I8_PAIR forces either one, so both are held to the oracle on ragged pools, odd row-block counts (129 -> 2 row
+    blocks, 300 -> 3, 2304 -> 18) and a single candidate -- and to each other's top-k."""
+    from bayesianoptimizer_b200 import sobol_state
+    monkeypatch.setenv("BO_B200_I8_PAIR", variant)
+    X, y = synth_problem(n, d, 41, 42)
+    ls = np.linspace(0.5, 0.9, d)
+    gp = o.fit(X, y, kind, ls, 1.2, 1e-3, mean=0.1)
+    engine.fit(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda(), _kname(kind), ls, 1.2, 1e-3, mean=0.1)
+    engine.set_sweep_mode(mode)
+    se = torch.quasirandom.SobolEngine(d, scramble=True, seed=5)
+    pts = o.sobol_points(se.sobolstate.numpy(), se.shift.numpy(), 77, N)
+    st = sobol_state(d, 5)
+    bf = float(y.max())
+    k = min(8, N)
+    tv, ti, mu, var, av = o.sweep(gp, pts, o.ACQ_UCB, bf, 2.0, k=k, first_index=77)
+    vals, idx, gm, gv, ga = engine.sweep("ucb", bf, 2.0, sobol=st, first_index=77, count=N, topk=k, return_all=True)
+    assert engine.last_sweep_path() == int(mode[-1])
+    assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
+    assert_acq_close("ucb", ga.cpu().numpy(), av)
+    got = idx.cpu().numpy()
+    for r in range(k):
+        assert got[r] == ti[r] or abs(av[got[r] - 77] - tv[r]) <= 1e-6 * abs(tv[r])
