@@ -5,7 +5,7 @@
 // (tools/i8_probe.cu).  Every row of L^-1 is scaled by a power of two to |x| < 1 and cut into S balanced radix-128
 // digits x ~= sum_s d_s 2^(-6-7s), d_s in [-64, 64]; the candidates' K(X, x*) columns likewise (fixed scale, the
 // kernel is bounded by the output scale).  Digit products are exact integers; products with equal s + t share one
-// INT32 accumulator (|sum| <= S * 64 * 64 * n < 2^31 for n <= 74 000); the S accumulators are recombined in FP64
+// INT32 accumulator (|sum| <= S * 64 * 64 * n < 2^31 for n < 65 536 at S = 8: the eligibility bound); the S accumulators are recombined in FP64
 // (Horner in 2^-7) when a 128-row block is complete, squared and summed per candidate.  Pairs with s + t >= S are
 // dropped: S (S + 1) / 2 products per FP64 multiply-add.  tools/ozaki_feasibility.py: S = 7 reproduces sigma^2 to
 // 6e-10 relative at the C3 shape (bar: 1e-8), S = 8 is indistinguishable from the FP64 product.
