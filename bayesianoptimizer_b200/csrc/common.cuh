@@ -257,6 +257,53 @@ __device__ __forceinline__ double exp_neg(double t) {
     return (t > 700.0) ? 0.0 : r;
 }
 
+// ---- leaner variants for the sliced sweep's panel build, where every FP64 instruction is paid for with tensor-pipe idle
+// time (FP64 and kind::i8 MMAs throttle each other: DESIGN section 4).  Same accuracy class (~1.5 ulp), 9 FP64 instructions
+// fewer per kernel evaluation: one Newton step less in the square root (rsqrt.approx 2^-22 -> 2^-43 -> Heron ~2^-86), exp
+// through a 16-entry table of 2^(j/16) (shared memory, conflict-free) + a degree-7 polynomial on |f| <= ln2/32 (remainder
+// 1e-18), the output scale folded into the Matern polynomial.
+__device__ __forceinline__ double sqrt_pos_fast(double x) {
+    const double xs = x + 1e-300;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    y = y * fma(-0.5 * xs, y * y, 1.5);
+    const double r = xs * y;
+    return fma(0.5 * y, fma(-r, r, xs), r);
+}
+// EXP2_16[j] = 2^(j/16), correctly rounded
+#define BO_EXP2_16_TABLE {1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484, \
+                          1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407, \
+                          1.6104903319492543, 1.681792830507429, 1.7562521603732995, 1.8340080864093424, 1.9152065613971474}
+__device__ __forceinline__ double exp_neg_fast(double t, const double* __restrict__ tab /* shared: 2^(j/16) */) {
+    const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52
+    const double z = fma(-t, 23.083120654223414, MAGIC);            // n = rint(-t * 16 log2(e)) in the low word
+    const int n = __double2loint(z);
+    const double nf = z - MAGIC;
+    double f = fma(nf, -4.33216987730702385306e-02, -t);            // f = -t - n ln2/16 (Cody-Waite: hi part has 32 significant bits)
+    f = fma(nf, -1.19263433079411731251e-11, f);                    //                     (lo part)
+    double p = 1.98412698412698413e-04;                             // Taylor of exp(f), |f| <= ln2/32, degree 7
+    p = fma(p, f, 1.38888888888888894e-03);
+    p = fma(p, f, 8.33333333333333322e-03);
+    p = fma(p, f, 4.16666666666666644e-02);
+    p = fma(p, f, 1.66666666666666657e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    p *= tab[n & 15];                                               // 2^((n mod 16)/16)
+    const double r = __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));   // * 2^floor(n/16), in [-1010, 0]
+    return (t > 700.0) ? 0.0 : r;
+}
+template <int KIND>
+__device__ __forceinline__ double kernel_value_fast_t(double sq, double outputscale, const double* __restrict__ tab) {
+    if (KIND == BO_KERNEL_MATERN52) {
+        const double s5 = 2.23606797749978969640917366873128;
+        const double r = sqrt_pos_fast(sq);
+        const double p = fma(sq, outputscale * (5.0 / 3.0), fma(outputscale * s5, r, outputscale));     // s2 (1 + sqrt5 r + 5/3 r^2): loop-invariant constants
+        return p * exp_neg_fast(s5 * r, tab);
+    }
+    return outputscale * exp_neg_fast(0.5 * sq, tab);
+}
+
 // Matern-5/2 / RBF value from the scaled squared distance (KIND known at compile time)
 template <int KIND>
 __device__ __forceinline__ double kernel_value_t(double sq, double outputscale) {

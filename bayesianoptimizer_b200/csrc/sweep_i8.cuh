@@ -102,6 +102,36 @@ __device__ __forceinline__ void i8_digits(double xs, int* d) {
     d[0] = (int)v;
 }
 
+// Digits of FOUR fixed-point values at once, packed one 32-bit word (4 consecutive k) per slice: what the panel builders
+// store.  Adding the bias sum_{k < S-1} 64 * 128^k turns the balanced digits into plain bit fields: v + bias =
+// sum_k (d_k + 64) 128^k with d_k in [-64, 63] for k < S - 1 and the signed top digit d_{S-1} in [-64, 64] -- an exact
+// decomposition of the same integer v as i8_digits' (|digit| <= 64, so the INT32 accumulator bound is unchanged), but the
+// fields come out with one shift + mask each and the "- 64" is applied to four packed bytes at once
+// (b - 64 in two's complement = flip bit 6, copy the new bit 6 into bit 7).  ~28 integer instructions per value instead
+// of ~75 for the residual recursion: the build is bound by the integer pipe as much as by FP64
+// (79 integer + 55 FP64 instructions per kernel evaluation before this).
+template <int S>
+__device__ __forceinline__ void i8_digit_words(const long long (&v)[4], uint32_t (&w)[S]) {
+    unsigned long long bias = 0;
+#pragma unroll
+    for (int k = 0; k < S - 1; ++k) bias += 64ull << (7 * k);
+    unsigned long long u[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) u[e] = (unsigned long long)v[e] + bias;
+#pragma unroll
+    for (int k = 0; k < S - 1; ++k) {
+        uint32_t W = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) W |= ((uint32_t)(u[e] >> (7 * k)) & 127u) << (8 * e);
+        const uint32_t T = W ^ 0x40404040u;
+        w[S - 1 - k] = T | ((T & 0x40404040u) << 1);
+    }
+    uint32_t W = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) W |= ((uint32_t)((long long)u[e] >> (7 * (S - 1))) & 255u) << (8 * e);
+    w[0] = W;
+}
+
 // bounded mbarrier wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.  The bound is ~1 minute of
 // SM cycles: the longest legitimate wait is one row block of MMAs (milliseconds), but the context may be time-sliced with
 // another one on the same GPU (the reference runs its Taichi simulator there) and the cycle counter keeps running meanwhile.
@@ -362,15 +392,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             uint32_t w[S];
+                            long long v4[4];
 #pragma unroll
-                            for (int s = 0; s < S; ++s) w[s] = 0;
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                int dg[S];
-                                i8_digits<S>(kv[gi][hh * 4 + e] * b.dig_scale, dg);
-#pragma unroll
-                                for (int s = 0; s < S; ++s) w[s] |= (uint32_t)(uint8_t)(int8_t)dg[s] << (8 * e);
-                            }
+                            for (int e = 0; e < 4; ++e) v4[e] = __double2ll_rn(kv[gi][hh * 4 + e] * b.dig_scale);
+                            i8_digit_words<S>(v4, w);
                             const size_t off = ((size_t)(wb + 4 * gi) * (I8_KC / 16) + ch0 + hh) * 128 + g * 16 + q * 4;
 #pragma unroll
                             for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t*>(st_tile + (size_t)s * I8_B_SLICE + off) = w[s];

@@ -35,7 +35,8 @@ struct P8Smem {
     static constexpr int OFF_XCH   = OFF_COL + 4 * I8_BN * 8;           // xch[2][32]: partner's partial sums for my candidates
     static constexpr int OFF_MU    = OFF_XCH + 2 * P8_BH * 8;           // mu[2][4][32]: per panel buffer and row quarter
     static constexpr int OFF_PRI   = OFF_MU + 8 * P8_BH * 8;            // pri[2][32] prior variance k(x*, x*), ebc[2][32] operand bound 2^e per candidate
-    static constexpr int OFF_TKV   = OFF_PRI + 4 * P8_BH * 8;
+    static constexpr int OFF_TAB   = OFF_PRI + 4 * P8_BH * 8;           // 2^(j/16), j < 16 (exp_neg_fast)
+    static constexpr int OFF_TKV   = OFF_TAB + 16 * 8;
     static constexpr int OFF_TKI   = OFF_TKV + BO_MAX_TOPK * 8;
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;
     static constexpr int OFF_CMASK = OFF_ACQ + P8_BH * 8;
@@ -73,10 +74,15 @@ __device__ __forceinline__ bool p8_try_wait(uint64_t* bar, uint32_t parity) {   
 #ifndef BO_I8_WAIT_CYCLES
 #define BO_I8_WAIT_CYCLES 100000000000LL
 #endif
+// CLUSTER = true: cluster-scope acquire (the waiter goes on to read data another CTA stored: the DSMEM exchange; ptxas
+// follows every such try_wait with CCTL.IVALL, an L1 invalidate -- 21.8 M of them per 4 ms in the first version, when every
+// wait was cluster-scope).  CLUSTER = false: the usual CTA-scope wait for barriers completed by TMA, tcgen05.commit or this
+// CTA's own threads (what CUTLASS's 2-SM kernels use for the same barriers).
+template <bool CLUSTER = false>
 __device__ __forceinline__ void p8_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     for (uint32_t spin = 0;; ++spin) {
-        if (p8_try_wait(bar, parity)) return;
+        if (CLUSTER ? p8_try_wait(bar, parity) : mbar_try_wait(bar, parity)) return;
         if ((spin & 1023u) == 1023u && clock64() - t0 > BO_I8_WAIT_CYCLES) {
             printf("sweep_i8_pair_kernel: mbarrier wait timed out (block %d thread %d barrier +%d parity %u)\n", blockIdx.x, threadIdx.x,
                    (int)(smem_u32(bar) & 0x7f), parity);
@@ -128,6 +134,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
     double* mu_s    = reinterpret_cast<double*>(smem + SM::OFF_MU);       // [2][4][32]
     double* pri_s   = reinterpret_cast<double*>(smem + SM::OFF_PRI);      // [2][32]
     double* ebc_s   = pri_s + 2 * P8_BH;                                  // [2][32]
+    double* exp_tab = reinterpret_cast<double*>(smem + SM::OFF_TAB);
     double* tkv     = reinterpret_cast<double*>(smem + SM::OFF_TKV);
     long long* tki  = reinterpret_cast<long long*>(smem + SM::OFF_TKI);
     double* acq_s   = reinterpret_cast<double*>(smem + SM::OFF_ACQ);
@@ -157,6 +164,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     if (tid < BO_MAX_TOPK) { tkv[tid] = -INFINITY; tki[tid] = IDX_EMPTY; }
+    if (tid >= 64 && tid < 80) { const double t16[16] = BO_EXP2_16_TABLE; exp_tab[tid - 64] = t16[tid - 64]; }
     if (a.sobol) {
         for (int e = tid; e < DP * BO_SOBOL_BITS; e += I8_THREADS)
             dirs[e] = a.sobol->direction[e / BO_SOBOL_BITS][e % BO_SOBOL_BITS];
@@ -261,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                         double sq = 0.0;
 #pragma unroll
                         for (int k = 0; k < DP; ++k) { const double df = __dsub_rn(xc[gi][k], x[k]); sq = fma(df, df, sq); }
-                        double v = kernel_value_t<LIN ? BO_KERNEL_MATERN52 : KIND>(sq, a.hyp.outputscale);
+                        double v = kernel_value_fast_t<LIN ? BO_KERNEL_MATERN52 : KIND>(sq, a.hyp.outputscale, exp_tab);
                         if (LIN) {
                             double lin = 0.0;
 #pragma unroll
@@ -281,15 +289,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                         int8_t* st_tile = panel + (size_t)(jj / I8_KC) * B_STAGE;
                         const int ch = (jj % I8_KC) / 16;
                         uint32_t w[S];
+                        long long v4[4];
 #pragma unroll
-                        for (int s = 0; s < S; ++s) w[s] = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            int dg[S];
-                            i8_digits<S>(kv[gi][hh * 4 + e] * dsc[gi], dg);
-#pragma unroll
-                            for (int s = 0; s < S; ++s) w[s] |= (uint32_t)(uint8_t)(int8_t)dg[s] << (8 * e);
-                        }
+                        for (int e = 0; e < 4; ++e) v4[e] = __double2ll_rn(kv[gi][hh * 4 + e] * dsc[gi]);
+                        i8_digit_words<S>(v4, w);
                         const size_t off = ((size_t)(cgrp * 2 + gi) * (I8_KC / 16) + ch) * 128 + g * 16 + q * 4;
 #pragma unroll
                         for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t*>(st_tile + (size_t)s * P8_B_SLICE + off) = w[s];
@@ -374,7 +377,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 const bool leader = i8_elect();
                 for (int ibp = 0; ibp < nbp; ++ibp, ++rb) {
                     const long long w1 = prof ? clock64() : 0;
-                    p8_wait(tempty, (rb & 1) ^ 1);             // both CTAs have drained the previous row-block pair
+                    p8_wait<true>(tempty, (rb & 1) ^ 1);       // both CTAs have drained the previous row-block pair
                     if (prof) t_w1 += clock64() - w1;
                     tc_fence_after();
                     const int nkc = (2 * ibp + 2) * KCH;
@@ -494,7 +497,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 mine = (colsum[cm] + colsum[I8_BN + cm]) + (colsum[2 * I8_BN + cm] + colsum[3 * I8_BN + cm]);
                 p8_st_remote_f64(p8_mapa(&xch[p * P8_BH + tid], 1 - rank), theirs);
                 p8_arrive_remote(p8_mapa(&xfull[p], 1 - rank));           // release.cluster: orders this thread's store before it
-                p8_wait(&xfull[p], (it >> 1) & 1);
+                p8_wait<true>(&xfull[p], (it >> 1) & 1);
                 p8_wait(&pfull[p], (it >> 1) & 1);                        // acquire: mu_s[p] of this CTA's builders
             }
             // ================= epilogue: variance, acquisition, CTA-local top-k (32 candidates) =====================
