@@ -10,7 +10,9 @@
 // (16 row-block pairs instead of 32 row blocks), and the builders' FP64 work per SM and block halves.
 //
 // Roles per CTA (384 threads, as in the one-CTA kernel): warps 0-3 drain + epilogue, warp 4 TMA producer, warp 5 MMA issuer
-// (rank 0 only), warps 8-11 panel builders.  Cross-CTA protocol (all cluster-scope release/acquire):
+// (rank 0 only), warps 8-11 panel builders.  The panel of block j + 1 is built BEFORE the MMAs of block j start, by the drain
+// and builder groups together (8 warps): FP64 instructions and kind::i8 MMAs throttle each other (tools/i8_probe2.cu,
+// interference runs), so building underneath the MMAs cost both sides more than taking turns does.  Cross-CTA protocol (all cluster-scope release/acquire):
 //   full[s]      leader only: the stage tiles of BOTH CTAs (each its own row block of L^-1 + its own panel half, in its own
 //                shared memory) have landed -- the copies are 2-D tensor TMA loads with .cta_group::2, whose completion may be
 //                signalled on the partner's barrier (plain cp.async.bulk cannot: with the leader's barrier as operand the copy

@@ -369,7 +369,9 @@ def sweep_roofline(eng, cfg, name, mode, count, kms, n_obs, side=None):
     a_tops = count * ops / (kms * 1e-3) * 1e-12
     return {"bound": "tensor", "achieved": a_tops, "peak": peak_tops, "unit": "TOP/s", "frac": a_tops / peak_tops,
             "traffic": traffic, "traffic_source": tsrc,
-            "kernel": f"sweep_i8_kernel<{cfg['d']}, matern52, {slices}> (tcgen05.mma kind::i8 with A-collector reuse, INT32 accumulators in TMEM)",
+            "kernel": (f"sweep_i8_pair_kernel<{cfg['d']}, matern52, {slices}> (tcgen05.mma.cta_group::2 kind::i8, M=256 over a CTA pair, A-collector reuse, "
+                       f"INT32 accumulators in TMEM)" if (n_obs + 127) // 128 * 128 >= 2048 else
+                       f"sweep_i8_kernel<{cfg['d']}, matern52, {slices}> (tcgen05.mma kind::i8 with A-collector reuse, INT32 accumulators in TMEM)"),
             "peak_source": "INT8 tensor-pipe peak measured live by bo_i8_peak (tcgen05.mma kind::i8 128x256x32 on resident operands, "
                            "0.5 s burst); MEASURED_PEAKS.json has no INT8 entry",
             "peak_sustained": peak_sus, "frac_of_sustained_peak": a_tops / peak_sus,
