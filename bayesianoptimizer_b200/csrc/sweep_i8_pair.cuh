@@ -80,11 +80,15 @@ __device__ __forceinline__ bool p8_try_wait(uint64_t* bar, uint32_t parity) {   
 // follows every such try_wait with CCTL.IVALL, an L1 invalidate -- 21.8 M of them per 4 ms in the first version, when every
 // wait was cluster-scope).  CLUSTER = false: the usual CTA-scope wait for barriers completed by TMA, tcgen05.commit or this
 // CTA's own threads (what CUTLASS's 2-SM kernels use for the same barriers).
-template <bool CLUSTER = false>
+// NAP > 0: nanoseconds to sleep between polls -- for waits that last most of a block and are not on the critical path (the
+// builder group waiting for its panel buffer, the drain warps waiting for the next accumulators): a polling warp still
+// issues, and the step is power-bound.
+template <bool CLUSTER = false, int NAP = 0>
 __device__ __forceinline__ void p8_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     for (uint32_t spin = 0;; ++spin) {
         if (CLUSTER ? p8_try_wait(bar, parity) : mbar_try_wait(bar, parity)) return;
+        if (NAP > 0) __nanosleep(NAP);
         if ((spin & 1023u) == 1023u && clock64() - t0 > BO_I8_WAIT_CYCLES) {
             printf("sweep_i8_pair_kernel: mbarrier wait timed out (block %d thread %d barrier +%d parity %u)\n", blockIdx.x, threadIdx.x,
                    (int)(smem_u32(bar) & 0x7f), parity);
@@ -319,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
         int j = 0;
         for (long long blk = pair; blk < a.nblocks; blk += npairs, ++j) {
-            p8_wait(&pempty[j & 1], ((j >> 1) & 1) ^ 1);      // the block that used this buffer two turns ago is done (epilogue)
+            p8_wait<false, 500>(&pempty[j & 1], ((j >> 1) & 1) ^ 1);      // the block that used this buffer two turns ago is done (epilogue)
             build(blk, j, 4 + (warp - 8));
         }
     } else if (warp >= 4) {
@@ -444,7 +448,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 for (int ibp = 0; ibp < nbp; ++ibp, ++rb) {
                     const int ib = 2 * ibp + (int)rank;
                     const double rs = ib < nbm ? b.rowscale[ib * SW_BM + tid] * b.eb_scale : 0.0;
-                    p8_wait(tfull, rb & 1);
+                    p8_wait<false, 100>(tfull, rb & 1);
                     tc_fence_after();
                     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
