@@ -547,23 +547,25 @@ def bench_c4(ctx, name, cfg):
     eng.set_sweep_mode(mode)
     kms = []
 
-    def pick(host):
+    def pick(host, solo=False):
+        """solo: this rank alone sweeps the whole pool (rank 0's side measurements: no collective may be called there)."""
+        f0, c0 = (0, pool) if solo else (first, count)
         if host:
-            v, i = eng.sweep_host("logei", best_f, 2.0, sobol=sob, first_index=first, count=count, topk=TOPK)
+            v, i = eng.sweep_host("logei", best_f, 2.0, sobol=sob, first_index=f0, count=c0, topk=TOPK)
             v, i = v.to(dev), i.to(dev)
         else:
-            v, i = eng.sweep("logei", best_f, 2.0, sobol=sob, first_index=first, count=count, topk=TOPK)
+            v, i = eng.sweep("logei", best_f, 2.0, sobol=sob, first_index=f0, count=c0, topk=TOPK)
         kms.append(eng.last_sweep_ms())
-        if world > 1:
+        if world > 1 and not solo:
             v, i = allgather_topk(v, i, TOPK)
         x = eng.sobol_points(sob, i[:1])
         if host:
             x = x.cpu().to(dev)                       # the pick crosses to the host (the caller logs it) and comes back
         eng.append(x[0])
 
-    def batch(host=False):
+    def batch(host=False, solo=False):
         for _ in range(q):
-            pick(host)
+            pick(host, solo)
 
     for _ in range(ctx.W):
         fit(Xd, yd)
@@ -625,7 +627,7 @@ def bench_c4(ctx, name, cfg):
         # one q=16 batch that crosses n = 8192 (re-sweeps at the configured pool)
         eng.set_sweep_mode(mode)
         t0 = time.perf_counter()
-        batch()
+        batch(solo=True)
         torch.cuda.synchronize()
         batch_8k_ms = (time.perf_counter() - t0) * 1e3
 
@@ -648,7 +650,7 @@ def bench_c4(ctx, name, cfg):
                     "includes": "bo_fit_host at n=4096 (H2D X,y + refit) + 16 x (bo_sweep_host + D2H winner + pick D2H/H2D + bo_append)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "per_pick_ms": ms_per_step / q, "sweep_kernel_ms": sweep_kms,
-            "append": appends, "batch_crossing_8192_ms": batch_8k_ms,
+            "append": appends, "batch_crossing_8192_ms_one_gpu": batch_8k_ms,
         }
         if not args.no_cpu_baseline and world == 1:
             r = cpu_c4_run(cfg)
