@@ -2,8 +2,8 @@
 // slices on the INT8 tensor path (tcgen05.mma kind::i8, INT32 accumulators in TMEM) -- included by sweep.cu.
 //
 // Why: the FP64 sweep (sweep_kernel) sits at 0.95 of the DMMA roof (37 TFLOP/s); INT8 tcgen05 runs at 4.4 POP/s
-// (tools/i8_probe.cu).  Every row of L^-1 is scaled by a power of two to |x| < 1 and cut into S balanced radix-128
-// digits x ~= sum_s d_s 2^(-6-7s), d_s in [-64, 64]; the candidates' K(X, x*) columns likewise (fixed scale, the
+// (tools/i8_probe.cu).  Every row of L^-1 is scaled by a power of two to |x| < 1 and cut into S balanced digits (I8Dig:
+// eight 7-bit ones, or one 7-bit + six 8-bit ones); the candidates' K(X, x*) columns likewise (fixed scale, the
 // kernel is bounded by the output scale).  Digit products are exact integers; products with equal s + t share one
 // INT32 accumulator (|sum| <= S * 64 * 64 * n < 2^31 for n < 65 536 at S = 8: the eligibility bound); the S accumulators are recombined in FP64
 // (Horner in 2^-7) when a 128-row block is complete, squared and summed per candidate.  Pairs with s + t >= S are
@@ -77,29 +77,48 @@ struct SweepI8Args {
     long long* flag_idx; int* flag_count; long long flag_cap;
 };
 
-// Slicing error of ||u||^2 (what the guard bounds).  Row i of L^-1 is cut at 2^(-7 S) of its power-of-two scale and the
-// products of slices s + t >= S are dropped: per element product an error of about 2^(-7 S) rowscale_i eb with random sign
-// (eb: the power-of-two bound of |k*|), (S - 1) dropped pairs of rms 1/3 each, i + 1 products per row:
-//     delta u_i ~ 2^(-7 S) eb rowscale_i sqrt((S - 1)(i + 1)) / 3,      delta ||u||^2 = 2 sum_i u_i delta u_i
-//     rms(delta ||u||^2) <= 2 sqrt(S - 1) / 3  2^(-7 S) eb sqrt(W ||u||^2)        (< 1.8 x that expression for S <= 8).
+// Slicing error of ||u||^2 (what the guard bounds).  The products of slices s + t >= S are dropped: per element product an
+// error of about 2^GEXP rowscale_i eb with random sign (eb: the power-of-two bound of |k*|; GEXP = 2 W - 14 - W S from the digit
+// geometry I8Dig: -56 for eight 7-bit slices, -54 for one 7-bit + six 8-bit ones), (S - 1) dropped pairs of rms 1/3 each,
+// i + 1 products per row:
+//     delta u_i ~ 2^GEXP eb rowscale_i sqrt((S - 1)(i + 1)) / 3,      delta ||u||^2 = 2 sum_i u_i delta u_i
+//     rms(delta ||u||^2) <= 2 sqrt(S - 1) / 3  2^GEXP eb sqrt(W ||u||^2)          (< 1.8 x that expression for S <= 8).
 // tools/ozaki_guard_study.py measures the true 7- and 8-slice errors on the reference's CSV rows against it.  A candidate is
 // flagged when I8_GUARD_KAPPA times the expression exceeds I8_GUARD_RTOL of its variance: unflagged candidates carry a slicing
 // error below 2e-9 relative (4.5 sigma), a fifth of the 1e-8 bar, on top of the FP64 recombination's own rounding.
 constexpr double I8_GUARD_KAPPA = 8.0;
 constexpr double I8_GUARD_RTOL  = 2e-9;
 
-// S balanced radix-128 digits of x (|x| <= 1): x ~= sum_s d[s] 2^(-6-7s), rounding only in the last place.
-// xs = x * 2^(6 + 7 (S - 1)) (an exact scaling, folded into the caller's power-of-two scale).
+// Digit geometry.  An operand value x (|x| <= 1) becomes the integer v = rint(x 2^F) and is cut into S signed digits:
+// a 7-bit top digit d[0] in [-64, 64] and S - 1 lower digits of W bits each, balanced ([-2^(W-1), 2^(W-1) - 1]):
+//     x ~= d[0] 2^-6 + sum_{s >= 1} d[s] 2^(-6 - W s),      F = 6 + W (S - 1).
+//   S = 8: W = 7 -> F = 55: eight 7-bit slices, 36 slice products per multiply-add (BO_SWEEP_I8X8);
+//   S = 7: W = 8 -> F = 54: one 7-bit + six 8-bit slices, 28 products (BO_SWEEP_I8X7).  One bit less than the 8-slice form,
+//          a 3.3x larger slicing error of ||u||^2 on the reference's CSV rows (CPU emulation: 2.6e-14 / 1.2e-14 / 4.4e-14
+//          absolute at n = 512 / 512 / 3000 against 8.3e-15 / 3.1e-15 / 1.3e-14, FP64 BLAS 4.8e-15 / 3.7e-15 / 1.4e-14;
+//          seven 7-BIT slices: 1.3e-12) -- for 22 % fewer MMAs.  INT32 accumulators: |sum| <= 7 * 128^2 * np < 2^31 up
+//          to np = 16 384 (8 * 64^2 * np < 2^31 up to 65 535 for S = 8).
+template <int S> struct I8Dig {
+    static constexpr int W = (S == 7) ? 8 : 7;
+    static constexpr int F = 6 + W * (S - 1);
+    static constexpr int NP_MAX = (S == 7) ? 16384 : 65535;
+    static constexpr double HORNER = (S == 7) ? 0.00390625 : 0.0078125;        // 2^-W: one accumulator group down
+    // slicing-error scale of one element product: sqrt(S-1)/3 * 2^GEXP (dropped pairs s + t >= S: (S-1) products of two
+    // digits of rms 2^(W-1)/sqrt(3) at weight 2^(-12 - W S)); GEXP = 2 W - 14 - W S  (= -7 S for W = 7)
+    static constexpr int GEXP = 2 * W - 14 - W * S;
+};
+// the S digits of xs = x 2^F as plain bit fields: adding the bias sum_{k < S-1} 2^(W-1) 2^(W k) turns the balanced lower
+// digits into the W-bit fields of one 64-bit integer (an exact decomposition: v = sum_k d_k 2^(W k))
 template <int S>
 __device__ __forceinline__ void i8_digits(double xs, int* d) {
-    long long v = __double2ll_rn(xs);
+    constexpr int W = I8Dig<S>::W;
+    unsigned long long bias = 0;
 #pragma unroll
-    for (int s = S - 1; s > 0; --s) {
-        const int dg = (int)((v + 64) & 127) - 64;
-        d[s] = dg;
-        v = (v - dg) >> 7;
-    }
-    d[0] = (int)v;
+    for (int k = 0; k < S - 1; ++k) bias += (1ull << (W - 1)) << (W * k);
+    const unsigned long long u = (unsigned long long)__double2ll_rn(xs) + bias;
+#pragma unroll
+    for (int k = 0; k < S - 1; ++k) d[S - 1 - k] = (int)((u >> (W * k)) & ((1u << W) - 1u)) - (1 << (W - 1));
+    d[0] = (int)((long long)u >> (W * (S - 1)));
 }
 
 // Digits of FOUR fixed-point values at once, packed one 32-bit word (4 consecutive k) per slice: what the panel builders
@@ -112,24 +131,29 @@ __device__ __forceinline__ void i8_digits(double xs, int* d) {
 // (79 integer + 55 FP64 instructions per kernel evaluation before this).
 template <int S>
 __device__ __forceinline__ void i8_digit_words(const long long (&v)[4], uint32_t (&w)[S]) {
+    constexpr int W = I8Dig<S>::W;
     unsigned long long bias = 0;
 #pragma unroll
-    for (int k = 0; k < S - 1; ++k) bias += 64ull << (7 * k);
+    for (int k = 0; k < S - 1; ++k) bias += (1ull << (W - 1)) << (W * k);
     unsigned long long u[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) u[e] = (unsigned long long)v[e] + bias;
 #pragma unroll
     for (int k = 0; k < S - 1; ++k) {
-        uint32_t W = 0;
+        uint32_t P = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) W |= ((uint32_t)(u[e] >> (7 * k)) & 127u) << (8 * e);
-        const uint32_t T = W ^ 0x40404040u;
-        w[S - 1 - k] = T | ((T & 0x40404040u) << 1);
+        for (int e = 0; e < 4; ++e) P |= ((uint32_t)(u[e] >> (W * k)) & ((1u << W) - 1u)) << (8 * e);
+        if (W == 8) {
+            w[S - 1 - k] = P ^ 0x80808080u;                       // b - 128 in two's complement: flip bit 7
+        } else {
+            const uint32_t T = P ^ 0x40404040u;                   // b - 64: flip bit 6, copy the new bit 6 into bit 7
+            w[S - 1 - k] = T | ((T & 0x40404040u) << 1);
+        }
     }
-    uint32_t W = 0;
+    uint32_t P = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) W |= ((uint32_t)((long long)u[e] >> (7 * (S - 1))) & 255u) << (8 * e);
-    w[0] = W;
+    for (int e = 0; e < 4; ++e) P |= ((uint32_t)((long long)u[e] >> (W * (S - 1))) & 255u) << (8 * e);
+    w[0] = P;
 }
 
 // bounded mbarrier wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.  The bound is ~1 minute of
@@ -232,7 +256,7 @@ __global__ void __launch_bounds__(256) i8_pack_linv_kernel(const double* __restr
     for (int e = threadIdx.x; e < SW_BM * (I8_KC / 16); e += 256) {
         const int r = e / (I8_KC / 16), ch = e % (I8_KC / 16);
         const int i = ib * SW_BM + r, j0 = kc * I8_KC + ch * 16;
-        const double inv = ldexp(1.0, 6 + 7 * (S - 1)) / rowscale[i];      // exact: both are powers of two
+        const double inv = ldexp(1.0, I8Dig<S>::F) / rowscale[i];          // exact: both are powers of two
         uint32_t w[S][4];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -540,7 +564,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                         for (int j = 0; j < 8; ++j) {
                             double t = i8_s32_to_f64(v[S - 1][j]);
 #pragma unroll
-                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, i8_s32_to_f64(v[gq][j]));
+                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, I8Dig<S>::HORNER, i8_s32_to_f64(v[gq][j]));
                             const double u = t * rs;
                             acc[c0 + j] = fma(u, u, acc[c0 + j]);
                         }
@@ -643,13 +667,13 @@ static bool sweep_i8_model_ok(const bo_handle* h) {
     return h->fitted && !h->svgp && h->np >= I8_MIN_NP && h->np < 65536;
 }
 
-// Slice count of AUTO.  8 slices reproduce the FP64 product to within ~2x its own rounding error on everything the
-// emulation (tools/ozaki_feasibility.py, tests/test_sliced_numerics.py) was run on, including the reference's CSV rows
-// with duplicate and clustered points at the 1e-4 noise floor; the guard then only flags candidates with sigma^2 below
-// ~1e-4 of the prior variance.  7 slices are 1.25x faster, but their error bound is 128x larger, so the guard sends
-// every candidate with sigma^2 below a few percent of the prior variance to the FP64 pass -- a win only for pools that
-// stay away from the data: opt-in (BO_SWEEP_I8X7).
-static int sweep_i8_slices(const Hyper&) { return 8; }
+// Slice count of AUTO.  Both sliced forms carry the per-candidate accuracy guard, so both deliver the same guarantee
+// (slicing error of an unflagged candidate <= 2e-9 relative); they differ in how many candidates the guard sends to the FP64
+// pass and in cost.  Seven slices with 8-bit lower digits (54-bit operands, 28 products) have a 4x larger bound than eight
+// 7-bit slices (55 bits, 36 products): on the reference's CSV rows that is a few hundred more re-scored candidates out of
+// 20 000, on pools that stay off the data none -- for 22 % fewer MMAs on a power-bound kernel.  AUTO takes the 7-slice form
+// wherever its INT32 accumulators cannot overflow (np <= 16 384) and the 8-slice form above.
+static int sweep_i8_slices(const bo_handle* h) { return h->np <= I8Dig<7>::NP_MAX ? 7 : 8; }
 
 // The pinned mode a sweep over a pool of `pool` candidates runs in.  Pinned modes depend on the model only, so every
 // shard of a pool takes the same path and the per-candidate values are bit-identical for every shard layout; AUTO also
@@ -657,13 +681,14 @@ static int sweep_i8_slices(const Hyper&) { return 8; }
 // 64-candidate blocks) -- callers that shard a pool resolve AUTO once on the global size (bo_resolve_sweep_mode).
 int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
     if (mode == BO_SWEEP_FP64 || !sweep_i8_model_ok(h)) return BO_SWEEP_FP64;
-    if (mode == BO_SWEEP_I8X7 || mode == BO_SWEEP_I8X8) return mode;
+    if (mode == BO_SWEEP_I8X7) return h->np <= I8Dig<7>::NP_MAX ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;      // accumulator bound
+    if (mode == BO_SWEEP_I8X8) return mode;
     if ((pool + I8_BN - 1) / I8_BN < 2LL * h->sm_count) return BO_SWEEP_FP64;
     if (h->np < I8_AUTO_MIN_NP) return BO_SWEEP_FP64;     // measured gain starts at n = 512 (1.33x); below it was not measured
     // no hyper-parameter heuristic: every sliced sweep carries the per-candidate accuracy guard (I8_GUARD_*), which sends
     // the candidates the slicing error could matter for -- sigma^2 orders of magnitude below the prior variance, next to
     // training rows -- through the FP64 contraction
-    return sweep_i8_slices(h->hyp) == 7 ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;
+    return sweep_i8_slices(h) == 7 ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;
 }
 
 template <int S>
@@ -765,13 +790,14 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     b.Lp8 = h->Lp8; b.rowscale = h->rowscale; b.panel8 = h->panel8;
     b.Lp8_zero = h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
     int e; frexp(a.hyp.outputscale, &e);                      // |k*| <= outputscale < 2^e
-    b.dig_scale = ldexp(1.0, 6 + 7 * (S - 1) - e);
+    b.dig_scale = ldexp(1.0, (S == 7 ? I8Dig<7>::F : I8Dig<8>::F) - e);
     b.eb_scale = ldexp(1.0, -12);
     b.ss_scale = ldexp(1.0, 2 * e);
     const char* ng = getenv("BO_B200_I8_NO_GUARD");           // triage only: raw sliced values for every candidate
     const bool guard = !(ng && atoi(ng) == 1);
     // (linear + Matern kind: the pair kernel multiplies by the candidate's own eb instead of 2^e)
-    b.guard_scale = I8_GUARD_KAPPA / I8_GUARD_RTOL * ldexp(1.0, (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52 ? 0 : e) - 7 * S);
+    b.guard_scale = I8_GUARD_KAPPA / I8_GUARD_RTOL *
+                    ldexp(1.0, (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52 ? 0 : e) + (S == 7 ? I8Dig<7>::GEXP : I8Dig<8>::GEXP));
     b.guard_w = h->guard_dev;
     b.flag_idx = h->flag_idx; b.flag_count = guard ? h->flag_count_dev : nullptr; b.flag_cap = (long long)h->flag_cap;
     a.part_val = h->part_val; a.part_idx = (long long*)h->part_idx;

@@ -222,7 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 for (int k = 0; k < DP; ++k) { xw[gi][k] = __dmul_rn(a.hyp.lin_w[k], xc[gi][k]); nn = fma(xw[gi][k], xc[gi][k], nn); }
                 const double bound = a.hyp.outputscale * (sqrt(nn * __ldg(b.guard_w + 1)) + 1.0);
                 const int ec = ((__double2hiint(bound) >> 20) & 0x7ff) - 1023 + 1;              // 2^ec > bound
-                dsc[gi] = __hiloint2double((1023 + 6 + 7 * (S - 1) - ec) << 20, 0);
+                dsc[gi] = __hiloint2double((1023 + I8Dig<S>::F - ec) << 20, 0);
                 if (quarter == 0 && q == 0) {
                     pri_s[p * P8_BH + cgrp * 16 + gi * 8 + g] = a.hyp.outputscale * (nn + 1.0);
                     ebc_s[p * P8_BH + cgrp * 16 + gi * 8 + g] = __hiloint2double((1023 + ec) << 20, 0);
@@ -469,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                         for (int j = 0; j < 8; ++j) {
                             double t = i8_s32_to_f64(v[S - 1][j]);
 #pragma unroll
-                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, 0.0078125, i8_s32_to_f64(v[gq][j]));
+                            for (int gq = S - 2; gq >= 0; --gq) t = fma(t, I8Dig<S>::HORNER, i8_s32_to_f64(v[gq][j]));
                             const double u = t * rs;
                             acc[c0 + j] = fma(u, u, acc[c0 + j]);
                         }

@@ -111,7 +111,7 @@ def test_pinned_mode_shard_merge_is_bit_identical(engine, mode):
 
 
 def test_auto_mode_policy_and_sharded_resolution(engine):
-    """AUTO: 8 slices for large pools of an eligible model, FP64 for small pools and for models the sliced path does not
+    """AUTO: 7 slices (one 7-bit + six 8-bit digits: 54-bit operands, 28 products) for large pools of an eligible model, FP64 for small pools and for models the sliced path does not
     cover; the sharded helper resolves on the global pool size, so a rank with a small shard follows."""
     from bayesianoptimizer_b200 import sobol_state
     from bayesianoptimizer_b200.dist import sharded_sweep
@@ -119,14 +119,14 @@ def test_auto_mode_policy_and_sharded_resolution(engine):
     Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
     engine.set_sweep_mode("auto")
     engine.fit(Xd, yd, "matern52", 0.6, 1.0, 1e-3)
-    assert engine.resolve_sweep_mode(10**6) == "i8x8" and engine.resolve_sweep_mode(10**4) == "fp64"
+    assert engine.resolve_sweep_mode(10**6) == "i8x7" and engine.resolve_sweep_mode(10**4) == "fp64"
     engine.fit(Xd, yd, "matern52", 0.6, 1.0, 5e-6)
-    assert engine.resolve_sweep_mode(10**6) == "i8x8"            # no hyper-parameter heuristic: the per-candidate guard covers it
+    assert engine.resolve_sweep_mode(10**6) == "i8x7"            # no hyper-parameter heuristic: the per-candidate guard covers it
     engine.set_sweep_mode("i8x7")
     assert engine.resolve_sweep_mode(10**6) == "i8x7" and engine.resolve_sweep_mode(10) == "i8x7"   # pinned: the model decides
     engine.set_sweep_mode("auto")
     engine.fit(Xd, yd, "linear_matern52", 0.6, 1.0, 1e-3, linear_variance=0.3)
-    assert engine.resolve_sweep_mode(10**6) == "i8x8"            # per-candidate operand scale (CTA-pair kernel)
+    assert engine.resolve_sweep_mode(10**6) == "i8x7"            # per-candidate operand scale (CTA-pair kernel)
     engine.fit(Xd[:100], yd[:100], "rbf", 0.6, 1.0, 1e-3)
     assert engine.resolve_sweep_mode(10**6) == "fp64"            # one stage of rows: not worth a pipeline
     engine.fit(Xd[:300], yd[:300], "rbf", 0.6, 1.0, 1e-3)        # 384 padded rows: AUTO waits for 512, a pinned mode does not
@@ -138,7 +138,7 @@ def test_auto_mode_policy_and_sharded_resolution(engine):
     st = sobol_state(5, 3)
     total, k = 60_000, 4
     v1, i1 = engine.sweep("ei", float(y.max()), sobol=st, count=total, topk=k)
-    assert engine.last_sweep_path() == 8
+    assert engine.last_sweep_path() == 7
     # world of 8: each shard alone (7 500 candidates) would fall under AUTO's pool threshold
     parts = [sharded_sweep(engine, "ei", float(y.max()), 2.0, st, total, k, rank=r, world=1) for r in range(1)]
     assert parts[0][1].tolist() == i1.tolist()
@@ -147,7 +147,7 @@ def test_auto_mode_policy_and_sharded_resolution(engine):
         lo, cnt = r * 7500, 7500
         engine.set_sweep_mode(engine.resolve_sweep_mode(total))
         v, i = engine.sweep("ei", float(y.max()), sobol=st, first_index=lo, count=cnt, topk=k)
-        assert engine.last_sweep_path() == 8
+        assert engine.last_sweep_path() == 7
         engine.set_sweep_mode("auto")
         vs.append(v.cpu().numpy()); is_.append(i.cpu().numpy())
     mv, mi = o.merge_topk(vs, is_, k)
@@ -176,7 +176,7 @@ def test_low_noise_model_takes_8_slices_and_meets_the_variance_bar(engine):
 
 def test_full_size_c3_sample_i8_against_oracle(engine):
     """BASELINE config 3 shape (n_obs = 4096, d = 8): a 20 000-candidate prefix of the headline pool on the path AUTO
-    picks for it (8 slices), dense outputs against the oracle."""
+    picks for it (7 slices with 8-bit lower digits), dense outputs against the oracle."""
     from bayesianoptimizer_b200 import sobol_state
     n, d, N = 4096, 8, 20_000
     X, y = synth_problem(n, d, 4, 5)
@@ -190,7 +190,7 @@ def test_full_size_c3_sample_i8_against_oracle(engine):
     for acq, ak in (("ei", o.ACQ_EI), ("ucb", o.ACQ_UCB)):
         tv, ti, mu, var, av = o.sweep(gp, pts, ak, bf, 2.0, k=4)
         vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, sobol=st, count=N, topk=4, return_all=True)
-        assert engine.last_sweep_path() == 8
+        assert engine.last_sweep_path() == 7
         assert_posterior_close(gm.cpu().numpy(), gv.cpu().numpy(), mu, var)
         assert_acq_close(acq, ga.cpu().numpy(), av)
         assert idx.cpu().tolist() == ti.tolist()
@@ -205,10 +205,10 @@ def test_release_workspace_then_sliced_sweep_is_bit_identical(engine):
     engine.set_sweep_mode("auto")
     st = sobol_state(6, 5)
     v1, i1 = engine.sweep("ei", float(y.max()), sobol=st, count=40_000, topk=8)
-    assert engine.last_sweep_path() == 8
+    assert engine.last_sweep_path() == 7
     engine.release_workspace()
     v2, i2 = engine.sweep("ei", float(y.max()), sobol=st, count=40_000, topk=8)
-    assert engine.last_sweep_path() == 8 and torch.equal(v1, v2) and torch.equal(i1, i2)
+    assert engine.last_sweep_path() == 7 and torch.equal(v1, v2) and torch.equal(i1, i2)
 
 
 def test_i8_peak_probe_reports_a_tensor_rate(engine):

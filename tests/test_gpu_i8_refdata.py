@@ -1,4 +1,4 @@
-"""GPU tier (-m gpu): the DEFAULT sweep contraction (AUTO -> 8 INT8 slices + accuracy guard) and the pinned sliced modes on
+"""GPU tier (-m gpu): the DEFAULT sweep contraction (AUTO -> 7 INT8 slices with 8-bit lower digits + accuracy guard) and the pinned sliced modes on
 the reference's own data -- rows of results/optimization_results.csv (tests/golden/csv_*.npz: duplicated rows {12, 20},
 {17, 50}, clusters, sigma^2 down to ~1e-6 of the prior variance) -- with a 20 000-candidate explicit pool that mixes
 uniform points with 2 400 points 1e-2 .. 1e-5 away from training rows (conftest.refdata_pool), through the C ABI against
@@ -68,11 +68,10 @@ def test_sliced_sweep_on_reference_rows_strict(engine, name, noise, near_min, va
     cd = torch.from_numpy(cand).cuda()
     for acq in ("ei", "ucb", "logei"):
         vals, idx, gm, gv, ga = engine.sweep(acq, bf, 2.0, candidates=cd, topk=8, return_all=True)
-        assert engine.last_sweep_path() == (7 if mode == "i8x7" else 8), "the pool must take the sliced path"
+        assert engine.last_sweep_path() == (8 if mode == "i8x8" else 7), "the pool must take the sliced path (AUTO: 7 wide slices)"
         flagged = engine.last_sweep_flagged()
         assert flagged > 0, "points next to training rows must reach the guard's FP64 re-score"
-        if mode != "i8x7":
-            assert 0 < flagged < 10_000, flagged          # ... and only those: most of the pool stays on the tensor path
+        assert 0 < flagged < 10_000, flagged              # ... and only those: most of the pool stays on the tensor path
         gm, gv, ga = gm.cpu().numpy(), gv.cpu().numpy(), ga.cpu().numpy()
         assert_posterior_close(gm, gv, mu, var, var_abs=var_ulps * s2)
         if acq == "logei":

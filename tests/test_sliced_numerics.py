@@ -60,3 +60,31 @@ def test_eight_slices_meet_the_variance_bar_on_reference_data_and_seven_do_not()
     assert err[8] <= 1e-9 and err[8] <= 4 * e64 + 1e-12           # 8 slices (AUTO): the FP64 product's own level
     assert 1e-8 < err[7] < 1e-7                                   # 7 slices miss the 1e-8 bar next to clustered rows: opt-in only
     assert err[6] > 50 * err[7] and err[7] > 50 * err[8]          # each slice buys ~7 bits
+
+
+def test_kernel_digit_geometry_is_int8_and_exact():
+    """sweep_i8.cuh's I8Dig: eight 7-bit digits, or one 7-bit + six 8-bit ones, as bit fields of rint(x 2^F) + bias."""
+    x = np.random.default_rng(1).uniform(-1, 1, 2000)
+    x[:5] = [1.0, -1.0, 0.0, 2.0 ** -40, -(1.0 - 2.0 ** -50)]
+    for S, W in ((8, 7), (7, 8)):
+        dig = oz.field_digits(x, S, W)
+        assert np.abs(dig[0]).max() <= 64                                           # the 7-bit top digit
+        for dgt in dig[1:]:
+            assert dgt.min() >= -(1 << (W - 1)) and dgt.max() <= (1 << (W - 1)) - 1   # signed W-bit: fits int8
+        rec = dig[0] * 2.0 ** -6 + sum(dgt * 2.0 ** (-6 - W * (s + 1)) for s, dgt in enumerate(dig[1:]))
+        assert np.abs(rec - x).max() <= 2.0 ** (-(6 + W * (S - 1)) - 1) * 1.0000001   # half a unit of the last place
+
+
+def test_seven_wide_slices_track_eight_narrow_ones_on_reference_data():
+    """The AUTO contraction: 7 slices with 8-bit lower digits (28 products) against 8 slices of 7 bits (36 products) and the
+    old 7 x 7-bit form on the reference's CSV rows: a few times the 8-slice error, two orders below the 7 x 7-bit one, and
+    INT32 accumulators far from overflow."""
+    Li, Ks, kss, var_true = _problem()
+    e64 = _rel(Li @ Ks, kss, var_true)
+    U87, n87, i87 = oz.sliced_matmul_fields(Li, Ks, 8, 7)
+    U78, n78, i78 = oz.sliced_matmul_fields(Li, Ks, 7, 8)
+    U77, _, _ = oz.sliced_matmul_fields(Li, Ks, 7, 7)
+    assert (n87, n78) == (36, 28) and max(i87, i78) < 2 ** 31
+    e87, e78, e77 = (_rel(U, kss, var_true) for U in (U87, U78, U77))
+    assert e87 <= 1e-9 and e78 <= 2e-9                              # both inside the bar next to clustered rows (sigma^2 ~ 3e-5)
+    assert e78 <= 8 * max(e87, e64) and e77 >= 20 * e78             # ~1 bit behind 8 x 7; the 7 x 7-bit form is ~6 bits behind

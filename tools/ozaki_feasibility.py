@@ -41,6 +41,38 @@ def slices(x, S, W=7):
     return out, r
 
 
+def field_digits(x, S, W):
+    """The kernels' digit geometry (sweep_i8.cuh, I8Dig): v = rint(x 2^F), F = 6 + W (S - 1); a 7-bit top digit in [-64, 64] and
+    S - 1 balanced W-bit digits in [-2^(W-1), 2^(W-1) - 1], read as bit fields of v + bias.  Returns the S digit arrays
+    (top first, integer-valued float64) -- an exact decomposition: x' = d0 2^-6 + sum_{s>=1} d_s 2^(-6 - W s) = v 2^-F."""
+    F = 6 + W * (S - 1)
+    v = np.rint(np.asarray(x, dtype=np.float64) * 2.0 ** F).astype(object)            # exact Python integers
+    bias = sum((1 << (W - 1)) << (W * k) for k in range(S - 1))
+    u = v + bias
+    low = [np.array([(int(t) >> (W * k)) & ((1 << W) - 1) for t in u.ravel()], dtype=np.float64).reshape(np.shape(x)) - (1 << (W - 1))
+           for k in range(S - 1)]
+    top = np.array([int(t) >> (W * (S - 1)) for t in u.ravel()], dtype=np.float64).reshape(np.shape(x))
+    return [top] + low[::-1]
+
+
+def sliced_matmul_fields(A, B, S, W):
+    """A @ B through the kernels' digit geometry: slice pairs s + t < S, one exact integer accumulator per s + t."""
+    ea = pow2_scale(A, 1); eb = pow2_scale(B, 0)
+    As = field_digits(A / ea, S, W); Bs = field_digits(B / eb, S, W)
+    acc, imax = None, 0.0
+    for g in range(S - 1, -1, -1):
+        G = None
+        for s in range(S):
+            t = g - s
+            if 0 <= t < S:
+                P = As[s] @ Bs[t]
+                G = P if G is None else G + P
+        imax = max(imax, float(np.abs(G).max()))
+        term = G * 2.0 ** (-12 - W * g)
+        acc = term if acc is None else acc + term
+    return acc * ea * eb, S * (S + 1) // 2, imax
+
+
 def pow2_scale(v, axis):
     m = np.max(np.abs(v), axis=axis, keepdims=True)
     m = np.where(m > 0, m, 1.0)
