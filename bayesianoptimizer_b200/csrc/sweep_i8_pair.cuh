@@ -32,7 +32,10 @@ constexpr int P8_B_SLICE = P8_BH * I8_KC;              // 2 KB
 template <int S, int DP>
 struct P8Smem {
     static constexpr int STAGE_BYTES = S * (I8_A_SLICE + P8_B_SLICE);
-    static constexpr int OFF_BAR   = P8_STAGES * STAGE_BYTES;           // full[2] empty[2] tfull tempty pfull[2] pempty[2] xfull[2], tmem base
+    // ring depth: as many stages as 227 KB hold next to ~9 KB of bookkeeping -- three 70 KB stages with 7 slices (the 56 MMAs of a
+    // stage last ~1.8 k cycles: a two-stage ring left the issuer waiting for tiles 19 % of the time), two 80 KB stages with 8
+    static constexpr int STAGES    = (BO_I8_KC == 64) ? ((3 * STAGE_BYTES + 12 * 1024 <= 232448) ? 3 : 2) : P8_STAGES;
+    static constexpr int OFF_BAR   = STAGES * STAGE_BYTES;              // full[] empty[] tfull tempty pfull[2] pempty[2] xfull[2], tmem base
     static constexpr int OFF_COL   = OFF_BAR + 256;                     // colsum[4][64]
     static constexpr int OFF_XCH   = OFF_COL + 4 * I8_BN * 8;           // xch[2][32]: partner's partial sums for my candidates
     static constexpr int OFF_MU    = OFF_XCH + 2 * P8_BH * 8;           // mu[2][4][32]: per panel buffer and row quarter
@@ -43,12 +46,15 @@ struct P8Smem {
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;
     static constexpr int OFF_CMASK = OFF_ACQ + P8_BH * 8;
     static constexpr int OFF_SOB   = OFF_CMASK + 32;
-    static constexpr int OFF_X     = (OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4 + 127) / 128 * 128;
+    static constexpr int BYTES     = (OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4 + 127) / 128 * 128;
+    // The builders' X~ / alpha staging ALIASES the stage ring: a panel is built while the ring is idle (block j + 1 before the
+    // MMAs of block j start, after those of block j - 1 have been drained), never while copies are in flight
+    static constexpr int OFF_X     = 0;
     static constexpr int X_ROW     = (DP + 2 + 1) * 8;
-    static constexpr int X_FREE    = 232448 - OFF_X;
+    static constexpr int X_FREE    = STAGES * STAGE_BYTES;
     static constexpr int XCH       = X_FREE >= 2 * 512 * X_ROW ? 512 : X_FREE >= 2 * 256 * X_ROW ? 256 : 128;     // multiple of 128 (build loop)
     static_assert(X_FREE >= 2 * XCH * X_ROW, "no room for the X~ staging buffers");
-    static constexpr int BYTES     = OFF_X + 2 * XCH * X_ROW;
+    static_assert(BYTES <= 232448, "shared memory");
 };
 
 // ---- cluster-scope primitives ---------------------------------------------------------------------------------
@@ -127,14 +133,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
     static_assert(S * I8_BN <= 512, "TMEM has 512 columns");
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full     = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
-    uint64_t* empty    = full + P8_STAGES;
-    uint64_t* tfull    = empty + P8_STAGES;
+    constexpr int NST = SM::STAGES;
+    uint64_t* empty    = full + NST;
+    uint64_t* tfull    = empty + NST;
     uint64_t* tempty   = tfull + 1;
     uint64_t* pfull    = tempty + 1;          // [2] panel buffer p holds a finished block half
     uint64_t* pempty   = pfull + 2;           // [2] panel buffer p has been consumed
     uint64_t* xfull    = pempty + 2;          // [2] partner's partial sums have arrived
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(xfull + 2);
-    static_assert((2 * P8_STAGES + 8) * 8 + 4 <= 256, "barrier block");
+    static_assert((2 * NST + 8) * 8 + 4 <= 256, "barrier block");
     double* colsum  = reinterpret_cast<double*>(smem + SM::OFF_COL);
     double* xch     = reinterpret_cast<double*>(smem + SM::OFF_XCH);      // [2][32]
     double* mu_s    = reinterpret_cast<double*>(smem + SM::OFF_MU);       // [2][4][32]
@@ -160,7 +167,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
     int8_t* panel0 = b.panel8 + (size_t)blockIdx.x * 2 * panel_bytes;      // two half-panel buffers per CTA
 
     if (tid == 0) {
-        for (int s = 0; s < P8_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tfull, 1); mbar_init(tempty, 8);
         for (int s = 0; s < 2; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); mbar_init(&xfull[s], P8_BH); }
         fence_mbar_init();
@@ -353,7 +360,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                     // to back-to-back kind::i8 MMAs, and each one costs the tensor pipe ~1 cycle: profiles/r02_i8_collector_probe.log,
                     // interference runs), so the panel of the NEXT block is built before this block's MMAs start rather than
                     // underneath them: the builders run at full FP64 rate and the MMAs undisturbed
-                    if (!(a.flags & 8) && blk + npairs < a.nblocks) p8_wait(&pfull[p ^ 1], ((it + 1) >> 1) & 1);
+                    // (not optional: the builders stage X~ through the idle stage ring)
+                    if (blk + npairs < a.nblocks) p8_wait(&pfull[p ^ 1], ((it + 1) >> 1) & 1);
                     if (profp) t_pp += clock64() - wq;
                     for (int ibp = 0; ibp < nbp; ++ibp) {
                         const int ib = 2 * ibp + (int)rank;   // this CTA's row block of the pair
@@ -371,7 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                             const uint32_t fb = p8_mapa(&full[stage], 0);
                             p8_tma_rows(sb, &tmA, (uint32_t)(tile * (S * I8_A_SLICE / 256)), fb);
                             p8_tma_rows(sb + S * I8_A_SLICE, &tmB, (uint32_t)((panel - b.panel8 + (size_t)kc * B_STAGE) / 256), fb);
-                            if (++stage == P8_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == NST) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
@@ -415,7 +423,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                             if (kc == nkc - 1) p8_commit_both(tfull);    // the accumulators of the row-block pair are complete
                         }
                         __syncwarp();
-                        if (++stage == P8_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }

@@ -376,7 +376,8 @@ def sweep_roofline(eng, cfg, name, mode, count, kms, n_obs, side=None):
                            "0.5 s burst); MEASURED_PEAKS.json has no INT8 entry",
             "peak_sustained": peak_sus, "frac_of_sustained_peak": a_tops / peak_sus,
             "int8_ops_per_candidate": ops, "kernel_ms": kms,
-            "note": "the FP64 contraction u = L^-1 k* runs as an error-free product of signed 7-bit slices; TMEM (512 columns) limits "
+            "note": "the FP64 contraction u = L^-1 k* runs as an error-free product of signed int8 slices (AUTO: one 7-bit + six 8-bit digits per "
+                    "operand, 28 slice products; i8x8: eight 7-bit digits, 36 products); TMEM (512 columns) limits "
                     "the tile to 64 candidates x S accumulators; with the A operand kept in the collector across the S - s panel slices "
                     "it multiplies, a 128x64x32 kind::i8 MMA takes 37 SM cycles in isolation (floor 32; 50 without the reuse: "
                     "profiles/r02_i8_collector_probe.log); the step is long, so the sustained (power-capped) peak is the like-for-like "
@@ -483,12 +484,33 @@ def bench_sweep(ctx, name, cfg):
                  "rel_diff": abs(float(vf[0].item()) - winner[0]) / max(abs(winner[0]), 1e-300)}
         eng.set_sweep_mode(mode)
 
+    # the other sliced form beside the one that ran (N = 1 only): a fifth of the shard, two sweeps, the second one timed
+    other = None
+    if mode in ("i8x7", "i8x8") and world == 1:
+        om = "i8x8" if mode == "i8x7" else "i8x7"
+        eng.set_sweep_mode(om)
+        if eng.resolve_sweep_mode(pool) == om:
+            sub = max(count // 5, 1)
+            for _ in range(2):
+                eng.sweep("ei", best_f, 2.0, sobol=sob, first_index=first, count=sub, topk=TOPK)
+                torch.cuda.synchronize()
+            ms = eng.last_sweep_ms()
+            osl = int(om[-1])
+            other = {"mode": om, "value": sub / (ms * 1e-3), "unit": UNIT, "pool": sub, "kernel_ms": ms,
+                     "int8_ops_per_candidate": int8_ops_per_candidate(n, osl),
+                     "achieved_tops": sub * int8_ops_per_candidate(n, osl) / (ms * 1e-3) * 1e-12,
+                     "note": "short run (the clock has not settled under the power cap): compare per-clock, not absolute"}
+        eng.set_sweep_mode(mode)
+
     elapsed_ms, e2e_ms, kern_ms, launches = ctx.reduce_times([elapsed_ms, e2e_local_ms, float(np.mean(kernel_ms)), float(launches)])
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
         value = pool / (ms_per_step * 1e-3)
         e2e_value = pool / (e2e_ms / args.steps * 1e-3)
         roofline = sweep_roofline(eng, cfg, name, mode, count, float(np.mean(kernel_ms)), n, side)
+        if other is not None:
+            other["frac_of_int8_peak"] = other["achieved_tops"] / roofline["peak"]
+            roofline["other_sliced_form"] = other
         slices = {"fp64": 0, "i8x7": 7, "i8x8": 8}[mode]
         line = {
             "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": ctx.W,
@@ -497,9 +519,10 @@ def bench_sweep(ctx, name, cfg):
             "config": {"workload": cfg["workload"], "n_obs": n, "d": d, "pool": pool, "acq": "EI",
                        "parallelism": f"candidate-shard x{world}",
                        "contraction": ("FP64 DMMA" if not slices else
-                                       f"{slices} signed 7-bit slices per operand on INT8 tensor cores, exact INT32 accumulation, FP64 "
-                                       f"recombination, per-candidate accuracy guard with FP64 re-score (bo_set_sweep_mode {mode}, "
-                                       f"resolved from --sweep-mode {args.sweep_mode}); {flagged} candidates re-scored per step"),
+                                       f"{slices} signed slices per operand ({'one 7-bit + six 8-bit digits: 54-bit operands, 28' if slices == 7 else 'eight 7-bit digits: 55-bit operands, 36'} "
+                                       f"slice products) on INT8 tensor cores, exact INT32 accumulation, FP64 recombination, per-candidate accuracy guard "
+                                       f"with FP64 re-score (bo_set_sweep_mode {mode}, resolved from --sweep-mode {args.sweep_mode}); "
+                                       f"{flagged} candidates re-scored per step"),
                        "l2": ("inputs larger than L2: packed L^-1 + per-CTA K* panels streamed every wave" if n >= 2048 else
                               "between timed iterations every CTA rewrites its K* panels (int8 slices) and the pool index range is "
                               "re-generated in-kernel; the operands of this small model fit L2 by design")},

@@ -53,11 +53,11 @@ extern "C" {
 #define BO_ACQ_MEAN  4   /* posterior mean                                                              */
 
 /* contraction used by bo_sweep for the variance term u = L^-1 k* (bo_set_sweep_mode) */
-#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path (8 slices, guarded) for large pools of a stationary-kernel exact GP,
-                           * FP64 DMMA otherwise (see bo_set_sweep_mode) */
+#define BO_SWEEP_AUTO 0   /* INT8-sliced tensor path (BO_SWEEP_I8X7 up to 16 384 padded observations, I8X8 above; guarded) for large
+                           * pools of an exact GP, FP64 DMMA otherwise (see bo_set_sweep_mode) */
 #define BO_SWEEP_FP64 1   /* always the FP64 DMMA contraction */
-#define BO_SWEEP_I8X7 2   /* INT8-sliced with 7 slices wherever eligible */
-#define BO_SWEEP_I8X8 3   /* INT8-sliced with 8 slices wherever eligible */
+#define BO_SWEEP_I8X7 2   /* INT8-sliced, 7 slices per operand: one 7-bit + six 8-bit digits (54-bit operands, 28 slice products) */
+#define BO_SWEEP_I8X8 3   /* INT8-sliced, 8 slices per operand: eight 7-bit digits (55-bit operands, 36 slice products) */
 
 /* error codes (negative statuses) */
 #define BO_E_INVALID  (-1)  /* bad argument                                  */
@@ -227,16 +227,17 @@ int bo_fp64_peak(bo_handle* h, int32_t use_dmma, double seconds, double* tflops_
 int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, int32_t reps, double* tflops_host);
 
 /* Choose how bo_sweep contracts L^-1 with the K(X, X*) panel (BO_SWEEP_*; default BO_SWEEP_AUTO).  The INT8-sliced path
- * computes the same FP64 quantity: both operands are cut into S signed 7-bit slices (error-free, Ozaki scheme I), the
+ * computes the same FP64 quantity: both operands are cut into S signed int8 slices (error-free, Ozaki scheme I), the
  * S (S + 1) / 2 leading slice products run on the INT8 tensor cores (tcgen05.mma kind::i8) with exact INT32
- * accumulation and are recombined in FP64.  Every sliced sweep carries a per-candidate accuracy guard: the slicing
- * error of ||u||^2 is bounded from the row scales of L^-1 and ||u||^2 itself, and a candidate whose variance is not at
- * least 5e8 x that bound (slicing error <= 2e-9 relative) is re-scored on the FP64 DMMA contraction inside the same
- * call -- same outputs, same top-k order; bo_last_sweep_flagged() reports how many.  With 8 slices (what AUTO uses) that
- * is candidates with sigma^2 below ~1e-4 of the prior variance (next to training rows); with 7 slices (opt-in, 1.25x
- * faster per sliced candidate) the bound is 128x larger.  Eligible models: exact GP of any kernel kind (the linear + Matern
- * kind scales each candidate's operand by its own bound on |k*|) with at least 256 (padded) observations; SVGP handles run
- * the FP64 DMMA path in every mode.
+ * accumulation and are recombined in FP64.  Two digit geometries: I8X8 = eight 7-bit digits (55-bit operands, 36 products),
+ * I8X7 = one 7-bit + six 8-bit digits (54-bit operands, 28 products: 3.3x the slicing error of I8X8 on the reference's data,
+ * 22 % fewer MMAs; INT32 accumulators hold up to 16 384 padded observations, above that I8X7 resolves to I8X8).
+ * Every sliced sweep carries a per-candidate accuracy guard: the slicing error of ||u||^2 is bounded from the row scales of
+ * L^-1 and ||u||^2 itself, and a candidate whose variance is not at least 5e8 x that bound (slicing error <= 2e-9 relative)
+ * is re-scored on the FP64 DMMA contraction inside the same call -- same outputs, same top-k order;
+ * bo_last_sweep_flagged() reports how many (candidates with sigma^2 below ~2e-4 (I8X8) / ~7e-4 (I8X7) of the prior variance:
+ * next to training rows).  Eligible models: exact GP of any kernel kind (the linear + Matern kind scales each candidate's
+ * operand by its own bound on |k*|) with at least 256 (padded) observations; SVGP handles run the FP64 DMMA path in every mode.
  * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
  * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates and models with fewer than 512
  * (padded) observations on the FP64 path.  bo_posterior / bo_posterior_multi stay on the FP64 contraction under AUTO
