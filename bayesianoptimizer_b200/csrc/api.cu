@@ -94,7 +94,7 @@ void bo_destroy(bo_handle* h) {
     lml_release(h);
     void* ptrs[] = {h->qbuf, h->split_ws, h->Xs, h->Xraw, h->yv, h->alpha, h->Lm, h->Li, h->Tw, h->Lp, h->vec1, h->vec2, h->vec3,
                     h->info_dev, h->plan_dev, h->part_val, h->part_idx, h->sobol_dev,
-                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws, h->Lp8, h->rowscale, h->guard_dev, h->flag_count_dev};
+                    h->out_stage_val, h->out_stage_idx, h->Lp2, h->select_ws, h->Lp8, h->rowscale, h->guard_dev, h->flag_count_dev, h->svB};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->info_host) cudaFreeHost(h->info_host);
     if (h->flag_count_host) cudaFreeHost(h->flag_count_host);

@@ -90,6 +90,8 @@ struct bo_handle {
     double sv_add = 0.0;         // K_uu jitter (gpytorch adds it to k** as well) + likelihood noise
     double* Lp2 = nullptr;       // packed J Ls^T J (second triangular factor of the predictive variance)
     size_t  Lp2_elems = 0;
+    double* svB = nullptr;       // B = Ls^T L^-1 (np x np, dense, pitch np): the sliced sweep contracts the stack [L^-1; B] in one pass
+    size_t  svB_elems = 0;
     double* panel2 = nullptr;    // [grid, np/SW_BK, SW_TILE] row-reversed interp-term panels
     size_t  panel2_bytes = 0;
 

@@ -720,6 +720,46 @@ __global__ void __launch_bounds__(256) pack_rev_chol_kernel(const double* __rest
     }
 }
 
+// Ls (M x M, lower triangle used) -> zero-padded np x np copy, so that the GEMM below reads whole tiles
+__global__ void pad_lower_kernel(const double* __restrict__ Ls, int M, int np, double* __restrict__ out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)np * np) return;
+    const int i = (int)(e / np), j = (int)(e % np);
+    out[e] = (i < M && j <= i) ? Ls[(size_t)i * M + j] : 0.0;
+}
+
+// B = Ls^T L^-1 (dense np x np) for the sliced sweep of an SVGP state: ||Ls^T u||^2 = ||B k*||^2 makes the second term of the
+// predictive variance a contraction of the SAME sliced panel k* as ||L^-1 k*||^2 -- one pass over the stacked factor [L^-1; B]
+// instead of a second pass over u (which would have to be re-sliced per candidate).  One grouped-GEMM launch at load time.
+static int svgp_build_b(bo_handle* h, const double* Ls_dev, int M, cudaStream_t st) {
+    const int np = h->np;
+    const size_t elems = (size_t)np * np;
+    if (elems > h->svB_elems) {
+        if (h->svB) cudaFree(h->svB);
+        h->svB = nullptr; h->svB_elems = 0;
+        BO_CUDA(h, cudaMalloc(&h->svB, elems * sizeof(double)));
+        h->svB_elems = elems;
+    }
+    double* pad = nullptr; GemmProblem* pd = nullptr;
+    BO_CUDA(h, cudaMalloc(&pad, elems * sizeof(double)));
+    if (cudaMalloc(&pd, sizeof(GemmProblem)) != cudaSuccess) { cudaFree(pad); cudaGetLastError(); return fail(h, BO_E_NOMEM, "bo_svgp_load: allocation failed"); }
+    pad_lower_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(Ls_dev, M, np, pad);
+    h->launches++;
+    GemmBatch g(64);
+    // C[m][n] = sum_k Ls[k][m] L^-1[k][n]: A given as [K][M]; both operands vanish for k < max(m, n)
+    g.add(pad, np, h->Li, h->cap_np, h->svB, np, np, np, np, 1.0, 0.0, /*transB=*/0, GEMM_TRANS_A | GEMM_K_FROM_MAX);
+    cudaError_t e = cudaMemcpyAsync(pd, g.probs.data(), sizeof(GemmProblem), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        dgemm_grouped_kernel<64, 64, 16, 2, 4><<<g.tiles, 256, GemmSmem<64, 64, 16, 2>::BYTES, st>>>(pd, 1);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(pad); cudaFree(pd);
+    if (e != cudaSuccess) { h->err = std::string("bo_svgp_load: building Ls^T L^-1 failed: ") + cudaGetErrorString(e); cudaGetLastError(); return BO_E_CUDA; }
+    return 0;
+}
+
 int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, const double* ls_host, double outputscale,
                    double linear_variance, double mean, double noise, double jitter, const double* var_mean_dev,
                    const double* var_chol_dev, cudaStream_t st) {
@@ -741,6 +781,7 @@ int svgp_load_impl(bo_handle* h, const double* Z_dev, int M, int d, int kind, co
     }
     pack_rev_chol_kernel<<<dim3(np / SW_BK, np / SW_BM), 256, 0, st>>>(var_chol_dev, M, np, h->Lp2);
     BO_LAUNCH_CHECK(h);
+    if ((rc = svgp_build_b(h, var_chol_dev, M, st))) return rc;
     BO_CUDA(h, cudaStreamSynchronize(st));               // var_chol_dev is borrowed for the call only
     h->svgp = true;
     h->sv_add = jitter + noise;

@@ -75,6 +75,10 @@ struct SweepI8Args {
     // flag_count) and the FP64 contraction re-scores it after the kernel
     double guard_scale; const double* guard_w;
     long long* flag_idx; int* flag_count; long long flag_cap;
+    // SVGP predictive state (CTA-pair kernel only): Lp8 holds the slices of the stack [L^-1; B], B = Ls^T L^-1 (dense row blocks
+    // behind the triangular ones), rowscale has 2 np entries, guard_w[2] is W of B's rows, and the variance is
+    // k** + sv_add - ||L^-1 k*||^2 + ||B k*||^2
+    int sv; double sv_add;
 };
 
 // Slicing error of ||u||^2 (what the guard bounds).  The products of slices s + t >= S are dropped: per element product an
@@ -218,12 +222,14 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- operand preparation: row scales and int8 slices of L^-1 in stage-tile order --------------------------------
+// dense_cols > 0: the rows are full (B = Ls^T L^-1 of an SVGP state): dense_cols products per row instead of i + 1
 __global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restrict__ Li, int ld, int np, int n, double* __restrict__ rowscale,
-                                                          double* __restrict__ guard_w) {
+                                                          double* __restrict__ guard_w, int dense_cols = 0) {
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= np) return;
     double m = 0.0;
-    for (int j = lane; j <= i; j += 32) m = fmax(m, fabs(Li[(size_t)i * ld + j]));
+    const int jend = dense_cols > 0 ? dense_cols : i + 1;
+    for (int j = lane; j < jend; j += 32) m = fmax(m, fabs(Li[(size_t)i * ld + j]));
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(128) i8_rowscale_kernel(const double* __restri
         const double rs = (m > 0.0) ? ldexp(1.0, e) : 1.0;
         rowscale[i] = rs;
         // W = max over the real rows of rowscale_i^2 (i + 1): positive doubles order like their bit patterns
-        if (i < n) atomicMax(reinterpret_cast<unsigned long long*>(guard_w), (unsigned long long)__double_as_longlong(rs * rs * (double)(i + 1)));
+        if (i < n) atomicMax(reinterpret_cast<unsigned long long*>(guard_w), (unsigned long long)__double_as_longlong(rs * rs * (double)jend));
     }
 }
 
@@ -246,13 +252,16 @@ __global__ void __launch_bounds__(256) i8_xnorm_kernel(const double* __restrict_
 }
 
 // one thread per (row, 16-column chunk) of a stage tile: S x 16 B, tile (ib, kc) at ((ib (ib + 1) / 2) * 2 + kc) * S * 8 KB
+// dense = 1 (B = Ls^T L^-1 of an SVGP state): every (ib, kc) tile exists, row-block major, behind the triangular tiles
 template <int S>
 __global__ void __launch_bounds__(256) i8_pack_linv_kernel(const double* __restrict__ Li, int ld, const double* __restrict__ rowscale,
-                                                           int8_t* __restrict__ Lp8, int nbm) {
+                                                           int8_t* __restrict__ Lp8, int nbm, int dense = 0) {
     const int ib = blockIdx.y;
     const int kc = blockIdx.x;                        // 0 .. 2 nbm - 1 ; tiles right of the diagonal block do not exist
-    if (kc >= (ib + 1) * (SW_BM / I8_KC)) return;
-    int8_t* tile = Lp8 + ((size_t)ib * (ib + 1) / 2 * (SW_BM / I8_KC) + kc) * (size_t)(S * I8_A_SLICE);
+    if (!dense && kc >= (ib + 1) * (SW_BM / I8_KC)) return;
+    const size_t tidx = dense ? (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) + (size_t)ib * nbm * (SW_BM / I8_KC) + kc
+                              : (size_t)ib * (ib + 1) / 2 * (SW_BM / I8_KC) + kc;
+    int8_t* tile = Lp8 + tidx * (size_t)(S * I8_A_SLICE);
     for (int e = threadIdx.x; e < SW_BM * (I8_KC / 16); e += 256) {
         const int r = e / (I8_KC / 16), ch = e % (I8_KC / 16);
         const int i = ib * SW_BM + r, j0 = kc * I8_KC + ch * 16;
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(256) i8_pack_linv_kernel(const double* __restr
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int j = j0 + q4 * 4 + b;
-                const double x = (j <= i) ? Li[(size_t)i * ld + j] * inv : 0.0;
+                const double x = (dense || j <= i) ? Li[(size_t)i * ld + j] * inv : 0.0;
                 int dg[S];
                 i8_digits<S>(x, dg);
 #pragma unroll
@@ -664,7 +673,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
 static bool sweep_i8_model_ok(const bo_handle* h) {
     // np < 2^16: the INT32 group accumulators hold at most 8 * 64 * 64 * np
     // (the linear + Matern kind runs on the CTA-pair kernel only: per-candidate operand scale)
-    return h->fitted && !h->svgp && h->np >= I8_MIN_NP && h->np < 65536;
+    // (so does an SVGP predictive state: its stacked factor [L^-1; Ls^T L^-1] exists in the pair kernel only)
+    return h->fitted && (!h->svgp || (h->svB != nullptr && h->sm_count >= 2)) && h->np >= I8_MIN_NP && h->np < 65536;
 }
 
 // Slice count of AUTO.  Both sliced forms carry the per-candidate accuracy guard, so both deliver the same guarantee
@@ -683,7 +693,8 @@ int resolve_sweep_mode(const bo_handle* h, int mode, long long pool) {
     if (mode == BO_SWEEP_FP64 || !sweep_i8_model_ok(h)) return BO_SWEEP_FP64;
     if (mode == BO_SWEEP_I8X7) return h->np <= I8Dig<7>::NP_MAX ? BO_SWEEP_I8X7 : BO_SWEEP_I8X8;      // accumulator bound
     if (mode == BO_SWEEP_I8X8) return mode;
-    if ((pool + I8_BN - 1) / I8_BN < 2LL * h->sm_count) return BO_SWEEP_FP64;
+    // (an SVGP state has no row-split FP64 kernel to fall back on: one full turn of the CTA pairs is enough there)
+    if ((pool + I8_BN - 1) / I8_BN < (h->svgp ? h->sm_count / 2 : 2LL * h->sm_count)) return BO_SWEEP_FP64;
     if (h->np < I8_AUTO_MIN_NP) return BO_SWEEP_FP64;     // measured gain starts at n = 512 (1.33x); below it was not measured
     // no hyper-parameter heuristic: every sliced sweep carries the per-candidate accuracy guard (I8_GUARD_*), which sends
     // the candidates the slicing error could matter for -- sigma^2 orders of magnitude below the prior variance, next to
@@ -695,18 +706,19 @@ template <int S>
 static int ensure_i8_ws(bo_handle* h, int grid, long long pool) {
     const int nbm = h->np / SW_BM;
     // packed tiles + one all-zero stage tile behind them (Lp8_zero)
-    const size_t a_bytes = ((size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) + 1) * (size_t)(S * I8_A_SLICE);
+    const size_t a_bytes = ((size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) + (h->svgp ? (size_t)nbm * nbm * (SW_BM / I8_KC) : 0) + 1) *
+                           (size_t)(S * I8_A_SLICE);
     if (a_bytes > h->Lp8_bytes) {
         if (h->Lp8) cudaFree(h->Lp8);
         h->Lp8 = nullptr; h->Lp8_bytes = 0; h->Lp8_epoch = 0;
         BO_CUDA(h, cudaMalloc(&h->Lp8, a_bytes));
         h->Lp8_bytes = a_bytes;
     }
-    if ((size_t)h->np > h->rowscale_cap) {
+    if (2 * (size_t)h->np > h->rowscale_cap) {                 // (second half: the rows of B of an SVGP state)
         if (h->rowscale) cudaFree(h->rowscale);
         h->rowscale = nullptr; h->rowscale_cap = 0; h->Lp8_epoch = 0;
-        BO_CUDA(h, cudaMalloc(&h->rowscale, (size_t)h->cap_np * sizeof(double)));
-        h->rowscale_cap = h->cap_np;
+        BO_CUDA(h, cudaMalloc(&h->rowscale, 2 * (size_t)h->cap_np * sizeof(double)));
+        h->rowscale_cap = 2 * (size_t)h->cap_np;
     }
     const size_t p_bytes = (size_t)grid * 2 * (h->np / I8_KC) * (size_t)(S * I8_B_SLICE);      // two panel buffers per CTA
     if (p_bytes > h->panel8_bytes) {
@@ -717,7 +729,7 @@ static int ensure_i8_ws(bo_handle* h, int grid, long long pool) {
     }
     // guard: room for every candidate of the pool (8 B each).  The path a candidate takes must depend on the candidate alone --
     // a "too many flagged, re-score the whole pool" shortcut would make values depend on the shard layout
-    if (!h->guard_dev) { BO_CUDA(h, cudaMalloc(&h->guard_dev, 2 * sizeof(double))); h->Lp8_epoch = 0; }
+    if (!h->guard_dev) { BO_CUDA(h, cudaMalloc(&h->guard_dev, 4 * sizeof(double))); h->Lp8_epoch = 0; }
     if (!h->flag_count_dev) BO_CUDA(h, cudaMalloc(&h->flag_count_dev, sizeof(int)));
     if (!h->flag_count_host) BO_CUDA(h, cudaMallocHost(&h->flag_count_host, sizeof(int)));
     const size_t cap = (size_t)(pool > 0 ? pool : 1);
@@ -756,8 +768,8 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     // phase dominates; small models (few row blocks per candidate block) keep the one-CTA kernel, whose build overlaps the
     // MMAs: n = 512: 121 M cand/s one-CTA vs 74 M pair; n = 1024: 49 vs 35; n = 4096: 3.8 vs 4.1 (profiles/r02_*).
     const char* pe = getenv("BO_B200_I8_PAIR");
-    const bool pairs = h->sm_count >= 2 && (pe ? atoi(pe) != 0 : (h->np >= I8_PAIR_MIN_NP || h->hyp.kind == BO_KERNEL_LINEAR_MATERN52));
-    if (!pairs && h->hyp.kind == BO_KERNEL_LINEAR_MATERN52)          // the one-CTA kernel has no per-candidate operand scale
+    const bool pairs = h->sm_count >= 2 && (pe ? atoi(pe) != 0 : (h->np >= I8_PAIR_MIN_NP || h->hyp.kind == BO_KERNEL_LINEAR_MATERN52 || h->svgp));
+    if (!pairs && (h->hyp.kind == BO_KERNEL_LINEAR_MATERN52 || h->svgp))   // the one-CTA kernel has no per-candidate operand scale / stacked factor
         return sweep_fp64_run(h, a_in, 0, true, vals_dev, idx_dev, nullptr, st);
     int grid;
     if (pairs) {
@@ -771,9 +783,10 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
     if ((rc = ensure_sweep_ws(h, grid, false, grid + h->sm_count))) return rc;    // top-k lists: this kernel's + the re-score pass's
     if ((rc = (S == 8 ? ensure_i8_ws<8>(h, grid, a.N) : ensure_i8_ws<7>(h, grid, a.N)))) return rc;
     const int nbm = h->np / SW_BM;
+    const size_t tiles_all = (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) + (h->svgp ? (size_t)nbm * nbm * (SW_BM / I8_KC) : 0);
     if (h->Lp8_epoch != h->factor_epoch || h->Lp8_S != S) {
         // the factor changed since the operands were sliced (fit, append, refit) or the slice count did
-        BO_CUDA(h, cudaMemsetAsync(h->guard_dev, 0, 2 * sizeof(double), st));
+        BO_CUDA(h, cudaMemsetAsync(h->guard_dev, 0, 4 * sizeof(double), st));
         i8_rowscale_kernel<<<(h->np + 3) / 4, 128, 0, st>>>(h->Li, h->cap_np, h->np, h->n, h->rowscale, h->guard_dev);
         BO_LAUNCH_CHECK(h);
         if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->Li, h->cap_np, h->rowscale, h->Lp8, nbm);
@@ -783,12 +796,20 @@ static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals
             i8_xnorm_kernel<<<(h->n + 255) / 256, 256, 0, st>>>(h->Xs, h->n, h->hyp, h->guard_dev);
             BO_LAUNCH_CHECK(h);
         }
-        BO_CUDA(h, cudaMemsetAsync(h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE), 0, (size_t)S * I8_A_SLICE, st));
+        if (h->svgp) {          // the rows of B = Ls^T L^-1 behind those of L^-1: their scales, their W (guard_w[2]), their dense tiles
+            i8_rowscale_kernel<<<(h->np + 3) / 4, 128, 0, st>>>(h->svB, h->np, h->np, h->n, h->rowscale + h->np, h->guard_dev + 2, h->n);
+            BO_LAUNCH_CHECK(h);
+            if (S == 8) i8_pack_linv_kernel<8><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->svB, h->np, h->rowscale + h->np, h->Lp8, nbm, 1);
+            else        i8_pack_linv_kernel<7><<<dim3(nbm * (SW_BM / I8_KC), nbm), 256, 0, st>>>(h->svB, h->np, h->rowscale + h->np, h->Lp8, nbm, 1);
+            BO_LAUNCH_CHECK(h);
+        }
+        BO_CUDA(h, cudaMemsetAsync(h->Lp8 + tiles_all * (size_t)(S * I8_A_SLICE), 0, (size_t)S * I8_A_SLICE, st));
         h->Lp8_epoch = h->factor_epoch; h->Lp8_S = S;
     }
     SweepI8Args b{};
     b.Lp8 = h->Lp8; b.rowscale = h->rowscale; b.panel8 = h->panel8;
-    b.Lp8_zero = h->Lp8 + (size_t)nbm * (nbm + 1) / 2 * (SW_BM / I8_KC) * (size_t)(S * I8_A_SLICE);
+    b.Lp8_zero = h->Lp8 + tiles_all * (size_t)(S * I8_A_SLICE);
+    b.sv = h->svgp ? 1 : 0; b.sv_add = h->svgp ? h->sv_add : 0.0;
     int e; frexp(a.hyp.outputscale, &e);                      // |k*| <= outputscale < 2^e
     b.dig_scale = ldexp(1.0, (S == 7 ? I8Dig<7>::F : I8Dig<8>::F) - e);
     b.eb_scale = ldexp(1.0, -12);

@@ -36,9 +36,9 @@ struct P8Smem {
     // stage last ~1.8 k cycles: a two-stage ring left the issuer waiting for tiles 19 % of the time), two 80 KB stages with 8
     static constexpr int STAGES    = (BO_I8_KC == 64) ? ((3 * STAGE_BYTES + 12 * 1024 <= 232448) ? 3 : 2) : P8_STAGES;
     static constexpr int OFF_BAR   = STAGES * STAGE_BYTES;              // full[] empty[] tfull tempty pfull[2] pempty[2] xfull[2], tmem base
-    static constexpr int OFF_COL   = OFF_BAR + 256;                     // colsum[4][64]
-    static constexpr int OFF_XCH   = OFF_COL + 4 * I8_BN * 8;           // xch[2][32]: partner's partial sums for my candidates
-    static constexpr int OFF_MU    = OFF_XCH + 2 * P8_BH * 8;           // mu[2][4][32]: per panel buffer and row quarter
+    static constexpr int OFF_COL   = OFF_BAR + 256;                     // colsum[2][4][64] (second set: the SVGP factor's rows)
+    static constexpr int OFF_XCH   = OFF_COL + 2 * 4 * I8_BN * 8;       // xch[2][2][32]: partner's partial sums for my candidates
+    static constexpr int OFF_MU    = OFF_XCH + 4 * P8_BH * 8;           // mu[2][4][32]: per panel buffer and row quarter
     static constexpr int OFF_PRI   = OFF_MU + 8 * P8_BH * 8;            // pri[2][32] prior variance k(x*, x*), ebc[2][32] operand bound 2^e per candidate
     static constexpr int OFF_TAB   = OFF_PRI + 4 * P8_BH * 8;           // 2^(j/16), j < 16 (exp_neg_fast)
     static constexpr int OFF_TKV   = OFF_TAB + 16 * 8;
@@ -161,8 +161,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int nbm = a.np / SW_BM;
     const int nbp = (nbm + 1) / 2;                            // row-block pairs
+    // SVGP predictive state (b.sv): the factor is the stack [L^-1; B], B = Ls^T L^-1 -- var = k** + sv_add - ||L^-1 k*||^2 + ||B k*||^2
+    // from ONE pass over the same sliced panel (the FP64 kernel's second triangular pass needs u in full first)
+    const int nbp_all = b.sv ? 2 * nbp : nbp;
     constexpr int KCH = SW_BM / I8_KC;                        // stages per 128 columns
     constexpr int B_STAGE = S * P8_B_SLICE;
+    const size_t tiles_tri = (size_t)nbm * (nbm + 1) / 2 * KCH;               // packed L^-1 tiles; behind them B's (SVGP), then the zero tile
+    const size_t tile_zero = tiles_tri + (b.sv ? (size_t)nbm * nbm * KCH : 0);
     const size_t panel_bytes = (size_t)(a.np / I8_KC) * B_STAGE;
     int8_t* panel0 = b.panel8 + (size_t)blockIdx.x * 2 * panel_bytes;      // two half-panel buffers per CTA
 
@@ -363,10 +368,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                     // (not optional: the builders stage X~ through the idle stage ring)
                     if (blk + npairs < a.nblocks) p8_wait(&pfull[p ^ 1], ((it + 1) >> 1) & 1);
                     if (profp) t_pp += clock64() - wq;
-                    for (int ibp = 0; ibp < nbp; ++ibp) {
-                        const int ib = 2 * ibp + (int)rank;   // this CTA's row block of the pair
-                        const int nkc = (2 * ibp + 2) * KCH;  // the pair walks the K extent of its odd row block
-                        const int mykc = ib < nbm ? (ib + 1) * KCH : 0;
+                    for (int ibp = 0; ibp < nbp_all; ++ibp) {
+                        // SVGP: after the row blocks of L^-1 (lower block triangle) come those of B = Ls^T L^-1 (dense: every K step)
+                        const bool dense = ibp >= nbp;
+                        const int ib = 2 * (dense ? ibp - nbp : ibp) + (int)rank;   // this CTA's row block of the pair
+                        const int nkc = dense ? nbm * KCH : (2 * ibp + 2) * KCH;    // the pair walks the K extent of its odd row block
+                        const int mykc = ib < nbm ? (dense ? nbm * KCH : (ib + 1) * KCH) : 0;
+                        const size_t tile0 = dense ? tiles_tri + (size_t)ib * nbm * KCH : (size_t)ib * (ib + 1) / 2 * KCH;
                         for (int kc = 0; kc < nkc; ++kc) {
                             const long long we = profp ? clock64() : 0;
                             p8_wait(&empty[stage], phase ^ 1);
@@ -375,7 +383,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                             if (rank == 0) mbar_expect_tx(&full[stage], 2u * SM::STAGE_BYTES);     // both CTAs' tiles complete here
                             // beyond this row block's own K extent (the even block's last 128 columns, a row block past the
                             // end): structurally zero -> the all-zero tile parked behind the packed factor
-                            const size_t tile = kc < mykc ? (size_t)ib * (ib + 1) / 2 * KCH + kc : (size_t)nbm * (nbm + 1) / 2 * KCH;
+                            const size_t tile = kc < mykc ? tile0 + kc : tile_zero;
                             const uint32_t fb = p8_mapa(&full[stage], 0);
                             p8_tma_rows(sb, &tmA, (uint32_t)(tile * (S * I8_A_SLICE / 256)), fb);
                             p8_tma_rows(sb + S * I8_A_SLICE, &tmB, (uint32_t)((panel - b.panel8 + (size_t)kc * B_STAGE) / 256), fb);
@@ -389,12 +397,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 // leader: one elected lane issues the M = 256 MMAs of both CTAs (fully unrolled, warp-uniform control flow)
                 const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)((2 * SW_BM) >> 4) << 24);
                 const bool leader = i8_elect();
-                for (int ibp = 0; ibp < nbp; ++ibp, ++rb) {
+                for (int ibp = 0; ibp < nbp_all; ++ibp, ++rb) {
                     const long long w1 = prof ? clock64() : 0;
                     p8_wait<true>(tempty, (rb & 1) ^ 1);       // both CTAs have drained the previous row-block pair
                     if (prof) t_w1 += clock64() - w1;
                     tc_fence_after();
-                    const int nkc = (2 * ibp + 2) * KCH;
+                    const int nkc = ibp >= nbp ? nbm * KCH : (2 * ibp + 2) * KCH;
                     for (int kc = 0; kc < nkc; ++kc) {
                         const long long w0 = prof ? clock64() : 0;
                         p8_wait(&full[stage], phase);
@@ -449,13 +457,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
         if ((long long)pair + npairs < a.nblocks) build((long long)pair + npairs, 1, warp);
         for (long long blk = pair; blk < a.nblocks; blk += npairs, ++it) {
             const int p = it & 1;
-            {
+            for (int ph = 0; ph < (b.sv ? 2 : 1); ++ph) {          // ph = 1: the rows of B (SVGP), summed apart from those of L^-1
                 double acc[I8_BN];
 #pragma unroll
                 for (int c = 0; c < I8_BN; ++c) acc[c] = 0.0;
                 for (int ibp = 0; ibp < nbp; ++ibp, ++rb) {
                     const int ib = 2 * ibp + (int)rank;
-                    const double rs = ib < nbm ? b.rowscale[ib * SW_BM + tid] * b.eb_scale : 0.0;
+                    const double rs = ib < nbm ? b.rowscale[ph * a.np + ib * SW_BM + tid] * b.eb_scale : 0.0;
                     p8_wait<false, 100>(tfull, rb & 1);
                     tc_fence_after();
                     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -497,19 +505,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                     int base = 0;
 #pragma unroll
                     for (int o = 16, cnt = I8_BN / 2; o >= 1; o >>= 1, cnt >>= 1) base += (lane & o) ? cnt : 0;
-                    colsum[warp * I8_BN + base] = acc[0];
-                    colsum[warp * I8_BN + base + 1] = acc[1];
+                    colsum[(ph * 4 + warp) * I8_BN + base] = acc[0];
+                    colsum[(ph * 4 + warp) * I8_BN + base + 1] = acc[1];
                 }
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
 
             // partial sums over this CTA's row blocks: the partner's candidates go to the partner, mine stay
-            double mine = 0.0;
+            double mine = 0.0, mine2 = 0.0;
             if (tid < P8_BH) {
                 const int cp = (1 - (int)rank) * P8_BH + tid, cm = (int)rank * P8_BH + tid;
                 const double theirs = (colsum[cp] + colsum[I8_BN + cp]) + (colsum[2 * I8_BN + cp] + colsum[3 * I8_BN + cp]);
                 mine = (colsum[cm] + colsum[I8_BN + cm]) + (colsum[2 * I8_BN + cm] + colsum[3 * I8_BN + cm]);
                 p8_st_remote_f64(p8_mapa(&xch[p * P8_BH + tid], 1 - rank), theirs);
+                if (b.sv) {
+                    const double* c2 = colsum + 4 * I8_BN;
+                    const double theirs2 = (c2[cp] + c2[I8_BN + cp]) + (c2[2 * I8_BN + cp] + c2[3 * I8_BN + cp]);
+                    mine2 = (c2[cm] + c2[I8_BN + cm]) + (c2[2 * I8_BN + cm] + c2[3 * I8_BN + cm]);
+                    p8_st_remote_f64(p8_mapa(&xch[(2 + p) * P8_BH + tid], 1 - rank), theirs2);
+                }
                 p8_arrive_remote(p8_mapa(&xfull[p], 1 - rank));           // release.cluster: orders this thread's store before it
                 p8_wait<true>(&xfull[p], (it >> 1) & 1);
                 p8_wait(&pfull[p], (it >> 1) & 1);                        // acquire: mu_s[p] of this CTA's builders
@@ -522,9 +536,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                 const double ebc = LIN ? ebc_s[p * P8_BH + tid] : 1.0;           // (stationary kinds: eb is folded into ss_scale / guard_scale)
                 const double prior = LIN ? pri_s[p * P8_BH + tid] : a.hyp.outputscale;
                 // (even row blocks) + (odd row blocks): one order for both CTAs; then the operand bound squared (a power of two)
-                const double ss = (rank == 0 ? mine + other : other + mine) * (LIN ? ebc * ebc : b.ss_scale);
-                const bool flagged = b.flag_count != nullptr && li < a.N &&
-                                     !(prior - ss >= b.guard_scale * ebc * sqrt(__ldg(b.guard_w) * ss));
+                const double ssu = (rank == 0 ? mine + other : other + mine) * (LIN ? ebc * ebc : b.ss_scale);
+                double ss = ssu, gerr = sqrt(__ldg(b.guard_w) * ssu);
+                if (b.sv) {                 // ||B k*||^2 comes back; its slicing error adds to the bound (W of B's rows: guard_w[2])
+                    const double other2 = xch[(2 + p) * P8_BH + tid];
+                    const double ssw = (rank == 0 ? mine2 + other2 : other2 + mine2) * (LIN ? ebc * ebc : b.ss_scale);
+                    ss = ssu - ssw - b.sv_add;
+                    gerr += sqrt(__ldg(b.guard_w + 2) * ssw);
+                }
+                const bool flagged = b.flag_count != nullptr && li < a.N && !(prior - ss >= b.guard_scale * ebc * gerr);
                 {
                     const unsigned fm = __ballot_sync(0xffffffffu, flagged);
                     if (fm) {

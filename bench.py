@@ -4,6 +4,7 @@
     python bench.py [--config C3] [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 --config selects a BASELINE.json configuration (C3 is the default headline: the one the metric is quoted on):
+  C1  the reference's own CPU-runnable case: Bayesian.py loop on its results CSV rows, 10^4 pool     ms per BO iteration
   C2  synthetic d=5, n_obs=512, 10^6 EI candidates                       candidates/s
   C3  synthetic d=8, n_obs=4096, 10^7 EI candidates, sharded over N GPUs  candidates/s     (strong scaling: fixed pool)
   C4  Kriging-believer q=16 batches growing from n_obs=4096 (to 8192), 10^6-candidate LogEI re-sweep + one row append
@@ -32,6 +33,12 @@ if ROOT not in sys.path:
 UNIT = "candidates/s"
 TOPK = 1
 CONFIGS = {
+    "C1": dict(n=3000, d=5, pool=10_000, seeds=(0,), golden="csv_n3000_matern.npz", q_big=1000,
+               metric="GP refit+suggest ms (Bayesian.py loop, n_obs=3000 rows of the reference's results CSV, 10^4-candidate pool)",
+               workload="C1: the Bayesian.py loop through the drop-in class on the first 3000 rows of the reference's "
+                        "results/optimization_results.csv (tests/golden/csv_n3000_matern.npz; the Taichi simulator replaced by the cached "
+                        "CSV objective): per iteration fit_gp_model (warm-started MAP hyper-parameter fit on the exact LML + final fit) -> "
+                        "optimize_acquisition_function (LogEI over a 10^4 Sobol pool, 10 refined starts) -> register"),
     "C2": dict(n=512, d=5, pool=1_000_000, ls=0.5, s2=1.0, noise=1e-3, seeds=(1, 2, 3), cpu_sample=200_000,
                metric="EI candidates scored/s (n_obs=512,d=5)",
                workload="C2: synthetic d=5 n_obs=512 Matern-5/2 ARD, EI over a 10^6 in-kernel scrambled-Sobol pool"),
@@ -230,7 +237,8 @@ def run_reference(args, cfg):
         return
     name = args.config
     base = {"impl": "reference", "metric": cfg["metric"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+            "vs_baseline": None, "dtype": "f64",
+            "data": "reference CSV rows (tests/golden), cached-objective simulator" if name == "C1" else "synthetic"}
     if name in ("C2", "C3"):
         sample = cfg["cpu_sample"]
         for _ in range(1 if args.warmup > 0 else 0):
@@ -244,6 +252,14 @@ def run_reference(args, cfg):
         what = (f"{sample}-candidate prefix of the same Sobol pool per step (NumPy/SciPy FP64 oracle, one slice per core in a "
                 f"thread pool, chunk 2048 like Bayesian7.py:63)")
         config = {"workload": cfg["workload"], "n_obs": cfg["n"], "d": cfg["d"], "pool": cfg["pool"], "acq": "EI"}
+        cores = r["threads"]
+    elif name == "C1":
+        r = cpu_c1_run(cfg, steps=max(1, min(args.steps, 3)))
+        ms = r["s_per_iter"] * 1e3
+        value, unit, hib, scaling = ms, "ms", False, "strong"
+        what = (f"{r['steps']} warm iteration(s) of the same loop at n_obs=3000, every engine call answered by the NumPy/SciPy oracle "
+                f"(threaded LAPACK)")
+        config = {"workload": cfg["workload"], "n_obs": cfg["n"], "d": cfg["d"], "pool": cfg["pool"], "acq": "LogEI"}
         cores = r["threads"]
     elif name == "C4":
         times = []
@@ -760,6 +776,186 @@ def bench_c5(ctx, name, cfg):
     eng.close()
 
 
+def c1_problem(cfg):
+    """Rows of the reference's results CSV as committed under tests/golden (normalised X, standardised objective): returned as
+    physical parameters + 8 displacement columns whose mean is the objective (Bayesian.py:140), for CachedCSVSimulator."""
+    from bayesianoptimizer_b200.simulators import DEFAULT_BOUNDS
+    z = np.load(os.path.join(ROOT, "tests", "golden", cfg["golden"]))
+    lo, hi = np.asarray(DEFAULT_BOUNDS, dtype=np.float64).T
+    n = cfg["n"]
+    P = z["X"][:n] * (hi - lo) + lo
+    obj = z["y"][:n] * float(z["y_std"]) + float(z["y_mean"])
+    Y8 = np.repeat(obj[:, None], 8, axis=1)
+    hyper = (np.asarray(z["lengthscale"], dtype=np.float64), float(z["outputscale"]), float(z["noise"]), 0.0)
+    return P, Y8, hyper
+
+
+def c1_optimizer(cfg, out_dir, engine_factory=None, pool=None, **cfg_kw):
+    from bayesianoptimizer_b200.optimizer import BayesianOptimizer, GPConfig
+    from bayesianoptimizer_b200.simulators import DEFAULT_BOUNDS, CachedCSVSimulator
+    P, Y8, hyper = c1_problem(cfg)
+    gpc = GPConfig(seed=cfg["seeds"][0], candidates_pool_size=pool or cfg["pool"], **cfg_kw)
+    kw = {} if engine_factory is None else {"engine_factory": engine_factory}
+    opt = BayesianOptimizer(CachedCSVSimulator(P, Y8), DEFAULT_BOUNDS, out_dir, 0, 1, 1, gp_config=gpc, **kw)
+    for i in range(len(P)):
+        opt._append_observation(P[i], Y8[i], write=False)
+    return opt, hyper
+
+
+def c1_iteration(opt):
+    """One pass of the reference's loop body (Bayesian.py:150-172): refit, suggest, evaluate + record."""
+    gp = opt.fit_gp_model()
+    batch = opt.optimize_acquisition_function(gp)
+    for x in batch:
+        opt.register(x)
+    return batch
+
+
+def cpu_c1_run(cfg, steps=1):
+    """CPU leg of C1: the SAME host loop (drop-in class) with every engine call answered by the NumPy/SciPy oracle
+    (tests/oracle_engine.py), warm-started from the fixture's hyper-parameters like iteration k > 1 of the reference's loop."""
+    import contextlib
+    import io
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_engine import OracleEngine
+    with tempfile.TemporaryDirectory() as tmp:
+        opt, hyper = c1_optimizer(cfg, tmp, engine_factory=OracleEngine)
+        opt._hyper = hyper
+        opt._hyper_fits = 1
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                c1_iteration(opt)
+            ts.append(time.perf_counter() - t0)
+        opt.close()
+    return {"s_per_iter": float(np.mean(ts)), "steps": steps, "threads": os.cpu_count() or 1}
+
+
+def bench_c1(ctx, name, cfg):
+    """C1: one step = one iteration of the reference's BO loop through the drop-in class (host observations in, host
+    suggestion out -- the public call IS the host-buffer path, so `value` and `e2e` time the same calls, the first on the
+    device timeline, the second by wall clock)."""
+    import contextlib
+    import io
+    import tempfile
+    torch = ctx.torch
+    args, world, rank, dev = ctx.args, ctx.world, ctx.rank, ctx.dev
+    n, d = cfg["n"], cfg["d"]
+    tmp = tempfile.mkdtemp(prefix="bo_b200_c1_")
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())
+    opt, _ = c1_optimizer(cfg, tmp)
+    eng = opt._engine_get()
+    peak = eng.fp64_peak_tflops(True, 0.5)
+    # count the LML+gradient evaluations (K7) and their device time: the dominant kernel group of an iteration
+    stats = {"calls": 0, "restarts": 0, "ms": 0.0}
+    inner = eng.lml_grad_batched
+
+    def counted(X, y, thetas, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = inner(X, y, thetas, *a, **k)
+        e1.record(); e1.synchronize()
+        stats["calls"] += 1; stats["restarts"] += int(np.asarray(thetas).reshape(-1, np.asarray(thetas).shape[-1]).shape[0])
+        stats["ms"] += e0.elapsed_time(e1)
+        return out
+    eng.lml_grad_batched = counted
+
+    def timed(fn):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        with quiet():
+            r = fn()
+        torch.cuda.synchronize()
+        return r, (time.perf_counter() - t0) * 1e3
+
+    _, cold_ms = timed(opt.fit_gp_model)                # first refit: 16 screened restarts, the best 4 refined in lock step
+    cold = dict(stats)
+    for _ in range(ctx.W):
+        timed(lambda: c1_iteration(opt))
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
+    for k in stats:
+        stats[k] = 0
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    e0.record()
+    with quiet():
+        for _ in range(args.steps):
+            c1_iteration(opt)
+    e1.record()
+    ctx.barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    warm = dict(stats)
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.barrier()
+    t0 = time.perf_counter()
+    with quiet():
+        for _ in range(args.steps):
+            c1_iteration(opt)
+    torch.cuda.synchronize()
+    e2e_local_ms = (time.perf_counter() - t0) * 1e3
+    ctx.barrier()
+    # phases of one warm iteration + a q = 1000 suggestion (the reference's batch_size, main.py:15: one sweep -> top-K -> FPS)
+    phases = {}
+    gp, phases["fit_gp_model_ms"] = timed(opt.fit_gp_model)
+    _, phases["suggest_q1_ms"] = timed(lambda: opt.suggest(1, gp))
+    timed(lambda: opt.suggest(cfg["q_big"], gp))
+    xs, phases[f"suggest_q{cfg['q_big']}_ms"] = timed(lambda: opt.suggest(cfg["q_big"], gp))
+    phases[f"suggest_q{cfg['q_big']}_distinct"] = int(torch.unique(xs, dim=0).shape[0])
+    _, phases["suggest_q16_kriging_believer_ms"] = timed(lambda: opt.suggest(16, gp))
+    y_std, _, _, _ = opt._model_targets()
+    Xd = opt.train_X.to(dev)
+    _, phases["plain_fit_ms"] = timed(lambda: eng.fit(Xd, y_std.to(dev), "matern52", *opt._hyper[:3]))
+    n_end = int(opt.train_X.shape[0])
+    opt.close()
+    elapsed_ms, e2e_ms, launches = ctx.reduce_times([elapsed_ms, e2e_local_ms, float(launches)])
+    if rank == 0:
+        ms_per_step = elapsed_ms / args.steps
+        evals = warm["restarts"] / args.steps
+        flop = float(n) ** 3                              # per LML+gradient evaluation (DESIGN section 4, K7)
+        achieved = warm["restarts"] * flop / (max(warm["ms"], 1e-9) * 1e-3) * 1e-12
+        line = {
+            "metric": cfg["metric"], "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": ctx.W,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "reference CSV rows (tests/golden), cached-objective simulator",
+            "config": {"workload": cfg["workload"], "n_obs": n, "n_obs_end": n_end, "d": d, "pool": cfg["pool"], "acq": "LogEI",
+                       "parallelism": f"replicas x{world}: pool and hyper-fit restarts sharded, observations replicated",
+                       "l2": "inputs larger than L2: K, L and L^-1 of n=3000 (72 MB each) are rewritten by every LML evaluation"},
+            "e2e": {"value": e2e_ms / args.steps, "unit": "ms",
+                    "h2d_bytes_per_step": int((n * d * 8 + n * 8) * 2 + evals * (d + 2) * 8),
+                    "d2h_bytes_per_step": int(evals * (d + 4) * 8 + 10 * (d + 1) * 8 * 2),
+                    "includes": "the public calls of the reference's loop on host observations: fit_gp_model (H2D X, y; host thetas in, "
+                                "host lml/grad out per L-BFGS trial) + optimize_acquisition_function (D2H suggestion) + register (CSV row)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "bo_lml_grad_batched at R=1 (chol_panel_kernel chain + dgemm_grouped_kernel<64,64> FP64 DMMA updates)",
+                         "peak_source": "FP64 DMMA peak measured live by bo_fp64_peak; MEASURED_PEAKS.json has no FP64 entry",
+                         "flop_per_evaluation": flop, "evaluations_per_step": evals,
+                         "share_of_step": warm["ms"] / max(elapsed_ms, 1e-9),
+                         "note": "rate over the LML+gradient evaluations of the timed steps (CUDA events around each call)"},
+            "hyperfit": {"cold_fit_gp_model_ms": cold_ms, "cold_lml_calls": cold["calls"], "cold_lml_restart_evaluations": cold["restarts"],
+                         "cold_lml_device_ms": cold["ms"], "warm_lml_calls_per_step": warm["calls"] / args.steps,
+                         "warm_lml_device_ms_per_step": warm["ms"] / args.steps,
+                         "host_share_of_cold_fit": 1.0 - cold["ms"] / max(cold_ms, 1e-9),
+                         "note": "theta, the L-BFGS history and the line search live on the host (hyperfit.py); host_share is the part of "
+                                 "the cold fit NOT spent inside bo_lml_grad_batched -- what a device-resident optimiser could remove"},
+            "phases": phases,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_c1_run(cfg)
+            line["cpu_baseline"] = {"value": r["s_per_iter"] * 1e3, "unit": "ms", "cores": r["threads"], "kind": "port",
+                                    "sample": f"{r['steps']} warm iteration of the same loop at n_obs=3000 with the NumPy/SciPy oracle behind "
+                                              f"the class (threaded LAPACK; warm-started from the fixture's hyper-parameters)"}
+        _emit(line)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -778,7 +974,7 @@ def main():
         run_reference(args, cfg)
         return
     ctx = Ctx(args)
-    {"C2": bench_sweep, "C3": bench_sweep, "C4": bench_c4, "C5": bench_c5}[args.config](ctx, args.config, cfg)
+    {"C1": bench_c1, "C2": bench_sweep, "C3": bench_sweep, "C4": bench_c4, "C5": bench_c5}[args.config](ctx, args.config, cfg)
     ctx.finish()
 
 

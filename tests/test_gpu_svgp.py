@@ -57,6 +57,56 @@ def test_svgp_predictive_mean_and_variance(engine, M, d, N, kind):
     assert idx.cpu().tolist() == ti.tolist()
 
 
+@pytest.mark.parametrize("mode,path", [("i8x7", 7), ("i8x8", 8)])
+@pytest.mark.parametrize("M,d,N,kind", [(2048, 5, 20000, o.KERNEL_LINEAR_MATERN52), (1000, 5, 5000, o.KERNEL_LINEAR_MATERN52),
+                                        (300, 5, 9000, o.KERNEL_MATERN52), (640, 16, 4800, o.KERNEL_RBF),
+                                        (257, 3, 100, o.KERNEL_RBF)])
+def test_svgp_sliced_sweep_matches_oracle(engine, mode, path, M, d, N, kind):
+    """The INT8-sliced form of the SVGP sweep: ONE pass of the CTA-pair kernel over the stacked factor
+    [L^-1; Ls^T L^-1] -- var = k** + jitter - ||L^-1 k*||^2 + ||(Ls^T L^-1) k*||^2 (+ noise) -- with the per-candidate guard
+    covering both terms; strict 1e-8 against the oracle's two-solve evaluation (Bayesian7.py:664-682)."""
+    t = _task(M, d, M + d, kind)
+    _load(engine, t)
+    xs = np.random.default_rng(7).standard_normal((N, d))
+    xs[:4] = t.Z[:4]                                              # on top of inducing points: the cancellation case
+    engine.set_sweep_mode(mode)
+    try:
+        assert engine.resolve_sweep_mode(N) == mode
+        vals, idx, mu, var, av = engine.sweep("var", candidates=_cuda(xs), topk=8, return_all=True)
+        assert engine.last_sweep_path() == path
+        flagged = engine.last_sweep_flagged()
+    finally:
+        engine.set_sweep_mode("auto")
+    omu, ovar = o.svgp_predict(t, xs)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+    assert torch.equal(av, var)
+    tv, ti = o.topk(ovar, 8)
+    assert idx.cpu().tolist() == ti.tolist()
+    assert flagged < N // 2                                       # the guard does not simply send the pool to the FP64 pass
+    # same values as the FP64 form of the same handle, to the same tolerance
+    engine.set_sweep_mode("fp64")
+    try:
+        _, _, mu64, var64, _ = engine.sweep("var", candidates=_cuda(xs), topk=8, return_all=True)
+        assert engine.last_sweep_path() == 0
+    finally:
+        engine.set_sweep_mode("auto")
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), mu64.cpu().numpy(), var64.cpu().numpy())
+
+
+def test_svgp_auto_takes_the_sliced_path_for_the_reference_pool(engine):
+    """Bayesian7's shape: M = 2048 inducing points, a 10^4-candidate pool -> AUTO resolves to the sliced form (an SVGP state has
+    no row-split FP64 kernel to prefer for small pools); tiny pools stay on FP64."""
+    t = _task(2048, 5, 11, jitter=1e-4)
+    _load(engine, t)
+    assert engine.resolve_sweep_mode(10_000) == "i8x7"
+    assert engine.resolve_sweep_mode(1_000) == "fp64"
+    xs = np.random.default_rng(3).standard_normal((10_000, 5))
+    _, _, mu, var, _ = engine.sweep("var", candidates=_cuda(xs), topk=0, min_variance=1e-3, return_all=True)
+    assert engine.last_sweep_path() == 7
+    omu, ovar = o.svgp_predict(t, xs, min_variance=1e-3)
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+
+
 def test_svgp_float32_model_settings(engine):
     """The reference trains in float32: jitter 1e-4, min_variance 1e-3; clamp is honoured."""
     t = _task(200, 5, 3, jitter=1e-4)
