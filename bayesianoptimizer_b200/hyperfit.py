@@ -72,7 +72,9 @@ def lbfgs_lockstep(evaluate: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray
         fixed = ((x <= lo) & (g < 0)) | ((x >= hi) & (g > 0))       # active bounds: work in the free subspace
         pg = g.copy()
         pg[fixed] = 0.0
-        active &= np.abs(pg).max(axis=1) > gtol
+        # gtol is the reference's stopping rule: fit_gpytorch_mll hands SciPy's L-BFGS-B (pgtol = 1e-5) the PER-DATUM objective
+        # MLL / n, i.e. |projected gradient of F| <= gtol * fscale on the un-normalised F evaluated here
+        active &= np.abs(pg).max(axis=1) > gtol * max(fscale, 1.0)
         if not active.any():
             break
         # two-loop recursion (ascent direction = H * g), per restart, vectorised over R

@@ -869,7 +869,11 @@ def bench_c1(ctx, name, cfg):
         torch.cuda.synchronize()
         return r, (time.perf_counter() - t0) * 1e3
 
-    _, cold_ms = timed(opt.fit_gp_model)                # first refit: 16 screened restarts, the best 4 refined in lock step
+    _, cold_first_ms = timed(opt.fit_gp_model)          # very first refit: + one-off allocation of the 16-restart LML workspace (3.4 GB)
+    for k in stats:
+        stats[k] = 0
+    opt._hyper, opt._hyper_fits = None, 0               # forget the fit: the same cold 16-restart search again, workspaces in place
+    _, cold_ms = timed(opt.fit_gp_model)                # 16 screened restarts, the best 4 refined in lock step
     cold = dict(stats)
     for _ in range(ctx.W):
         timed(lambda: c1_iteration(opt))
@@ -938,7 +942,8 @@ def bench_c1(ctx, name, cfg):
                          "flop_per_evaluation": flop, "evaluations_per_step": evals,
                          "share_of_step": warm["ms"] / max(elapsed_ms, 1e-9),
                          "note": "rate over the LML+gradient evaluations of the timed steps (CUDA events around each call)"},
-            "hyperfit": {"cold_fit_gp_model_ms": cold_ms, "cold_lml_calls": cold["calls"], "cold_lml_restart_evaluations": cold["restarts"],
+            "hyperfit": {"first_fit_gp_model_ms_with_workspace_allocation": cold_first_ms,
+                         "cold_fit_gp_model_ms": cold_ms, "cold_lml_calls": cold["calls"], "cold_lml_restart_evaluations": cold["restarts"],
                          "cold_lml_device_ms": cold["ms"], "warm_lml_calls_per_step": warm["calls"] / args.steps,
                          "warm_lml_device_ms_per_step": warm["ms"] / args.steps,
                          "host_share_of_cold_fit": 1.0 - cold["ms"] / max(cold_ms, 1e-9),

@@ -237,10 +237,12 @@ int bo_gemm_probe(bo_handle* h, int32_t m, int32_t n, int32_t k, int32_t cfg, in
  * is re-scored on the FP64 DMMA contraction inside the same call -- same outputs, same top-k order;
  * bo_last_sweep_flagged() reports how many (candidates with sigma^2 below ~2e-4 (I8X8) / ~7e-4 (I8X7) of the prior variance:
  * next to training rows).  Eligible models: exact GP of any kernel kind (the linear + Matern kind scales each candidate's
- * operand by its own bound on |k*|) with at least 256 (padded) observations; SVGP handles run the FP64 DMMA path in every mode.
+ * operand by its own bound on |k*|) with at least 256 (padded) observations, and SVGP predictive states (bo_svgp_load): there
+ * the sliced sweep contracts the stacked factor [L^-1; Ls^T L^-1] with the same sliced panel in ONE pass -- the second variance
+ * term ||Ls^T u||^2 = ||(Ls^T L^-1) k*||^2 -- with the guard covering both terms (the FP64 form runs two triangular passes).
  * The pinned modes depend on the model only, so all shards of a pool take the same path (bit-identical values for
- * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates and models with fewer than 512
- * (padded) observations on the FP64 path.  bo_posterior / bo_posterior_multi stay on the FP64 contraction under AUTO
+ * every shard layout); AUTO additionally keeps pools below 2 x SMs x 64 candidates (SVGP states: below SMs / 2 x 64, they have
+ * no row-split FP64 kernel) and models with fewer than 512 (padded) observations on the FP64 path.  bo_posterior / bo_posterior_multi stay on the FP64 contraction under AUTO
  * (model.posterior numerics must not depend on N) and follow a pinned mode.  A sliced sweep synchronises the stream once
  * (the count of flagged candidates is read back). */
 int bo_set_sweep_mode(bo_handle* h, int32_t mode);

@@ -88,3 +88,44 @@ def test_seven_wide_slices_track_eight_narrow_ones_on_reference_data():
     e87, e78, e77 = (_rel(U, kss, var_true) for U in (U87, U78, U77))
     assert e87 <= 1e-9 and e78 <= 2e-9                              # both inside the bar next to clustered rows (sigma^2 ~ 3e-5)
     assert e78 <= 8 * max(e87, e64) and e77 >= 20 * e78             # ~1 bit behind 8 x 7; the 7 x 7-bit form is ~6 bits behind
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("collapsed", [False, True])
+def test_svgp_stacked_factor_one_pass_variance_meets_the_bar(collapsed):
+    """The sliced SVGP sweep contracts [L^-1; B], B = Ls^T L^-1 (formed in FP64 at load time), with ONE sliced panel:
+    var = k** + jitter - ||L^-1 k*||^2 + ||B k*||^2.  Against the extended-precision two-solve evaluation of the same formula
+    (Bayesian7.py:664-682 through gpytorch's whitened strategy) on a task with candidates on top of inducing points: the FP64
+    stacked form and both sliced geometries stay inside 1e-8 -- unlike the rejected k*^T W k* form, B does not square cond(K_uu)."""
+    rng = np.random.default_rng(5)
+    M, d, jitter = 256, 5, 1e-6
+    Z = rng.standard_normal((M, d))
+    Z[40:48] = Z[7] + 1e-3 * rng.standard_normal((8, d))           # a cluster: cond(K_uu) ~ 1e7
+    ls, s2 = rng.uniform(0.8, 2.0, d), 1.3
+    Ls = np.tril(rng.standard_normal((M, M)) * 0.05 / np.sqrt(M / 64)) + np.diag(0.3 + 0.5 * rng.random(M))
+    if collapsed:                # a trained q(u): S << I, the variance next to inducing points is 1e-3 of the prior (strong cancellation)
+        Ls = np.tril(rng.standard_normal((M, M)) * 5e-4) + np.diag(0.05 * (0.5 + rng.random(M)))
+    Xs = np.vstack([rng.standard_normal((192, d)), Z[:32], Z[40:48] + 1e-4, Z[100:124] + 1e-2 * rng.standard_normal((24, d))])
+    K = o.kernel_matrix(Z, Z, o.KERNEL_MATERN52, ls, s2) + jitter * np.eye(M)
+    L = np.linalg.cholesky(K)
+    Li = np.tril(sla.solve_triangular(L, np.eye(M), lower=True, check_finite=False))
+    Ks = o.kernel_matrix(Z, Xs, o.KERNEL_MATERN52, ls, s2)
+    kss = o.prior_variance(Xs, o.KERNEL_MATERN52, s2) + jitter
+    ld = np.longdouble
+    Ul = sla.solve_triangular(L, Ks, lower=True, check_finite=False).astype(ld)
+    Ul = Ul + sla.solve_triangular(L, (Ks.astype(ld) - L.astype(ld) @ Ul).astype(np.float64), lower=True).astype(ld)   # one refinement step
+    Wl = Ls.T.astype(ld) @ Ul
+    var_true = kss.astype(ld) - np.einsum("ij,ij->j", Ul, Ul) + np.einsum("ij,ij->j", Wl, Wl)
+    assert float(var_true.min()) > 0
+    B = Ls.T @ Li                                                   # what svgp_build_b forms with one FP64 GEMM
+    def rel(U, W):
+        var = kss - np.einsum("ij,ij->j", U, U) + np.einsum("ij,ij->j", W, W)
+        return float(np.abs((var - var_true) / var_true).max())
+    e64 = rel(Li @ Ks, B @ Ks)
+    e78 = rel(oz.sliced_matmul_fields(Li, Ks, 7, 8)[0], oz.sliced_matmul_fields(B, Ks, 7, 8)[0])
+    e87 = rel(oz.sliced_matmul_fields(Li, Ks, 8, 7)[0], oz.sliced_matmul_fields(B, Ks, 8, 7)[0])
+    two_pass = rel(Li @ Ks, Ls.T @ (Li @ Ks))
+    assert max(e64, two_pass) <= 1e-8, (e64, two_pass)
+    assert e87 <= 1e-8 and e78 <= 1e-8, (e87, e78, e64)
