@@ -123,17 +123,24 @@ __global__ void rescale_batched_kernel(int np, int d, const Hyper* __restrict__ 
 // rows <= j / columns <= j may hold anything -- a valid entry (i, k > j) is only ever updated with L[i][j] L[k][j],
 // both taken from the still-valid part of the pivot column, so stale values never reach a live entry.  This halves
 // the instructions of a step (the chain of 64 steps is issue-bound: 124 -> ~65 SASS instructions per warp and step).
+// BELOW = true: the CTA also carries 64 rows P of the panel below the diagonal block through the SAME rank-1 updates (the
+// right-looking form of X L^T = P: once column j of L is final, x_j = p_j / L[j][j] and p_k -= x_j L[k][j] for k > j), so the
+// triangular solve costs 16 more FMAs per step instead of a second chain of 64 dependent steps; S then receives X, not L.
+template <bool BELOW>
 __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int lda, double (*S)[NB + 1],
-                                              double (*colS)[NB], int* info, int pivot_base, bool report) {
+                                              double (*colS)[NB], int* info, int pivot_base, bool report,
+                                              const double* __restrict__ P = nullptr, double (*colB)[NB] = nullptr) {
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tk = tid & 15;
     double a[4][4];
+    double bw[BELOW ? 4 : 1][4];
 #pragma unroll
     for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
             const int i = ti + 16 * x, k = tk + 16 * y;
             a[x][y] = (k <= i) ? A[(size_t)i * lda + k] : 0.0;
+            if (BELOW) bw[x][y] = P[(size_t)i * lda + k];
         }
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {            // unrolled: every register index below is static
@@ -143,7 +150,10 @@ __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int 
             double* col = colS[j & 1];
             if (tk == jt) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x) col[ti + 16 * x] = a[x][jb];
+                for (int x = 0; x < 4; ++x) {
+                    col[ti + 16 * x] = a[x][jb];
+                    if (BELOW) colB[j & 1][ti + 16 * x] = bw[x][jb];
+                }
             }
             __syncthreads();
             double dj = col[j];
@@ -156,16 +166,29 @@ __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int 
             const double hj = 0.5 * dj;
             rs = rs * fma(-hj, rs * rs, 1.5);
             rs = rs * fma(-hj, rs * rs, 1.5);
-            double li[4], lk[4];
+            double li[4], lk[4], lb[BELOW ? 4 : 1];
 #pragma unroll
             for (int x = 0; x < 4; ++x) li[x] = col[ti + 16 * x] * rs;
 #pragma unroll
             for (int y = 0; y < 4; ++y) lk[y] = col[tk + 16 * y] * rs;
+            if (BELOW) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) lb[x] = colB[j & 1][ti + 16 * x] * rs;
+            }
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
-                    if (y >= jb) a[x][y] = fma(-li[x], lk[y], a[x][y]);      // column groups left of j are final
+                    if (y >= jb) {                                           // column groups left of j are final
+                        a[x][y] = fma(-li[x], lk[y], a[x][y]);
+                        if (BELOW) bw[x][y] = fma(-lb[x], lk[y], bw[x][y]);
+                    }
+            if (BELOW) {
+                if (tk == jt) {                      // column j of X is final
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) S[ti + 16 * x][j] = lb[x];
+                }
+            } else
             if (tk == jt) {                          // column j is final: park it in S (zero above the diagonal)
                 double sj = dj * rs;
                 sj = fma(0.5 * rs, fma(-sj, sj, dj), sj);          // sqrt(dj), Heron-corrected
@@ -187,21 +210,33 @@ __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int 
 // Replaces the potrf2 + TRSM launches of a block column.
 __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A, int lda, double* __restrict__ Lpark,
                                                          int* __restrict__ info, int pivot_base, size_t slot_stride,
-                                                         int ctas_per_slot) {
+                                                         int ctas_per_slot, int fused) {
     __shared__ double S[NB][NB + 1];
     __shared__ double colS[2][NB];
+    __shared__ double colB[2][NB];
     __shared__ double rdiag[NB];
     const int slot = blockIdx.x / ctas_per_slot, r = blockIdx.x % ctas_per_slot;
     A += slot * slot_stride; Lpark += slot * slot_stride; info += slot;
     const int tid = threadIdx.x;
-    leaf_cholesky(A, lda, S, colS, info, pivot_base, r == 0);
     if (r == 0) {
+        leaf_cholesky<false>(A, lda, S, colS, info, pivot_base, true);
         for (int e = tid; e < NB * NB; e += 256) {
             const int i = e / NB, k = e % NB;
             if (k <= i) Lpark[(size_t)i * lda + k] = S[i][k];
         }
         return;
     }
+    if (fused) {
+        // the rows below ride through the factorisation's own rank-1 updates: one chain of 64 steps instead of two
+        double* Pf = A + (size_t)r * NB * lda;
+        leaf_cholesky<true>(A, lda, S, colS, info, pivot_base, false, Pf, colB);
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int i = e / NB, k = e % NB;
+            Pf[(size_t)i * lda + k] = S[i][k];
+        }
+        return;
+    }
+    leaf_cholesky<false>(A, lda, S, colS, info, pivot_base, false);
     if (tid < NB) rdiag[tid] = 1.0 / S[tid][tid];
     __syncthreads();
     double* P = A + (size_t)r * NB * lda;                  // 64 rows of the panel below the diagonal block
@@ -404,6 +439,11 @@ static int pick_tile(int sm, std::initializer_list<int> dims, long tiles128) {
 // into outer blocks of OB; inside an outer block a panel only updates the remaining columns of that block (K = NB,
 // narrow), and the last panel of the block applies all OB panels to the rest of the matrix at once (K = OB * NB).
 // The K = 64 updates stream C through L2 once per 64 columns (4 flop/B, 20 TFLOP/s); K = 256 quarters that traffic.
+// BO_B200_PANEL_FUSED=0: the two-chain panel (factor the diagonal block, then forward-substitute the rows below) for A/B runs
+int chol_panel_fused() {
+    static int f = [] { const char* e = getenv("BO_B200_PANEL_FUSED"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+    return f;
+}
 static int chol_outer_blocks() {
     static int ob = [] { const char* e = getenv("BO_B200_CHOL_OB"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();
     return ob;
@@ -586,7 +626,7 @@ static int factor_and_pack(bo_handle* h, bool with_alpha, cudaStream_t st) {
     BO_CUDA(h, cudaMemset2DAsync(h->Li, (size_t)ld * 8, 0, (size_t)np * 8, np, st));
     for (int kb = 0; kb < nb; ++kb) {
         double* D = h->Lm + (size_t)kb * NB * ld + kb * NB;
-        chol_panel_kernel<<<nb - kb, 256, 0, st>>>(D, ld, h->Li + (size_t)kb * NB * ld + kb * NB, h->info_dev, kb * NB, 0, nb - kb);
+        chol_panel_kernel<<<nb - kb, 256, 0, st>>>(D, ld, h->Li + (size_t)kb * NB * ld + kb * NB, h->info_dev, kb * NB, 0, nb - kb, chol_panel_fused());
         BO_LAUNCH_CHECK(h);
         if (kb + 1 < nb && (rc = gemm_launch(h, h->plan_launches[kb], st))) return rc;
     }

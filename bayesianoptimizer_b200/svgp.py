@@ -85,6 +85,7 @@ class BatchSVGPPredictor:
         # one stream per task: a 10^4-candidate pool is only 79 blocks of 128 -- less than one wave of the 148 SMs -- so the
         # T task sweeps run concurrently and the block scheduler packs their CTAs onto the free SMs
         self._streams = [torch.cuda.Stream(device=self.device) for _ in self.engines] if self.device.type == "cuda" else None
+        self._pool = None
 
     @property
     def num_tasks(self):
@@ -110,11 +111,22 @@ class BatchSVGPPredictor:
         if not self._streams:
             return [fn(eng) for eng in self.engines]
         cur = torch.cuda.current_stream(self.device)
-        out = []
-        for eng, st in zip(self.engines, self._streams):
+        for st in self._streams:
             st.wait_stream(cur)
+
+        def run(eng, st):
+            torch.cuda.set_device(self.device)          # the current device is per host thread
             with torch.cuda.stream(st):
-                out.append(fn(eng))
+                return fn(eng)
+        if len(self.engines) > 1:
+            # one host thread per task: a sliced sweep reads its count of guard-flagged candidates back (one stream synchronise
+            # per call), which would serialise the T task sweeps if one thread issued them; the C ABI calls release the GIL
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=len(self.engines), thread_name_prefix="bo_svgp_task")
+            out = list(self._pool.map(run, self.engines, self._streams))
+        else:
+            out = [run(self.engines[0], self._streams[0])]
         for st in self._streams:
             cur.wait_stream(st)
         for o in out:                                   # allocated on the side streams, consumed on the current one
@@ -148,6 +160,9 @@ class BatchSVGPPredictor:
         return big[sel], idx_big[sel]
 
     def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         for e in self.engines:
             e.close()
         self.engines = []

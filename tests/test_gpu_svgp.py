@@ -52,7 +52,11 @@ def test_svgp_predictive_mean_and_variance(engine, M, d, N, kind):
     assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
     # the pool scan's score path: dense variance + top-k of it
     vals, idx, m2, v2, av = engine.sweep("var", candidates=_cuda(xs), topk=8, return_all=True)
-    assert torch.equal(v2, var) and torch.equal(av, var)
+    if engine.last_sweep_path() == 0:
+        assert torch.equal(v2, var) and torch.equal(av, var)
+    else:            # AUTO took the sliced one-pass form (M >= 512, pool >= one turn of the CTA pairs): same tolerance as above
+        assert_posterior_close(m2.cpu().numpy(), v2.cpu().numpy(), omu, ovar)
+        assert torch.equal(av, v2)
     tv, ti = o.topk(ovar, 8)
     assert idx.cpu().tolist() == ti.tolist()
 
