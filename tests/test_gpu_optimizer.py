@@ -62,3 +62,30 @@ def test_full_loop_with_hyperparameter_fit(tmp_path):
     assert st.tolist() == [0, 0] and lml[0] >= lml[1] - 1e-6
     assert len(best_disp) == 8 and np.all(np.isfinite(best_params))
     opt.close()
+
+
+def test_large_batches_believer_beyond_16_and_q1000(tmp_path):
+    """The reference's real batch sizes (main.py:15 batch_size=1000; Bayesian.py:105-112 q=batch_size): a Kriging-believer batch of
+    q = 40 (believer_max_q raised: 40 sweeps, 39 appends crossing no refit) picks the same points as the oracle-backed class, and a
+    q = 1000 suggestion (one sweep -> top-K_big -> device FPS, the shape of Bayesian7.py:676-688) returns 1000 distinct pool points
+    identical to the oracle-backed selection."""
+    from bayesianoptimizer_b200.optimizer import BayesianOptimizer, GPConfig
+    from bayesianoptimizer_b200.simulators import DEFAULT_BOUNDS
+    z = np.load(os.path.join(GOLDEN_DIR, "csv_cache_rows.npz"))
+    got = {}
+    for factory, dev, sub in ((None, torch.device("cuda", 0), "gpu"), (OracleEngine, torch.device("cpu"), "cpu")):
+        cfg = GPConfig(candidates_pool_size=6_000, num_restarts=4, refine_iters=0, fit_hyperparameters=False,
+                       lengthscale=[0.5, 0.4, 0.6, 0.8, 0.7], outputscale=1.3, noise=1e-3, seed=5, believer_max_q=40)
+        opt = BayesianOptimizer(_sim(), DEFAULT_BOUNDS, str(tmp_path / sub), 0, 1, 40, gp_config=cfg, engine_factory=factory, device=dev)
+        for i in range(150):
+            opt._append_observation(z["params"][i], z["outputs"][i], write=False)
+        gp = opt.fit_gp_model()
+        kb = opt.suggest(40, gp).cpu().numpy()
+        assert kb.shape == (40, 5) and len(np.unique(kb.round(12), axis=0)) == 40
+        gp = opt.fit_gp_model()                                  # drop the 39 believer rows again
+        big = opt.suggest(1000, gp).cpu().numpy()
+        assert big.shape == (1000, 5) and len(np.unique(big, axis=0)) == 1000
+        got[sub] = (kb, big)
+        opt.close()
+    assert np.array_equal(got["gpu"][0], got["cpu"][0])
+    assert np.array_equal(got["gpu"][1], got["cpu"][1])
