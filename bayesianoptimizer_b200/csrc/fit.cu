@@ -129,7 +129,7 @@ __global__ void rescale_batched_kernel(int np, int d, const Hyper* __restrict__ 
 template <bool BELOW>
 __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int lda, double (*S)[NB + 1],
                                               double (*colS)[NB], int* info, int pivot_base, bool report,
-                                              const double* __restrict__ P = nullptr, double (*colB)[NB] = nullptr) {
+                                              const double* __restrict__ P = nullptr, double (*colB)[NB] = nullptr, int kpre = 0) {
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tk = tid & 15;
     double a[4][4];
@@ -142,6 +142,40 @@ __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int 
             a[x][y] = (k <= i) ? A[(size_t)i * lda + k] : 0.0;
             if (BELOW) bw[x][y] = P[(size_t)i * lda + k];
         }
+    // LEFT-LOOKING inside an outer block (kpre > 0): the kpre columns to the left of this block column (the earlier panels of the
+    // outer block, final) have not been applied to it -- no narrow K = 64 GEMM launch between two panels -- so this CTA subtracts
+    // their product from its copy of the diagonal block and from its own rows first: D -= Dl Dl^T, P -= Pl Dl^T with
+    // Dl = A[:, -kpre:0), Pl = P[:, -kpre:0).  Chunks of 32 columns are staged k-major in S (unused until a column is final).
+    if (kpre > 0) {
+        double (*T0)[NB + 1] = S;                       // [32][65]: Dl chunk, T0[k][row]
+        double (*T1)[NB + 1] = S + 32;                  // [32][65]: Pl chunk
+        for (int k0 = -kpre; k0 < 0; k0 += 32) {
+            __syncthreads();
+            for (int e = tid; e < NB * 32; e += 256) {
+                const int row = e >> 5, k = e & 31;
+                const ptrdiff_t off = (ptrdiff_t)row * lda + k0 + k;        // k0 < 0: columns left of the block
+                T0[k][row] = A[off];
+                if (BELOW) T1[k][row] = P[off];
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                double dI[4], dK[4], pI[BELOW ? 4 : 1];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) { dI[x] = T0[k][ti + 16 * x]; if (BELOW) pI[x] = T1[k][ti + 16 * x]; }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) dK[y] = T0[k][tk + 16 * y];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        a[x][y] = fma(-dI[x], dK[y], a[x][y]);
+                        if (BELOW) bw[x][y] = fma(-pI[x], dK[y], bw[x][y]);
+                    }
+            }
+        }
+        __syncthreads();                                 // S is free again before the first finished column lands in it
+    }
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {            // unrolled: every register index below is static
 #pragma unroll 1
@@ -210,7 +244,7 @@ __device__ __forceinline__ void leaf_cholesky(const double* __restrict__ A, int 
 // Replaces the potrf2 + TRSM launches of a block column.
 __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A, int lda, double* __restrict__ Lpark,
                                                          int* __restrict__ info, int pivot_base, size_t slot_stride,
-                                                         int ctas_per_slot, int fused) {
+                                                         int ctas_per_slot, int fused, int kpre) {
     __shared__ double S[NB][NB + 1];
     __shared__ double colS[2][NB];
     __shared__ double colB[2][NB];
@@ -219,7 +253,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A,
     A += slot * slot_stride; Lpark += slot * slot_stride; info += slot;
     const int tid = threadIdx.x;
     if (r == 0) {
-        leaf_cholesky<false>(A, lda, S, colS, info, pivot_base, true);
+        leaf_cholesky<false>(A, lda, S, colS, info, pivot_base, true, nullptr, nullptr, kpre);
         for (int e = tid; e < NB * NB; e += 256) {
             const int i = e / NB, k = e % NB;
             if (k <= i) Lpark[(size_t)i * lda + k] = S[i][k];
@@ -229,7 +263,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A,
     if (fused) {
         // the rows below ride through the factorisation's own rank-1 updates: one chain of 64 steps instead of two
         double* Pf = A + (size_t)r * NB * lda;
-        leaf_cholesky<true>(A, lda, S, colS, info, pivot_base, false, Pf, colB);
+        leaf_cholesky<true>(A, lda, S, colS, info, pivot_base, false, Pf, colB, kpre);
         for (int e = tid; e < NB * NB; e += 256) {
             const int i = e / NB, k = e % NB;
             Pf[(size_t)i * lda + k] = S[i][k];
@@ -444,6 +478,14 @@ int chol_panel_fused() {
     static int f = [] { const char* e = getenv("BO_B200_PANEL_FUSED"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
     return f;
 }
+// BO_B200_CHOL_LEFT=0: right-looking inside the outer blocks (a narrow K = 64 GEMM launch after every panel) for A/B runs
+int chol_left_looking() {
+    static int f = [] { const char* e = getenv("BO_B200_CHOL_LEFT"); return (e ? (atoi(e) != 0 ? 1 : 0) : 1) && chol_panel_fused(); }();
+    return f;
+}
+static int chol_outer_blocks();
+// columns of the outer block to the left of block column kb that its panel kernel applies itself (left-looking form)
+int chol_panel_kpre(int kb) { return chol_left_looking() ? (kb % chol_outer_blocks()) * NB : 0; }
 static int chol_outer_blocks() {
     static int ob = [] { const char* e = getenv("BO_B200_CHOL_OB"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();
     return ob;
@@ -454,6 +496,7 @@ static void add_trailing_update(GemmBatch& g, double* Lm, int ld, int np, int kb
     const int r0 = (kb + 1) * NB;
     double* C = Lm + (size_t)r0 * ld + r0;
     if (kb + 1 < oend) {
+        if (chol_left_looking()) return;                             // the later panels of the outer block apply panel kb themselves
         double* P = Lm + (size_t)r0 * ld + kb * NB;                  // panel kb below its diagonal block
         g.add(P, ld, P, ld, C, ld, np - r0, oend * NB - r0, NB, -1.0, 1.0, /*transB=*/1, GEMM_LOWER_C);
     } else if (r0 < np) {
@@ -626,7 +669,7 @@ static int factor_and_pack(bo_handle* h, bool with_alpha, cudaStream_t st) {
     BO_CUDA(h, cudaMemset2DAsync(h->Li, (size_t)ld * 8, 0, (size_t)np * 8, np, st));
     for (int kb = 0; kb < nb; ++kb) {
         double* D = h->Lm + (size_t)kb * NB * ld + kb * NB;
-        chol_panel_kernel<<<nb - kb, 256, 0, st>>>(D, ld, h->Li + (size_t)kb * NB * ld + kb * NB, h->info_dev, kb * NB, 0, nb - kb, chol_panel_fused());
+        chol_panel_kernel<<<nb - kb, 256, 0, st>>>(D, ld, h->Li + (size_t)kb * NB * ld + kb * NB, h->info_dev, kb * NB, 0, nb - kb, chol_panel_fused(), chol_panel_kpre(kb));
         BO_LAUNCH_CHECK(h);
         if (kb + 1 < nb && (rc = gemm_launch(h, h->plan_launches[kb], st))) return rc;
     }

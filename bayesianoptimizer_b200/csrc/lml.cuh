@@ -342,7 +342,7 @@ static int lml_run_slots(bo_handle* h, LmlBatch* b, int s0, int Sa, int n, int d
     BO_CUDA(h, cudaMemsetAsync(Li, 0, (size_t)Sa * mat * sizeof(double), st));
     for (int kb = 0; kb < nb; ++kb) {
         const size_t off = (size_t)kb * NB * ld + kb * NB;
-        chol_panel_kernel<<<Sa * (nb - kb), 256, 0, st>>>(Lm + off, ld, Li + off, b->info + s0, kb * NB, mat, nb - kb, chol_panel_fused());
+        chol_panel_kernel<<<Sa * (nb - kb), 256, 0, st>>>(Lm + off, ld, Li + off, b->info + s0, kb * NB, mat, nb - kb, chol_panel_fused(), chol_panel_kpre(kb));
         BO_LAUNCH_CHECK(h);
         if (kb + 1 < nb && (rc = lml_gemm(h, b, kb, s0, Sa, st))) return rc;
     }
