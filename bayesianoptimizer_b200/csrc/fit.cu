@@ -478,9 +478,12 @@ int chol_panel_fused() {
     static int f = [] { const char* e = getenv("BO_B200_PANEL_FUSED"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
     return f;
 }
-// BO_B200_CHOL_LEFT=0: right-looking inside the outer blocks (a narrow K = 64 GEMM launch after every panel) for A/B runs
+// BO_B200_CHOL_LEFT=1 (A/B only, OFF by default): left-looking inside the outer blocks -- no narrow K = 64 GEMM launch after a panel,
+// the next panel kernels apply it themselves.  Measured slower (refit 4.13 -> 4.66 ms at n = 4096, n = 3000 LML 3.08 -> 3.51 ms, C5
+// 103.7 -> 108.7 ms): every CTA of a panel launch repeats the update of the diagonal block, and 64 x 64 x 64m products on plain FP64
+// FMAs from shared memory cost more than the 12-23 us grouped-DMMA launches they replace.
 int chol_left_looking() {
-    static int f = [] { const char* e = getenv("BO_B200_CHOL_LEFT"); return (e ? (atoi(e) != 0 ? 1 : 0) : 1) && chol_panel_fused(); }();
+    static int f = [] { const char* e = getenv("BO_B200_CHOL_LEFT"); return (e ? (atoi(e) != 0 ? 1 : 0) : 0) && chol_panel_fused(); }();
     return f;
 }
 static int chol_outer_blocks();
