@@ -353,9 +353,23 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
     Li += blockIdx.z * mat_stride; v += (size_t)blockIdx.z * np; z += (size_t)blockIdx.z * np;      // slot
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= np) return;
-    const double* a = Li + (size_t)row * ld;
-    double s = 0.0;
-    for (int j = lane; j <= row; j += 32) s = fma(a[j], v[j], s);
+    // 16-byte loads, four independent pairs of accumulators: 2 KB of the row in flight per warp (the first version issued one
+    // 8-byte load per lane and iteration: 36 us for the 71 MB of an n = 4224 factor, 2 TB/s; rows and vectors are 16-byte aligned)
+    const double2* a2 = reinterpret_cast<const double2*>(Li + (size_t)row * ld);
+    const double2* v2 = reinterpret_cast<const double2*>(v);
+    const int npair = (row + 1) >> 1;                   // pairs (2p, 2p + 1) entirely inside j <= row
+    double sx[4] = {0.0, 0.0, 0.0, 0.0}, sy[4] = {0.0, 0.0, 0.0, 0.0};
+    int p = lane;
+    for (; p + 96 < npair; p += 128) {
+        double2 av[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { av[u] = a2[p + 32 * u]; vv[u] = v2[p + 32 * u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sx[u] = fma(av[u].x, vv[u].x, sx[u]); sy[u] = fma(av[u].y, vv[u].y, sy[u]); }
+    }
+    for (; p < npair; p += 32) { const double2 av = a2[p], vv = v2[p]; sx[0] = fma(av.x, vv.x, sx[0]); sy[0] = fma(av.y, vv.y, sy[0]); }
+    double s = ((sx[0] + sx[1]) + (sx[2] + sx[3])) + ((sy[0] + sy[1]) + (sy[2] + sy[3]));
+    if (lane == 0 && !(row & 1)) s = fma(Li[(size_t)row * ld + row], v[row], s);       // odd count: the diagonal element is left over
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) z[row] = s;
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restr
     const int chunk = ((rows + TRMVT_SPLITS - 1) / TRMVT_SPLITS + 7) & ~7;
     const int r0 = j0 + blockIdx.y * chunk, r1 = min(np, r0 + chunk);
     double s = 0.0;
-    for (int i = r0 + ty; i < r1; i += 8)
+    for (int i = r0 + ty; i < r1; i += 8)          // (an explicit four-rows-in-flight form of this loop measured 50 % slower)
         if (i >= j) s = fma(Li[(size_t)i * ld + j], z[i], s);
     red[ty][tx] = s;
     __syncthreads();

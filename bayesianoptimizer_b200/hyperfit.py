@@ -50,20 +50,26 @@ def log_prior_and_grad(theta: np.ndarray, d: int, prior: Optional[str]) -> Tuple
 
 def lbfgs_lockstep(evaluate: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray]], theta0: np.ndarray,
                    lo: np.ndarray, hi: np.ndarray, maxiter: int = 50, history: int = 8, gtol: float = 1e-5,
-                   ftol: float = 1e-9, fscale: float = 1.0):
+                   ftol: float = 1e-9, fscale: float = 1.0, memory: Optional[dict] = None):
     """Maximise F over the box [lo, hi] from R starts at once.  ``evaluate(thetas[R,p]) -> (F[R], G[R,p])``;
     a failed evaluation returns F = -inf.  Returns (theta[R,p], F[R], n_evaluations).
 
     ``fscale`` is the natural scale of F (the number of observations for an un-normalised log marginal likelihood --
     the reference optimises MLL / n): the first, curvature-free step is at most 10 / fscale long per
     unit gradient.  Without it a warm start (|g| ~ 1 next to an optimum whose curvature is ~ n) overshoots by three
-    orders of magnitude and spends 8 batched evaluations backtracking."""
+    orders of magnitude and spends 8 batched evaluations backtracking.
+
+    ``memory``: a dict the caller keeps between calls on a slowly changing objective (the BO loop's warm refit: one more
+    observation per iteration).  The curvature pairs (s, y) of the previous call seed this one, so the first step is already a
+    quasi-Newton step instead of a short steepest-ascent one, and the pairs of this call are left in it for the next."""
     x = np.clip(np.array(theta0, dtype=np.float64, copy=True), lo, hi)
     R, p = x.shape
     f, g = evaluate(x)
     f = np.where(np.isfinite(f), f, -np.inf)
     nev = 1
     S, Y = [], []                      # each [R, p]
+    if memory is not None and memory.get("shape") == (R, p):
+        S, Y = [a.copy() for a in memory["S"]], [a.copy() for a in memory["Y"]]
     active = np.isfinite(f)
     for _ in range(maxiter):
         if not active.any():
@@ -135,11 +141,13 @@ def lbfgs_lockstep(evaluate: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray
         df = f_new - f
         x, f, g = x_new, f_new, g_new
         active &= ~(moved & (np.abs(df) <= ftol * np.maximum(1.0, np.abs(f))))
+    if memory is not None:
+        memory.update(shape=(R, p), S=[a.copy() for a in S], Y=[a.copy() for a in Y])
     return x, f, nev
 
 
 def fit_map(engine, X, y, kernel: str, theta0: np.ndarray, lo: np.ndarray, hi: np.ndarray, prior: Optional[str] = None,
-            maxiter: int = 50, mean: float = 0.0):
+            maxiter: int = 50, mean: float = 0.0, memory: Optional[dict] = None):
     """Lock-step multi-restart MAP fit.  Returns (best theta, best objective, all thetas, all objectives, n_evals)."""
     d = int(X.shape[1])            # theta = log lengthscale[d], log outputscale, log noise [, log linear variance]
 
@@ -155,6 +163,6 @@ def fit_map(engine, X, y, kernel: str, theta0: np.ndarray, lo: np.ndarray, hi: n
         G[bad] = 0.0
         return F, G
 
-    th, F, nev = lbfgs_lockstep(evaluate, theta0, lo, hi, maxiter=maxiter, fscale=float(X.shape[0]))
+    th, F, nev = lbfgs_lockstep(evaluate, theta0, lo, hi, maxiter=maxiter, fscale=float(X.shape[0]), memory=memory)
     best = int(np.argmax(F))
     return th[best], float(F[best]), th, F, nev

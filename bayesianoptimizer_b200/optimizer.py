@@ -60,6 +60,7 @@ class GPConfig:
     hyper_refine_warm: int = 1           # ... once a previous fit warm-starts the search (the reference refits from one start)
     hyper_full_every: int = 8            # every k-th refit repeats the full screened multi-start (guards against a stale local optimum)
     hyper_maxiter: int = 50              # lock-step L-BFGS iterations
+    hyper_warm_curvature: bool = True    # warm refits also inherit the previous refit's L-BFGS curvature pairs
     hyper_prior: Optional[str] = "auto"  # "auto": botorch defaults (rbf -> lognormal, matern52 -> gamma); None = max. likelihood
     lengthscale: Optional[Sequence[float]] = None   # fixed / initial ARD lengthscales (unit cube)
     outputscale: float = 1.0
@@ -142,6 +143,7 @@ class BayesianOptimizer:
         self._engine = None
         self._hyper = None            # (lengthscale[d], outputscale, noise, linear variance) carried between refits (warm start)
         self._hyper_fits = 0          # hyper-parameter refits so far (every hyper_full_every-th one is a full multi-start)
+        self._lbfgs_memory = {}       # curvature pairs carried between warm refits (hyperfit.lbfgs_lockstep)
         self._y_mean, self._y_std = 0.0, 1.0
         self._suggest_count = 0
         self._rng = np.random.default_rng(self.config.seed)
@@ -330,8 +332,14 @@ class BayesianOptimizer:
                 thetas[1:, d + 2] = self._rng.uniform(math.log(1e-2), math.log(1e1), size=R - 1)
         unpack = lambda t: (np.exp(t[:d]), float(np.exp(t[d])), float(np.exp(t[d + 1])), float(np.exp(t[d + 2])) if lin else 0.0)
         if R == 1:                                    # nothing to screen: refine the (warm) start directly
-            th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas, lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter))
+            # the L-BFGS curvature pairs survive from one warm refit to the next (the objective gains one observation per
+            # iteration): the first step is a quasi-Newton step, not a short steepest-ascent one
+            if self._lbfgs_memory.get("key") != (cfg.kernel, len(th0)):
+                self._lbfgs_memory = {"key": (cfg.kernel, len(th0))}
+            th, F, _, _, _ = fit_map(eng, X, y, cfg.kernel, thetas, lo, hi, prior=prior, maxiter=int(cfg.hyper_maxiter),
+                                     memory=self._lbfgs_memory if cfg.hyper_warm_curvature else None)
             return unpack(th if np.isfinite(F) else th0)
+        self._lbfgs_memory = {}                       # a full multi-start may land in another basin: its curvature starts afresh
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             from .dist import sharded_lml_grad                    # restarts are independent: shard the screening over the ranks
