@@ -111,6 +111,33 @@ def test_svgp_auto_takes_the_sliced_path_for_the_reference_pool(engine):
     assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
 
 
+def test_svgp_sliced_sweep_guard_rescoring_on_collapsed_posterior(engine):
+    """A trained q(u) with S << I: next to inducing points the variance is a cancellation down to the jitter level, the guard
+    flags those candidates and the FP64 two-pass kernel re-scores them at their pool positions (idx_map) -- values and top-k
+    order are those of the oracle."""
+    M, d = 600, 5
+    t = _task(M, d, 21, jitter=1e-6)
+    t.noise = 0.0
+    t.Ls = np.tril(np.random.default_rng(2).standard_normal((M, M)) * 1e-5) + np.eye(M) * 1e-3
+    _load(engine, t)
+    rng = np.random.default_rng(4)
+    xs = np.vstack([t.Z[:200] + 1e-4 * rng.standard_normal((200, d)), t.Z[200:300] + 3e-2 * rng.standard_normal((100, d)),
+                    rng.standard_normal((9700, d))])
+    engine.set_sweep_mode("i8x7")
+    try:
+        vals, idx, mu, var, _ = engine.sweep("var", candidates=_cuda(xs), topk=8, return_all=True)
+        assert engine.last_sweep_path() == 7
+        flagged = engine.last_sweep_flagged()
+    finally:
+        engine.set_sweep_mode("auto")
+    assert 100 <= flagged < 5000, flagged
+    omu, ovar = o.svgp_predict(t, xs)
+    # same tolerance as the FP64 form earns on this state: 1e-8 relative with the 64-ulp floor of tests/test_gpu_i8_refdata.py
+    assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar, var_abs=64 * np.finfo(np.float64).eps * t.outputscale * 4)
+    tv, ti = o.topk(ovar, 8)
+    assert idx.cpu().tolist() == ti.tolist()
+
+
 def test_svgp_float32_model_settings(engine):
     """The reference trains in float32: jitter 1e-4, min_variance 1e-3; clamp is honoured."""
     t = _task(200, 5, 3, jitter=1e-4)
