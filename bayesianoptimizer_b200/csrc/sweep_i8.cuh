@@ -54,7 +54,8 @@ struct I8Smem {
     static constexpr int OFF_ACQ   = OFF_TKI + BO_MAX_TOPK * 8;
     static constexpr int OFF_CMASK = OFF_ACQ + I8_BN * 8;
     static constexpr int OFF_SOB   = OFF_CMASK + 32;
-    static constexpr int OFF_X     = (OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4 + 127) / 128 * 128;
+    static constexpr int OFF_TAB   = (OFF_SOB + (BO_MAX_DIM * BO_SOBOL_BITS + BO_MAX_DIM) * 4 + 127) / 128 * 128;   // 2^(j/16), j < 16 (exp_neg_fast)
+    static constexpr int OFF_X     = OFF_TAB + 128;
     // builders' X~ / alpha staging: two buffers of XCH rows, as many rows as the 227 KB budget leaves
     static constexpr int X_ROW     = (DP + 2 + 1) * 8;
     static constexpr int X_FREE    = 232448 - OFF_X;
@@ -316,6 +317,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
     unsigned* cmask = reinterpret_cast<unsigned*>(smem + SM::OFF_CMASK);
     uint32_t* dirs  = reinterpret_cast<uint32_t*>(smem + SM::OFF_SOB);
     uint32_t* shift = dirs + BO_MAX_DIM * BO_SOBOL_BITS;
+    double* exp_tab = reinterpret_cast<double*>(smem + SM::OFF_TAB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < BO_MAX_TOPK) { tkv[tid] = -INFINITY; tki[tid] = IDX_EMPTY; }
+    if (tid >= 64 && tid < 80) { const double t16[16] = BO_EXP2_16_TABLE; exp_tab[tid - 64] = t16[tid - 64]; }
     if (a.sobol) {
         for (int e = tid; e < DP * BO_SOBOL_BITS; e += I8_THREADS)
             dirs[e] = a.sobol->direction[e / BO_SOBOL_BITS][e % BO_SOBOL_BITS];
@@ -413,7 +416,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) sweep_i8_kernel(const SweepArgs
                             double sq = 0.0;
 #pragma unroll
                             for (int k = 0; k < DP; ++k) { const double df = __dsub_rn(xc[gi][k], x[k]); sq = fma(df, df, sq); }
-                            const double v = kernel_value_t<KIND>(sq, a.hyp.outputscale);
+                            // (the lean square root / table exponential of the CTA-pair kernel's build: this kernel is build-bound at the
+                            // small n it serves -- four builder warps against 20 stages of MMAs per block at n = 512)
+                            const double v = kernel_value_fast_t<KIND>(sq, a.hyp.outputscale, exp_tab);
                             kv[gi][r] = (j < a.n) ? v : 0.0;
                         }
                         mu0 = fma(kv[0][r], al, mu0); mu1 = fma(kv[1][r], al, mu1);
