@@ -20,9 +20,9 @@ struct LmlBatch {
     std::vector<GemmProblem> probs; std::vector<GemmLaunch> launches; GemmProblem* plan_dev = nullptr;
     // slot groups run their (panel -> SYRK -> panel ...) chains on separate streams, so one group's latency-bound panel
     // kernels hide behind another group's trailing updates
-    static constexpr int MAX_GROUPS = 4;
-    cudaStream_t gstream[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev = nullptr, join_ev[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int MAX_GROUPS = 8;
+    cudaStream_t gstream[MAX_GROUPS] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_GROUPS] = {};
 };
 
 static void lml_batch_free(LmlBatch* b) {
