@@ -480,11 +480,11 @@ __global__ void pad_identity_kernel(double* __restrict__ Lm, double* __restrict_
 
 __global__ void __launch_bounds__(1024) append_finalize_kernel(int n, int np, int ld, Hyper hyp, const double* __restrict__ x, int d,
                                                                double y, int believer, const double* __restrict__ kv,
-                                                               const double* __restrict__ l, const double* __restrict__ u,
+                                                               const double* __restrict__ l, const double* __restrict__ upart, int splits,
                                                                double* __restrict__ Lm, double* __restrict__ Li,
                                                                double* __restrict__ alpha, double* __restrict__ Xs,
                                                                double* __restrict__ Xraw, double* __restrict__ yv,
-                                                               int* __restrict__ info) {
+                                                               double* __restrict__ Lp, int* __restrict__ info) {
     __shared__ double red[2][32];
     __shared__ double bc[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -513,14 +513,29 @@ __global__ void __launch_bounds__(1024) append_finalize_kernel(int n, int np, in
     const double lam = sqrt(lam2), ilam = 1.0 / lam;
     const double ynew = believer ? hyp.mean + ka : y;
     const double znew = (ynew - hyp.mean - ka) * ilam;
+    // u = L^-T l arrives as row-split partial sums (added in ascending split order, as trmv_reduce_kernel does); the new row of
+    // L^-1 also goes straight into its place in the packed tiles of the FP64 sweep (pack_linv_kernel's layout) -- no separate
+    // reduction and block-row repack launches on a chain whose cost is launch latency
+    constexpr int KCH = SW_BM / SW_BK;
+    const int ib = n / SW_BM, r = n % SW_BM;
+    double* prow = Lp + (size_t)ib * (ib + 1) / 2 * KCH * SW_TILE;
+    auto packed = [&](int j) -> double& {
+        const int kc = j / SW_BK, k = j % SW_BK;
+        return prow[(size_t)kc * SW_TILE + ((r >> 3) * (SW_BK / 8) + (k >> 3)) * 64 + ((r & 7) * 4 + (k & 3)) * 2 + ((k & 7) >> 2)];
+    };
     for (int j = tid; j < n; j += 1024) {
+        double uj = 0.0;
+        for (int sp = 0; sp < splits; ++sp) uj += upart[(size_t)sp * np + j];
+        const double li = -uj * ilam;
         Lm[(size_t)n * ld + j] = l[j];
-        Li[(size_t)n * ld + j] = -u[j] * ilam;
-        alpha[j] = fma(-u[j] * ilam, znew, alpha[j]);
+        Li[(size_t)n * ld + j] = li;
+        packed(j) = li;
+        alpha[j] = fma(li, znew, alpha[j]);
     }
     if (tid == 0) {
         Lm[(size_t)n * ld + n] = lam;
         Li[(size_t)n * ld + n] = ilam;
+        packed(n) = ilam;
         alpha[n] = znew * ilam;
         yv[n] = ynew;
     }
@@ -534,6 +549,7 @@ __global__ void __launch_bounds__(1024) append_finalize_kernel(int n, int np, in
 // kernels defined in fit.cu, re-declared here through small host wrappers
 int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st);
 int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st);
+int launch_trmv_lower_t_partial(bo_handle* h, const double* z, const double** part, int* splits, cudaStream_t st);
 
 template <int DP>
 static int launch_kq1(bo_handle* h, const double* x, double* kv, cudaStream_t st) {
@@ -549,7 +565,8 @@ int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, c
     BO_CUDA(h, cudaSetDevice(h->device));
     int rc;
     const int np_before = h->np;
-    if (h->n == h->np) {
+    const bool opened = h->n == h->np;
+    if (opened) {
         // open a new padded block row: identity on the diagonal, zeros elsewhere
         const int np_new = h->np + PAD;
         if ((rc = ensure_capacity(h, np_new, st))) return rc;
@@ -562,13 +579,15 @@ int append_impl(bo_handle* h, const double* x_dev, double y, int use_believer, c
     double* kv = h->qbuf; double* l = kv + h->np; double* u = l + h->np;
     if ((rc = BO_DISPATCH_DP(h->dp, launch_kq1, h, x_dev, kv, st))) return rc;
     if ((rc = launch_trmv_lower(h, kv, l, st))) return rc;
-    if ((rc = launch_trmv_lower_t(h, l, u, 0, st))) return rc;
+    const double* upart = nullptr; int splits = 0;
+    if ((rc = launch_trmv_lower_t_partial(h, l, &upart, &splits, st))) return rc;
     BO_CUDA(h, cudaMemsetAsync(h->info_dev, 0, sizeof(int), st));
-    append_finalize_kernel<<<1, 1024, 0, st>>>(h->n, h->np, h->cap_np, h->hyp, x_dev, h->d, y, use_believer, kv, l, u, h->Lm, h->Li,
-                                              h->alpha, h->Xs, h->Xraw, h->yv, h->info_dev);
+    // a block row opened by this call is packed once as a whole (identity rows); after that each append writes its own row
+    if (opened && (rc = pack_row_block(h, h->n / SW_BM, st))) return rc;
+    append_finalize_kernel<<<1, 1024, 0, st>>>(h->n, h->np, h->cap_np, h->hyp, x_dev, h->d, y, use_believer, kv, l, upart, splits, h->Lm,
+                                              h->Li, h->alpha, h->Xs, h->Xraw, h->yv, h->Lp, h->info_dev);
     BO_LAUNCH_CHECK(h);
     BO_CUDA(h, cudaMemcpyAsync(h->info_host, h->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    if ((rc = pack_row_block(h, h->n / SW_BM, st))) return rc;
     BO_CUDA(h, cudaStreamSynchronize(st));
     if (*h->info_host != 0) {
         h->err = "bo_append: bordered matrix not positive definite (duplicate point with zero noise?)";

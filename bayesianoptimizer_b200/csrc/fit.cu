@@ -732,6 +732,14 @@ int launch_trmv_lower(bo_handle* h, const double* v, double* z, cudaStream_t st)
 int launch_trmv_lower_t(bo_handle* h, const double* z, double* out, int accumulate, cudaStream_t st) {
     return trmv_lower_t_m(h, h->Li, z, out, accumulate, st);
 }
+// the row-split partial sums of L^-T z only (h->Tw: [splits][np]); the caller adds the splits in ascending order itself
+// (bo_append folds that reduction into its finalize kernel: one launch less on a chain of launch latencies)
+int launch_trmv_lower_t_partial(bo_handle* h, const double* z, const double** part, int* splits, cudaStream_t st) {
+    trmv_lower_t_kernel<<<dim3(h->np / 32, TRMVT_SPLITS), 256, 0, st>>>(h->Li, h->cap_np, h->np, z, h->Tw, 0);
+    BO_LAUNCH_CHECK(h);
+    *part = h->Tw; *splits = TRMVT_SPLITS;
+    return 0;
+}
 
 int pack_row_block(bo_handle* h, int ib, cudaStream_t st) {
     dim3 grid(h->np / SW_BK, 1);
