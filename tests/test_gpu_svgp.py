@@ -242,3 +242,33 @@ def test_svgp_per_dimension_linear_variance(engine):
     mu, var = engine.posterior(_cuda(xs))
     omu, ovar = o.svgp_predict(t, xs)
     assert_posterior_close(mu.cpu().numpy(), var.cpu().numpy(), omu, ovar)
+
+
+def test_svgp_sliced_state_survives_release_and_mode_changes(engine):
+    """bo_release_workspace drops the sliced operand pack (re-sliced on demand) but not the model state B = Ls^T L^-1; an exact fit in
+    between returns the handle to the exact mode and a later bo_svgp_load rebuilds B: the sliced values are bit-identical each time."""
+    t = _task(700, 5, 33, jitter=1e-5)
+    xs = _cuda(np.random.default_rng(9).standard_normal((6000, 5)))
+
+    def sliced():
+        engine.set_sweep_mode("i8x7")
+        try:
+            out = engine.sweep("var", candidates=xs, topk=4, return_all=True)
+            assert engine.last_sweep_path() == 7
+        finally:
+            engine.set_sweep_mode("auto")
+        return out[3].clone(), out[1].clone()
+
+    _load(engine, t)
+    v0, i0 = sliced()
+    engine.release_workspace()
+    v1, i1 = sliced()
+    assert torch.equal(v0, v1) and torch.equal(i0, i1)
+    X, y = synth_problem(300, 5, 1, 2)
+    engine.fit(_cuda(X), _cuda(y), "matern52", 0.6, 1.0, 1e-2)             # exact mode in between (other n, other factor)
+    engine.sweep("ei", 0.5, candidates=xs, topk=1)
+    _load(engine, t)
+    v2, i2 = sliced()
+    assert torch.equal(v0, v2) and torch.equal(i0, i2)
+    omu, ovar = o.svgp_predict(t, xs.cpu().numpy())
+    np.testing.assert_allclose(v2.cpu().numpy(), ovar, rtol=1e-8)
