@@ -836,7 +836,12 @@ int sweep_impl(bo_handle* h, int acq_kind, double best_f, double beta, double mi
     a.n = h->n; a.np = h->np; a.d = h->d; a.hyp = h->hyp;
     a.acq = acq_kind; a.best_f = best_f; a.sqrt_beta = sqrt(beta); a.min_var = min_var;
     a.topk = topk; a.mean_out = mean_dev; a.var_out = var_dev; a.acq_out = acq_dev;
-    { const char* f = getenv("BO_B200_SWEEP_FLAGS"); a.flags = f ? atoi(f) : 2; }
+    // bit 1: skip structurally-zero diagonal tiles (FP64 kernel); bit 2: warp-role cycle accounting (sliced kernels, triage);
+    // bits 3-6: L2 eviction priority of the CTA-pair kernel's TMA loads -- default 8 | 64: the packed L^-1 tiles (read by every CTA pair
+    // of the grid) evict_last, the per-pair panel tiles evict_first: +2.6 % candidates/s at C3 on a power-bound kernel (fewer DRAM
+    // re-reads of L^-1, SM clock 1492 -> 1515 MHz under the same cap; each hint alone, or the opposite pairing, measured no gain:
+    // profiles/r02_l2_hint_ab.log)
+    { const char* f = getenv("BO_B200_SWEEP_FLAGS"); a.flags = f ? atoi(f) : (2 | 8 | 64); }
 
     if (N == 0) {
         if (topk > 0) {

@@ -122,6 +122,17 @@ __device__ __forceinline__ void p8_tma_rows(void* smem_dst, const CUtensorMap* t
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(0u), "r"(y), "r"(bar_cluster) : "memory");
 }
+// the same copy with an L2 eviction-priority hint (A/B runs only: flags bits 3-6, see the producer)
+__device__ __forceinline__ void p8_tma_rows_hint(void* smem_dst, const CUtensorMap* tm, uint32_t y, uint32_t bar_cluster, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(0u), "r"(y), "r"(bar_cluster), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t p8_policy(bool last) {
+    uint64_t pol;
+    if (last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void p8_commit_both(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -353,6 +364,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
         int stage = 0; uint32_t phase = 0;
         uint32_t rb = 0;                          // running row-block-pair counter (accumulator full/empty phases)
         int it = 0;
+        // L2 eviction-priority experiments (BO_B200_SWEEP_FLAGS bits: 8 / 16 = L^-1 tiles evict_last / evict_first, 32 / 64 = panel tiles)
+        const bool hintA = (a.flags & 24) != 0, hintB = (a.flags & 96) != 0;
+        const uint64_t polA = hintA ? p8_policy((a.flags & 8) != 0) : 0, polB = hintB ? p8_policy((a.flags & 32) != 0) : 0;
         for (long long blk = pair; blk < a.nblocks; blk += npairs, ++it) {
             const int p = it & 1;
             const int8_t* panel = panel0 + (size_t)p * panel_bytes;
@@ -385,8 +399,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1) sweep
                             // end): structurally zero -> the all-zero tile parked behind the packed factor
                             const size_t tile = kc < mykc ? tile0 + kc : tile_zero;
                             const uint32_t fb = p8_mapa(&full[stage], 0);
-                            p8_tma_rows(sb, &tmA, (uint32_t)(tile * (S * I8_A_SLICE / 256)), fb);
-                            p8_tma_rows(sb + S * I8_A_SLICE, &tmB, (uint32_t)((panel - b.panel8 + (size_t)kc * B_STAGE) / 256), fb);
+                            if (hintA) p8_tma_rows_hint(sb, &tmA, (uint32_t)(tile * (S * I8_A_SLICE / 256)), fb, polA);
+                            else       p8_tma_rows(sb, &tmA, (uint32_t)(tile * (S * I8_A_SLICE / 256)), fb);
+                            const uint32_t yb = (uint32_t)((panel - b.panel8 + (size_t)kc * B_STAGE) / 256);
+                            if (hintB) p8_tma_rows_hint(sb + S * I8_A_SLICE, &tmB, yb, fb, polB);
+                            else       p8_tma_rows(sb + S * I8_A_SLICE, &tmB, yb, fb);
                             if (++stage == NST) { stage = 0; phase ^= 1; }
                         }
                     }
