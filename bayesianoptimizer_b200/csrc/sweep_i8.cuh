@@ -766,6 +766,9 @@ static int launch_sweep_i8(bo_handle* h, const SweepArgs& a, const SweepI8Args& 
 // Synchronises the stream once (the 4-byte count of flagged candidates decides whether a second pass is needed).
 static int sweep_i8_run(bo_handle* h, const SweepArgs& a_in, int S, double* vals_dev, int64_t* idx_dev, cudaStream_t st) {
     SweepArgs a = a_in;
+    // the L2 eviction hints pin ONE model's L^-1 tiles; an SVGP scan runs T handles' stacked factors side by side (8 x 44 MB at
+    // M = 2048), where "evict last" for all of them measured 2-3 % slower than no hint (profiles/r02_l2_hint_ab.log)
+    if (h->svgp && !getenv("BO_B200_SWEEP_FLAGS")) a.flags &= ~(8 | 16 | 32 | 64);
     a.G = 1; a.seg[0] = 0; a.seg[1] = h->np / SW_BM;
     a.nblocks = (a.N + I8_BN - 1) / I8_BN;
     // CTA pairs (cta_group::2, sweep_i8_pair.cuh) share one 64-candidate block; BO_B200_I8_PAIR=0 keeps the one-CTA kernel (triage / A-B)
